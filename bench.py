@@ -1,0 +1,386 @@
+#!/usr/bin/env python
+"""Benchmark of the block-decode hot path (BASELINE.json metric: 4x4 blocks/s).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload bc1|bc7|bc6h|mixed|bc1_1e8]
+  python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+  python bench.py --impl reference ...      # the reference's own CPU decode on the host cores
+
+A "step" is one pass of the hot path over one batch of synthetic blocks (the whole texture of
+the workload).  Default workload = BASELINE.json configs[1]: BC1 8192x8192 (4 194 304 blocks,
+distribution U) through the LINEAR layout, native pixel format.
+
+One JSON line is printed by rank 0:
+  value      whole-job blocks/s with inputs and outputs resident in HBM, timed on the device
+             (CUDA events on the launching stream, barrier + synchronize on both sides, max over
+             ranks).  Buffers rotate over sets totalling >> L2 so nothing is served from cache.
+  e2e        the same metric through the reference-facing C-ABI call
+             detexDecompressTextureLinear with pinned HOST buffers: host->device copy of the
+             blocks and device->host copy of the pixels inside the timed region, every step.
+  roofline   HBM roofline of the decode kernel: algorithmic bytes per launch (72 B/block for
+             BC1) / average launch duration, against MEASURED_PEAKS.json.
+  cpu_baseline  the reference's CPU decode (oracle/_ref, else the oracle port) on this box's
+             host cores, on the same texture (rank 0, N=1 only).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# workload -> list of (format, width, height, layout, seed, force_modes, bytes_per_block)
+WORKLOADS = {
+    "bc1": dict(name="BC1 8192x8192 synthetic (BASELINE configs[1]), distribution U, LINEAR",
+                parts=[("BC1", 8192, 8192, "linear", 1, 0)]),
+    "bc7": dict(name="BC7/BPTC 16384x16384 synthetic (BASELINE configs[2]), distribution M, LINEAR",
+                parts=[("BPTC", 16384, 16384, "linear", 1, 8)]),
+    "bc7u": dict(name="BC7/BPTC 16384x16384 synthetic, distribution U, LINEAR",
+                 parts=[("BPTC", 16384, 16384, "linear", 1, 0)]),
+    "bc6h": dict(name="BC6H/BPTC_FLOAT 8192x8192 synthetic (BASELINE configs[3]), distribution M, LINEAR",
+                 parts=[("BPTC_FLOAT", 8192, 8192, "linear", 1, 14)]),
+    "mixed": dict(name="ETC2 + EAC_RG11 + RGTC2, 1e8 blocks total over all ranks (BASELINE configs[4]), TILED",
+                  parts=[("ETC2", 0, 0, "tiled", 1, 0), ("EAC_RG11", 0, 0, "tiled", 2, 0), ("RGTC2", 0, 0, "tiled", 3, 0)],
+                  total_blocks=100_000_000, strong=True),
+    "bc1_1e8": dict(name="BC1 1e8 blocks total over all ranks (scaling config), TILED",
+                    parts=[("BC1", 0, 0, "tiled", 1, 0)], total_blocks=100_000_000, strong=True),
+}
+ALGO_BYTES = {"BC1": 72, "BC1A": 72, "ETC1": 72, "ETC2": 72, "ETC2_PUNCHTHROUGH": 72, "BC2": 80, "BC3": 80,
+              "BPTC": 80, "ETC2_EAC": 80, "BPTC_FLOAT": 144, "BPTC_SIGNED_FLOAT": 144, "RGTC1": 24, "RGTC2": 48,
+              "SIGNED_RGTC1": 40, "EAC_R11": 40, "EAC_SIGNED_R11": 40, "SIGNED_RGTC2": 80, "EAC_RG11": 80,
+              "EAC_SIGNED_RG11": 80}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic(kernel_key):
+    """dram bytes per launch from the committed ncu capture, if any (profiles/ncu_traffic.json)."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get(kernel_key)
+        except Exception:
+            return None
+    return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the GPU is under load."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2])); power.append(float(r[3]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        # samples under load: power above the idle floor of this window
+        thr = min(power) + 0.3 * (max(power) - min(power))
+        loaded = [s for s, p in zip(sm, power) if p >= thr] or sm
+        return {"sm_mhz": float(np.median(loaded)), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                "samples": len(sm), "power_w_max": max(power),
+                "window": "warm-up + timed region + ~1 s sustained loop of the same kernel"}
+
+
+def shard(total, rank, world):
+    """Contiguous index range [lo, hi) of rank."""
+    return total * rank // world, total * (rank + 1) // world
+
+
+def run_reference_arm(args, rank, world):
+    """bench.py --impl reference: the reference's own CPU implementation on the host cores."""
+    if rank != 0:
+        return
+    from oracle import harness as H
+    lib, kind = H.best_cpu_decoder()
+    wl = WORKLOADS[args.workload]
+    threads = os.cpu_count() or 1
+    parts = []
+    total_blocks = 0
+    for (fmt, w, h, layout, seed, force) in wl["parts"]:
+        if w == 0:      # flat arrays: bounded sample of 2^22 blocks per format
+            w, h = 8192, 8192 // (2 if H.FORMATS[fmt][1] == 16 else 1)
+        if fmt == "BPTC" and w == 16384:
+            w, h = 8192, 8192       # bounded sample: a quarter of the 16384^2 texture
+        n = (w // 4) * (h // 4)
+        b = H.synth_blocks(fmt, n, seed=seed)
+        if force:
+            b = H.force_modes(fmt, b)
+        parts.append((fmt, b, w, h, layout == "linear"))
+        total_blocks += n
+
+    def step():
+        t = 0.0
+        for (fmt, b, w, h, linear) in parts:
+            _, _, s = H.cpu_decode(lib, fmt, b, w, h, linear=linear, threads=threads)
+            t += s
+        return t
+    for _ in range(args.warmup):
+        step()
+    secs = sum(step() for _ in range(args.steps))
+    value = total_blocks * args.steps / secs
+    sample = "; ".join("%s %dx%d (%d blocks)" % (p[0], p[2], p[3], (p[2] // 4) * (p[3] // 4)) for p in parts)
+    line = {"impl": "reference", "metric": "4x4 blocks/s", "value": value, "unit": "blocks/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": wl["name"], "layout": parts[0][4] and "linear" or "tiled",
+                       "note": "each step decodes the bounded sample named in cpu_baseline.sample"},
+            "cpu_baseline": {"value": value, "unit": "blocks/s", "cores": threads, "kind": kind, "sample": sample},
+            "e2e": {"value": value, "unit": "blocks/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="bc1", choices=sorted(WORKLOADS))
+    ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the host-buffer leg (default min(steps, 10))")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import detex_b200 as D
+    if not torch.cuda.is_available():
+        sys.exit("bench.py: no CUDA device; the decode path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    lib = D.load()
+    wl = WORKLOADS[args.workload]
+    strong = bool(wl.get("strong"))
+    stream = torch.cuda.current_stream()
+    sp = stream.cuda_stream
+
+    # ---- build the device-resident inputs: rotating buffer sets totalling >> L2 (126 MB) ------------
+    parts = []          # per part: dict(fmt, n, w, h, layout, sets=[(blocks, pixels)])
+    step_blocks = 0
+    step_bytes = 0
+    for (fmt, w, h, layout, seed, force) in wl["parts"]:
+        tf = D.FORMATS[fmt]
+        bs, ps = D.block_size(tf), D.pixel_size(tf & 0xFFFF)
+        if w == 0:
+            share = wl["total_blocks"] // len(wl["parts"]) + (1 if wl["parts"].index((fmt, w, h, layout, seed, force)) < wl["total_blocks"] % len(wl["parts"]) else 0)
+            lo, hi = shard(share, rank, world)
+            lo, hi = lo & ~1, hi & ~1       # keep 16-byte units for the generator (8-byte blocks)
+            n, first = hi - lo, lo
+            wib, hib = n, 1
+            w_px, h_px = 4 * n, 4
+        else:
+            wib, hib = w // 4, h // 4
+            n, first = wib * hib, rank * wib * hib        # weak scaling: every rank its own texture
+            w_px, h_px = w, h
+        set_bytes = n * (bs + 16 * ps)
+        n_sets = max(2, min(8, int(np.ceil(600e6 / set_bytes))))
+        sets = []
+        for k in range(n_sets):
+            blocks = torch.empty(n * bs, dtype=torch.uint8, device=dev)
+            D.generate_blocks_device(blocks.data_ptr(), n, bs, seed=seed + 1000 * k, first_block=first, force_modes=force, stream=sp)
+            pixels = torch.empty(n * 16 * ps, dtype=torch.uint8, device=dev)
+            sets.append((blocks, pixels))
+        parts.append(dict(fmt=fmt, tf=tf, n=n, wib=wib, hib=hib, w=w_px, h=h_px, bs=bs, ps=ps, sets=sets, seed=seed,
+                          force=force, first=first, layout=D.LAYOUT_LINEAR if layout == "linear" else D.LAYOUT_TILED))
+        step_blocks += n
+        step_bytes += n * ALGO_BYTES[fmt]
+    flag = torch.zeros(1, dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()
+
+    def one_step(k):
+        for p in parts:
+            blocks, pixels = p["sets"][k % len(p["sets"])]
+            D.decode_device(p["tf"], blocks.data_ptr(), p["w"], p["h"], pixels.data_ptr(), layout=p["layout"],
+                            d_invalid=flag.data_ptr(), stream=sp, wib=p["wib"], hib=p["hib"])
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    for k in range(args.warmup):
+        one_step(k)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    launches0 = D.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for k in range(args.steps):
+        one_step(args.warmup + k)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    launches = D.launch_count() - launches0
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        dist.barrier()
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_max = float(t.item())
+        nb = torch.tensor([step_blocks], dtype=torch.float64, device=dev)
+        dist.all_reduce(nb, op=dist.ReduceOp.SUM)
+        job_blocks = float(nb.item())
+    else:
+        ms_max, job_blocks = ms, float(step_blocks)
+    # sustained loop for the clock sampler (not part of any reported number)
+    if rank == 0:
+        t_end = time.time() + 1.0
+        k = 0
+        while time.time() < t_end:
+            for _ in range(20):
+                one_step(k)
+                k += 1
+            torch.cuda.synchronize()
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- end-to-end leg: reference-facing API, pinned host buffers, copies inside the timed region ----
+    e2e_steps = args.e2e_steps or min(args.steps, 10)
+    e2e = None
+    p0 = parts[0]
+    if len(parts) == 1:
+        host_blocks = torch.empty(p0["n"] * p0["bs"], dtype=torch.uint8).pin_memory()
+        host_blocks.copy_(p0["sets"][0][0])
+        n_out = (p0["w"] * p0["h"] if p0["layout"] == D.LAYOUT_LINEAR else p0["n"] * 16) * p0["ps"]
+        host_pixels = torch.empty(n_out, dtype=torch.uint8).pin_memory()
+        tex = D.DetexTexture(p0["tf"], host_blocks.data_ptr(), p0["w"], p0["h"], p0["wib"], p0["hib"])
+        fn = lib.detexDecompressTextureLinear if p0["layout"] == D.LAYOUT_LINEAR else lib.detexDecompressTextureTiled
+        pf = p0["tf"] & 0xFFFF
+        for _ in range(3):
+            fn(C.byref(tex), host_pixels.data_ptr(), pf)
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            fn(C.byref(tex), host_pixels.data_ptr(), pf)
+        t_e2e = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            t_e2e = float(t.item())
+        e2e = {"value": job_blocks * e2e_steps / t_e2e, "unit": "blocks/s", "steps": e2e_steps,
+               "ms_per_step": 1e3 * t_e2e / e2e_steps, "h2d_bytes_per_step": int(p0["n"] * p0["bs"]),
+               "d2h_bytes_per_step": int(n_out), "api": "detexDecompressTexture%s, pinned host buffers" %
+               ("Linear" if p0["layout"] == D.LAYOUT_LINEAR else "Tiled")}
+        # keep the e2e output for the parity spot-check below
+        e2e_pixels = host_pixels.numpy()
+    else:
+        e2e_pixels = None
+
+    # ---- CPU baseline + parity of the timed configuration (rank 0, N = 1 only) ---------------------------
+    cpu_baseline = None
+    parity = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        from oracle import harness as H
+        cpu_lib, kind = H.best_cpu_decoder()
+        threads = os.cpu_count() or 1
+        fmt = p0["fmt"]
+        n_s, w_s, h_s = p0["n"], p0["w"], p0["h"]
+        linear = p0["layout"] == D.LAYOUT_LINEAR
+        if not linear:      # flat arrays: bounded sample of the first 2^22 blocks as a 2048-block-wide texture
+            n_s = min(p0["n"], 1 << 22)
+            n_s -= n_s % 2048
+            w_s, h_s = 8192, n_s // 2048 * 4
+        elif fmt == "BPTC" and p0["w"] == 16384:
+            n_s, w_s, h_s = p0["n"] // 4, 16384, 4096      # bounded sample: top quarter of the texture
+        hb = p0["sets"][0][0][: n_s * p0["bs"]].cpu().numpy()
+        best = None
+        want = None
+        for _ in range(3):
+            want, ok, s = H.cpu_decode(cpu_lib, fmt, hb, w_s, h_s, linear=linear, threads=threads)
+            best = s if best is None else min(best, s)
+        _, _, s1 = H.cpu_decode(cpu_lib, fmt, hb[: (n_s // 16) * p0["bs"]], w_s, h_s // 16, linear=linear, threads=1)
+        cpu_baseline = {"value": n_s / best, "unit": "blocks/s", "cores": threads, "kind": kind,
+                        "sample": "%s %dx%d, %d blocks, best of 3" % (fmt, w_s, h_s, n_s),
+                        "single_thread_value": (n_s // 16) / s1}
+        got = p0["sets"][0][1][: want.size].cpu().numpy()
+        parity = {"checked_blocks": int(n_s), "against": kind, "device_path_bit_exact": bool(np.array_equal(got, want))}
+        if e2e_pixels is not None:
+            parity["e2e_path_bit_exact"] = bool(np.array_equal(e2e_pixels[: want.size], want))
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        secs = ms_max / 1e3
+        value = job_blocks * args.steps / secs
+        # roofline of the dominant kernel: per-rank bytes per launch over the average launch time
+        dom = max(parts, key=lambda p: p["n"] * ALGO_BYTES[p["fmt"]])
+        per_launch_ms = ms_max / args.steps * (dom["n"] * ALGO_BYTES[dom["fmt"]]) / step_bytes
+        achieved = dom["n"] * ALGO_BYTES[dom["fmt"]] / (per_launch_ms / 1e3) / 1e9
+        kname = "decode_%s_kernel<%s>" % ("linear" if dom["layout"] == D.LAYOUT_LINEAR else "tiled", dom["fmt"])
+        line = {
+            "metric": "4x4 blocks/s", "value": value, "unit": "blocks/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
+            "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": wl["name"], "blocks_per_step_per_gpu": int(step_blocks),
+                       "pixel_format": "native", "sharding": "index range per rank, no data-path collective",
+                       "cache": "rotating buffer sets, %d x %.0f MB per rank (>> 126 MB L2)" %
+                       (len(p0["sets"]), sum(p["n"] * (p["bs"] + 16 * p["ps"]) for p in parts) / 1e6)},
+            "roofline": {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "peak_source": peak_src,
+                         "algorithmic_bytes_per_block": ALGO_BYTES[dom["fmt"]],
+                         "traffic": ncu_traffic(kname)},
+            "e2e": e2e, "cpu_baseline": cpu_baseline, "gpu_launches": int(launches), "clocks": clocks,
+            "parity": parity, "hbm_gbs_all_parts": step_bytes * args.steps / secs / 1e9,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,250 @@
+// BPTC (BC7) block decoder.  Behaviour follows reference decompress-bptc.c:23-512
+// (mode layout comment :23-42, per-mode constants :45-71,134,195-221,265-267).
+//
+// Design notes (B200-native, not the reference's byte-array loops):
+//   * every mode is a template instantiation: all field positions are compile-time
+//     constants, so extraction is a funnel shift + mask per field;
+//   * endpoints are kept as two registers per endpoint with 16-bit lanes
+//     (R | B<<16 and G | A<<16) and interpolation is one IMAD per register:
+//     T = (64*E0 + 32) + w*(E1 - E0), evaluated on the packed word.  Each lane's true
+//     value lies in [32, 16352], so the packed integer identity holds without
+//     cross-lane borrows even though (E1 - E0) is negative in some lanes;
+//   * the "anchor" pixels that carry one index bit less are handled once per block
+//     by inserting a zero bit into the 64-bit index stream (S += S & ~low(q) shifts
+//     everything from bit q upwards left by one), after which every pixel's index sits
+//     at the compile-time position i*IB;
+//   * partition sets come from bit-packed shared-memory tables (bptc_tables.cuh).
+#pragma once
+#include <type_traits>
+#include "common.cuh"
+#include "bptc_tables.cuh"
+
+namespace detexb200 {
+
+// Shared-memory copy of the packed partition tables (768 bytes).
+struct BptcTables {
+	uint32_t two[64];
+	uint2 three[64];
+};
+
+__device__ __forceinline__ void bptc_tables_load(BptcTables &t) {
+	for (int i = threadIdx.x; i < 64; i += blockDim.x) {
+		t.two[i] = bptc_two_global[i];
+		t.three[i] = bptc_three_global[i];
+	}
+}
+
+template <int I, int N, class F>
+__device__ __forceinline__ void static_for(F &&f) {
+	if constexpr (I < N) {
+		f(std::integral_constant<int, I>{});
+		static_for<I + 1, N>(f);
+	}
+}
+
+// Insert a zero bit at position q of a 64-bit stream (bits >= q move up by one).
+__device__ __forceinline__ uint64_t insert_zero_bit(uint64_t s, uint32_t q) {
+	return s + (s & ~((1ull << q) - 1ull));
+}
+
+// Interpolation weights aWeight2/3/4 (bptc-tables.c:192-201) in closed form:
+// {0,21,43,64} = 21i + (i>>1); {0,9,18,27,37,46,55,64} = 9i + (i>>2);
+// {0,4,9,13,...,60,64} = (273i + 32) >> 6.
+template <int BITS>
+__device__ __forceinline__ uint32_t bptc_weight(uint32_t i) {
+	if constexpr (BITS == 2)
+		return i * 21u + (i >> 1);
+	else if constexpr (BITS == 3)
+		return i * 9u + (i >> 2);
+	else
+		return (i * 273u + 32u) >> 6;
+}
+
+struct Bc7ModeInfo {
+	int ns, pb, rb, isb, cb, ab, epb, spb, ib, ib2;
+};
+__host__ __device__ constexpr Bc7ModeInfo bc7_mode_info(int m) {
+	constexpr Bc7ModeInfo t[8] = {
+		/*    NS PB RB ISB CB AB EPB SPB IB IB2 */
+		{ 3, 4, 0, 0, 4, 0, 1, 0, 3, 0 },
+		{ 2, 6, 0, 0, 6, 0, 0, 1, 3, 0 },
+		{ 3, 6, 0, 0, 5, 0, 0, 0, 2, 0 },
+		{ 2, 6, 0, 0, 7, 0, 1, 0, 2, 0 },
+		{ 1, 0, 2, 1, 5, 6, 0, 0, 2, 3 },
+		{ 1, 0, 2, 0, 7, 8, 0, 0, 2, 2 },
+		{ 1, 0, 0, 0, 7, 7, 1, 0, 4, 0 },
+		{ 2, 6, 0, 0, 5, 5, 1, 0, 2, 0 },
+	};
+	return t[m];
+}
+
+// Widen an N-bit value to 8 bits (left-align, replicate MSBs; decompress-bptc.c:160-175).
+template <int N>
+__device__ __forceinline__ uint32_t widen8(uint32_t v) {
+	if constexpr (N >= 8)
+		return v;
+	else
+		return ((v << (8 - N)) | (v >> (2 * N - 8))) & 0xFFu;
+}
+
+template <int M>
+__device__ __forceinline__ void bc7_decode_mode(const uint4 &w, const BptcTables &tab, uint32_t (&px)[16]) {
+	constexpr Bc7ModeInfo I = bc7_mode_info(M);
+	constexpr int NS = I.ns, NE = 2 * I.ns, CB = I.cb, AB = I.ab, IB = I.ib, IB2 = I.ib2;
+	constexpr int P_PART = M + 1;
+	constexpr int P_ROT = P_PART + I.pb;
+	constexpr int P_ISB = P_ROT + I.rb;
+	constexpr int P_COL = P_ISB + I.isb;
+	constexpr int P_ALPHA = P_COL + 3 * NE * CB;
+	constexpr int P_PBIT = P_ALPHA + NE * AB;
+	constexpr int P_IDX = P_PBIT + (I.epb ? NE : (I.spb ? NS : 0));
+	constexpr int P_IDX2 = P_IDX + 16 * IB - NS;
+	static_assert(IB2 == 0 || NS == 1, "dual index sets only occur in single-subset modes");
+	static_assert(P_IDX2 + (IB2 ? 16 * IB2 - 1 : 0) == 128, "mode layout must fill the block");
+
+	const uint32_t partition = field128<P_PART, I.pb>(w);
+	const uint32_t rotation = field128<P_ROT, I.rb>(w);
+	const uint32_t isb = field128<P_ISB, I.isb>(w);
+
+	// ---- endpoints: component-major fields (decompress-bptc.c:82-87) -> packed lanes
+	constexpr int CP = CB + ((I.epb || I.spb) ? 1 : 0);	// precision incl. p-bit
+	uint32_t e_rb[NE], e_ga[NE];
+	static_for<0, NE>([&](auto e_) {
+		constexpr int e = decltype(e_)::value;
+		constexpr Bc7ModeInfo J = bc7_mode_info(M);	// (constexpr locals of the enclosing scope are not usable here)
+		uint32_t r = field128<P_COL + (0 * NE + e) * CB, CB>(w);
+		uint32_t g = field128<P_COL + (1 * NE + e) * CB, CB>(w);
+		uint32_t b = field128<P_COL + (2 * NE + e) * CB, CB>(w);
+		uint32_t a = field128<P_ALPHA + e * AB, AB>(w);
+		if constexpr (J.epb != 0) {
+			// Q6: mode 6 keeps its two p-bits at stream bits 63 and 64 but the
+			// reference reads both from data0 >> 63, so the second is always 0
+			// (decompress-bptc.c:142-158).
+			const uint32_t p = (M == 6 && e == 1) ? 0u : field128<P_PBIT + e, 1>(w);
+			r = (r << 1) | p;	g = (g << 1) | p;	b = (b << 1) | p;	a = (a << 1) | p;
+		}
+		else if constexpr (J.spb != 0) {	// mode 1: one p-bit per subset, colour only (:297-306)
+			const uint32_t p = field128<P_PBIT + e / 2, 1>(w);
+			r = (r << 1) | p;	g = (g << 1) | p;	b = (b << 1) | p;
+		}
+		r = widen8<CP>(r);
+		g = widen8<CP>(g);
+		b = widen8<CP>(b);
+		if constexpr (J.ab > 0)
+			a = widen8<J.ab + (J.epb ? 1 : 0)>(a);
+		else
+			a = 0xFFu;					// modes 0-3: alpha 255 (:176-179)
+		e_rb[e] = r | (b << 16);
+		e_ga[e] = g | (a << 16);
+	});
+	// Per subset: A = 64*E0 + 32 (per lane), K = E1 - E0 (packed integer difference).
+	uint32_t a_rb[NS], k_rb[NS], a_ga[NS], k_ga[NS];
+#pragma unroll
+	for (int s = 0; s < NS; s++) {
+		a_rb[s] = e_rb[2 * s] * 64u + 0x00200020u;
+		k_rb[s] = e_rb[2 * s + 1] - e_rb[2 * s];
+		a_ga[s] = e_ga[2 * s] * 64u + 0x00200020u;
+		k_ga[s] = e_ga[2 * s + 1] - e_ga[2 * s];
+	}
+
+	// ---- partition / anchors
+	uint32_t subset_bits = 0u, anchor_b = 0u, anchor_c = 0u;
+	if constexpr (NS == 2) {
+		const uint32_t t = tab.two[partition];
+		subset_bits = t & 0xFFFFu;
+		anchor_b = t >> 16;
+	}
+	else if constexpr (NS == 3) {
+		const uint2 t = tab.three[partition];
+		subset_bits = t.x;
+		anchor_b = t.y & 0xFu;
+		anchor_c = t.y >> 8;
+	}
+
+	// ---- index streams, anchors expanded to full width (decompress-bptc.c:409-420)
+	const uint2 s1w = window64<P_IDX>(w);
+	uint64_t s1 = ((uint64_t)s1w.y << 32) | s1w.x;
+	s1 = insert_zero_bit(s1, IB - 1);
+	if constexpr (NS == 2)
+		s1 = insert_zero_bit(s1, anchor_b * IB + (IB - 1));
+	else if constexpr (NS == 3) {
+		const uint32_t qa = min(anchor_b, anchor_c) * IB + (IB - 1);
+		const uint32_t qb = max(anchor_b, anchor_c) * IB + (IB - 1);
+		s1 = insert_zero_bit(insert_zero_bit(s1, qa), qb);
+	}
+	uint64_t s2 = 0;
+	if constexpr (IB2 > 0) {
+		const uint2 s2w = window64<P_IDX2>(w);
+		s2 = insert_zero_bit(((uint64_t)s2w.y << 32) | s2w.x, IB2 - 1);
+	}
+	// Rotation: swap A with R / G / B after interpolation (:497-508).
+	uint32_t rot_sel = 0x3210u;
+	if constexpr (I.rb > 0)
+		rot_sel = rotation == 0u ? 0x3210u : (rotation == 1u ? 0x0213u : (rotation == 2u ? 0x1230u : 0x2310u));
+
+#pragma unroll
+	for (int i = 0; i < 16; i++) {
+		// endpoints of this pixel's subset
+		uint32_t arb = a_rb[0], krb = k_rb[0], aga = a_ga[0], kga = k_ga[0];
+		if constexpr (NS == 2) {
+			if ((subset_bits >> i) & 1u) {
+				arb = a_rb[1];	krb = k_rb[1];	aga = a_ga[1];	kga = k_ga[1];
+			}
+		}
+		else if constexpr (NS == 3) {
+			const uint32_t s = (subset_bits >> (2 * i)) & 3u;
+			if (s == 1u) {
+				arb = a_rb[1];	krb = k_rb[1];	aga = a_ga[1];	kga = k_ga[1];
+			}
+			if (s == 2u) {
+				arb = a_rb[NS - 1];	krb = k_rb[NS - 1];	aga = a_ga[NS - 1];	kga = k_ga[NS - 1];
+			}
+		}
+		const uint32_t i1 = (uint32_t)(s1 >> (i * IB)) & ((1u << IB) - 1u);
+		uint32_t t_rb, t_ga;
+		if constexpr (IB2 == 0) {
+			const uint32_t wgt = bptc_weight<IB>(i1);
+			t_rb = arb + wgt * krb;
+			t_ga = aga + wgt * kga;
+		}
+		else {
+			// Two index sets: colour and alpha weights may differ; in mode 4 the index
+			// selection bit swaps which set drives which (:380-385, :422-480).
+			const uint32_t i2 = (uint32_t)(s2 >> (i * IB2)) & ((1u << IB2) - 1u);
+			const uint32_t w1 = bptc_weight<IB>(i1), w2 = bptc_weight<IB2>(i2);
+			const uint32_t wc = isb ? w2 : w1, wa = isb ? w1 : w2;
+			t_rb = arb + wc * krb;
+			// split K_ga into its green lane (sign-extended) and its alpha lane
+			const uint32_t kg = (uint32_t)(int)(int16_t)(kga & 0xFFFFu);
+			const uint32_t ka = kga - kg;
+			t_ga = aga + wc * kg + wa * ka;
+		}
+		uint32_t p = ((t_rb >> 6) & 0x00FF00FFu) | ((t_ga << 2) & 0xFF00FF00u);
+		if constexpr (I.rb > 0)
+			p = prmt(p, 0u, rot_sel);
+		px[i] = p;
+	}
+}
+
+// BPTC -> RGBA8.  decompress-bptc.c:354-512.
+__device__ __forceinline__ bool decode_bptc(const uint4 blk, uint32_t mode_mask, uint32_t flags,
+const BptcTables &tab, uint32_t (&px)[16]) {
+	const int mode = __ffs((int)(blk.x & 0xFFu)) - 1;	// lowest set bit of byte 0; -1 -> invalid (Q7)
+	switch (mode) {
+	case 0: bc7_decode_mode<0>(blk, tab, px); break;
+	case 1: bc7_decode_mode<1>(blk, tab, px); break;
+	case 2: bc7_decode_mode<2>(blk, tab, px); break;
+	case 3: bc7_decode_mode<3>(blk, tab, px); break;
+	case 4: bc7_decode_mode<4>(blk, tab, px); break;
+	case 5: bc7_decode_mode<5>(blk, tab, px); break;
+	case 6: bc7_decode_mode<6>(blk, tab, px); break;
+	case 7: bc7_decode_mode<7>(blk, tab, px); break;
+	default: return false;
+	}
+	bool ok = (mode_mask >> mode) & 1u;					// :364
+	ok = ok && !(mode >= 4 && (flags & FLAG_OPAQUE_ONLY));			// :366-369
+	ok = ok && !(mode < 4 && (flags & FLAG_NON_OPAQUE_ONLY));
+	return ok;
+}
+
+}  // namespace detexb200

@@ -1,0 +1,268 @@
+// BPTC_FLOAT / BPTC_SIGNED_FLOAT (BC6H) block decoder.  Behaviour follows reference
+// decompress-bptc-float.c:23-644.  The output is the half-float BIT PATTERN built
+// with integer arithmetic only (no floating point anywhere), so the result is
+// bit-exact, not merely within 1 ULP.
+//
+// Design: the 14 irregular per-mode bit scatters are generated at compile time from
+// the layout strings of the format specification (constexpr parser below; the
+// reference spells the same layouts out as 14 hand-written switch cases,
+// decompress-bptc-float.c:128-485).  Only that scatter is mode-specific; delta
+// decoding, unquantisation, index expansion and interpolation are shared code with
+// the mode's constants passed as values, so a warp with mixed modes re-converges
+// after ~1/4 of the work.
+#pragma once
+#include "common.cuh"
+#include "decode_bptc.cuh"
+
+namespace detexb200 {
+
+// ---- compile-time layout description ------------------------------------------------
+// "x[a:b]": component bit b sits at the lowest stream position, walking towards a;
+// a < b therefore denotes a bit-reversed field (modes 12 and 13).  m = mode bits,
+// d = partition.  r/g/b + endpoint number 0..3.
+struct Bc6hPiece {
+	int comp;	// 0 r, 1 g, 2 b, 3 partition, 4 mode (skipped)
+	int ep;		// endpoint 0..3
+	int lo;		// lowest component bit written
+	int len;
+	int reversed;	// 1: ascending stream position = descending component bit
+	int pos;	// stream position of the field
+};
+struct Bc6hLayout {
+	Bc6hPiece piece[28];
+	int n;
+	int end;	// stream position after the last field (= start of the indices)
+};
+
+__host__ __device__ constexpr int parse_int(const char *s, int &i) {
+	int v = 0;
+	while (s[i] >= '0' && s[i] <= '9')
+		v = v * 10 + (s[i++] - '0');
+	return v;
+}
+
+__host__ __device__ constexpr Bc6hLayout bc6h_parse_layout(const char *s) {
+	Bc6hLayout L{};
+	int i = 0, pos = 0;
+	while (s[i]) {
+		if (s[i] == ' ') {
+			i++;
+			continue;
+		}
+		Bc6hPiece p{};
+		const char c = s[i++];
+		p.comp = c == 'r' ? 0 : (c == 'g' ? 1 : (c == 'b' ? 2 : (c == 'd' ? 3 : 4)));
+		if (p.comp <= 2)
+			p.ep = s[i++] - '0';
+		i++;				// '['
+		const int a = parse_int(s, i);
+		int b = a;
+		if (s[i] == ':') {
+			i++;
+			b = parse_int(s, i);
+		}
+		i++;				// ']'
+		p.reversed = a < b ? 1 : 0;
+		p.lo = a < b ? a : b;
+		p.len = (a < b ? b - a : a - b) + 1;
+		p.pos = pos;
+		pos += p.len;
+		L.piece[L.n++] = p;
+	}
+	L.end = pos;
+	return L;
+}
+
+__host__ __device__ constexpr const char *bc6h_layout_string(int mode) {
+	switch (mode) {
+	case 0: return "m[1:0] g2[4] b2[4] b3[4] r0[9:0] g0[9:0] b0[9:0] r1[4:0] g3[4] g2[3:0] g1[4:0] b3[0] g3[3:0] b1[4:0] b3[1] b2[3:0] r2[4:0] b3[2] r3[4:0] b3[3] d[4:0]";
+	case 1: return "m[1:0] g2[5] g3[4] g3[5] r0[6:0] b3[0] b3[1] b2[4] g0[6:0] b2[5] b3[2] g2[4] b0[6:0] b3[3] b3[5] b3[4] r1[5:0] g2[3:0] g1[5:0] g3[3:0] b1[5:0] b2[3:0] r2[5:0] r3[5:0] d[4:0]";
+	case 2: return "m[4:0] r0[9:0] g0[9:0] b0[9:0] r1[4:0] r0[10] g2[3:0] g1[3:0] g0[10] b3[0] g3[3:0] b1[3:0] b0[10] b3[1] b2[3:0] r2[4:0] b3[2] r3[4:0] b3[3] d[4:0]";
+	case 3: return "m[4:0] r0[9:0] g0[9:0] b0[9:0] r1[3:0] r0[10] g3[4] g2[3:0] g1[4:0] g0[10] g3[3:0] b1[3:0] b0[10] b3[1] b2[3:0] r2[3:0] b3[0] b3[2] r3[3:0] g2[4] b3[3] d[4:0]";
+	case 4: return "m[4:0] r0[9:0] g0[9:0] b0[9:0] r1[3:0] r0[10] b2[4] g2[3:0] g1[3:0] g0[10] b3[0] g3[3:0] b1[4:0] b0[10] b2[3:0] r2[3:0] b3[1] b3[2] r3[3:0] b3[4] b3[3] d[4:0]";
+	case 5: return "m[4:0] r0[8:0] b2[4] g0[8:0] g2[4] b0[8:0] b3[4] r1[4:0] g3[4] g2[3:0] g1[4:0] b3[0] g3[3:0] b1[4:0] b3[1] b2[3:0] r2[4:0] b3[2] r3[4:0] b3[3] d[4:0]";
+	case 6: return "m[4:0] r0[7:0] g3[4] b2[4] g0[7:0] b3[2] g2[4] b0[7:0] b3[3] b3[4] r1[5:0] g2[3:0] g1[4:0] b3[0] g3[3:0] b1[4:0] b3[1] b2[3:0] r2[5:0] r3[5:0] d[4:0]";
+	case 7: return "m[4:0] r0[7:0] b3[0] b2[4] g0[7:0] g2[5] g2[4] b0[7:0] g3[5] b3[4] r1[4:0] g3[4] g2[3:0] g1[5:0] g3[3:0] b1[4:0] b3[1] b2[3:0] r2[4:0] b3[2] r3[4:0] b3[3] d[4:0]";
+	case 8: return "m[4:0] r0[7:0] b3[1] b2[4] g0[7:0] b2[5] g2[4] b0[7:0] b3[5] b3[4] r1[4:0] g3[4] g2[3:0] g1[4:0] b3[0] g3[3:0] b1[5:0] b2[3:0] r2[4:0] b3[2] r3[4:0] b3[3] d[4:0]";
+	case 9: return "m[4:0] r0[5:0] g3[4] b3[0] b3[1] b2[4] g0[5:0] g2[5] b2[5] b3[2] g2[4] b0[5:0] g3[5] b3[3] b3[5] b3[4] r1[5:0] g2[3:0] g1[5:0] g3[3:0] b1[5:0] b2[3:0] r2[5:0] r3[5:0] d[4:0]";
+	case 10: return "m[4:0] r0[9:0] g0[9:0] b0[9:0] r1[9:0] g1[9:0] b1[9:0]";
+	case 11: return "m[4:0] r0[9:0] g0[9:0] b0[9:0] r1[8:0] r0[10] g1[8:0] g0[10] b1[8:0] b0[10]";
+	case 12: return "m[4:0] r0[9:0] g0[9:0] b0[9:0] r1[7:0] r0[10:11] g1[7:0] g0[10:11] b1[7:0] b0[10:11]";
+	default: return "m[4:0] r0[9:0] g0[9:0] b0[9:0] r1[3:0] r0[10:15] g1[3:0] g0[10:15] b1[3:0] b0[10:15]";
+	}
+}
+
+// Endpoint precision and per-component delta widths by detex mode number
+// (decompress-bptc-float.c:42-43 and the tail of each switch case); modes 9 and 10
+// store all endpoints directly (delta width 0 here).
+struct Bc6hModeInfo {
+	int epb, dr, dg, db;
+};
+__host__ __device__ constexpr Bc6hModeInfo bc6h_mode_info(int m) {
+	constexpr Bc6hModeInfo t[14] = {
+		{ 10, 5, 5, 5 }, { 7, 6, 6, 6 }, { 11, 5, 4, 4 }, { 11, 4, 5, 4 }, { 11, 4, 4, 5 },
+		{ 9, 5, 5, 5 }, { 8, 6, 5, 5 }, { 8, 5, 6, 5 }, { 8, 5, 5, 6 }, { 6, 0, 0, 0 },
+		{ 10, 0, 0, 0 }, { 11, 9, 9, 9 }, { 12, 8, 8, 8 }, { 16, 4, 4, 4 },
+	};
+	return t[m];
+}
+
+// Raw endpoint fields of one block: ep[e][c], c = r, g, b.
+struct Bc6hRaw {
+	uint32_t ep[4][3];
+	uint32_t partition;
+};
+
+template <int M>
+__device__ __forceinline__ void bc6h_scatter(const uint4 &w, Bc6hRaw &raw) {
+	constexpr Bc6hLayout L = bc6h_parse_layout(bc6h_layout_string(M));
+	static_assert(L.end == (M >= 10 ? 65 : 82), "layout must end where the indices start");
+#pragma unroll
+	for (int e = 0; e < 4; e++)
+#pragma unroll
+		for (int c = 0; c < 3; c++)
+			raw.ep[e][c] = 0u;
+	raw.partition = 0u;
+	static_for<0, L.n>([&](auto k_) {
+		constexpr int k = decltype(k_)::value;
+		constexpr Bc6hPiece P = L.piece[k];
+		if constexpr (P.comp != 4) {
+			uint32_t v = field128<P.pos, P.len>(w);
+			if constexpr (P.reversed)
+				v = __brev(v) >> (32 - P.len);
+			// Q9: mode 12 reads b0[11] (stream bit 63) through detexGetBits64(data0, 63, 63),
+			// whose mask is the undefined 1<<64 (bits.h:31); the reference build (gcc 13.3,
+			// -Ofast) yields 0 for it (decompress-bptc-float.c:462).
+			if constexpr (M == 12 && P.comp == 2 && P.ep == 0 && P.reversed)
+				v &= 1u;		// keep b0[10], drop b0[11]
+			if constexpr (P.comp == 3)
+				raw.partition |= v << P.lo;
+			else
+				raw.ep[P.ep][P.comp] |= v << P.lo;
+		}
+	});
+}
+
+__device__ __forceinline__ int sext_runtime(uint32_t v, int bits) {
+	return ((int)(v << (32 - bits))) >> (32 - bits);
+}
+
+// Shared tail: delta decode, unquantise, expand indices, interpolate, emit.
+// NS = 2 for detex modes 0-9 (3-bit indices from stream bit 82), 1 for modes 10-13
+// (4-bit indices from bit 65).
+template <bool SIGNED, int NS>
+__device__ __forceinline__ void bc6h_finish(const uint4 &w, const Bc6hRaw &raw, int epb, int dr, int dg, int db,
+const BptcTables &tab, uint32_t (&px)[32]) {
+	constexpr int NE = 2 * NS, IB = NS == 1 ? 4 : 3;
+	const uint32_t epmask = epb >= 32 ? 0xFFFFFFFFu : ((1u << epb) - 1u);
+	const int delta_bits[3] = { dr, dg, db };
+	int a_c[NS][3], k_c[NS][3];		// A = 64*e0 + 32, K = e1 - e0 per subset and component
+#pragma unroll
+	for (int c = 0; c < 3; c++) {
+		int e[NE];
+		e[0] = SIGNED ? sext_runtime(raw.ep[0][c], epb) : (int)raw.ep[0][c];	// :491-495
+#pragma unroll
+		for (int k = 1; k < NE; k++) {
+			uint32_t v = raw.ep[k][c];
+			if (delta_bits[c] != 0)		// transformed endpoints (:496-511)
+				v = ((uint32_t)e[0] + (uint32_t)sext_runtime(v, delta_bits[c])) & epmask;
+			e[k] = SIGNED ? sext_runtime(v, epb) : (int)v;
+		}
+#pragma unroll
+		for (int k = 0; k < NE; k++) {
+			int x = e[k], unq;
+			if (SIGNED) {			// UnquantizeSigned, :64-86
+				const bool neg = x < 0;
+				const int ax = neg ? -x : x;
+				if (epb >= 16)
+					unq = x;
+				else {
+					unq = ((ax << 15) + 0x4000) >> (epb - 1);
+					if (ax == 0)
+						unq = 0;
+					if (ax >= (1 << (epb - 1)) - 1)
+						unq = 0x7FFF;
+					if (neg)
+						unq = -unq;
+				}
+			}
+			else {				// Unquantize, :52-62 (mode 13 <=> epb 16)
+				unq = ((x << 15) + 0x4000) >> (epb - 1);
+				if (x == 0)
+					unq = 0;
+				if ((uint32_t)x == epmask)
+					unq = 0xFFFF;
+				if (epb >= 16)
+					unq = x;
+			}
+			e[k] = unq;
+		}
+#pragma unroll
+		for (int s = 0; s < NS; s++) {
+			a_c[s][c] = 64 * e[2 * s] + 32;
+			k_c[s][c] = e[2 * s + 1] - e[2 * s];
+		}
+	}
+	// Index stream with the anchor pixels widened to IB bits (:544-564).
+	const uint2 sw = window64<NS == 1 ? 65 : 82>(w);
+	uint64_t s = insert_zero_bit(((uint64_t)sw.y << 32) | sw.x, IB - 1);
+	uint32_t subset_bits = 0u;
+	if constexpr (NS == 2) {
+		const uint32_t t = tab.two[raw.partition];
+		subset_bits = t & 0xFFFFu;
+		s = insert_zero_bit(s, (t >> 16) * IB + (IB - 1));
+	}
+#pragma unroll
+	for (int i = 0; i < 16; i++) {
+		const bool second = NS == 2 && ((subset_bits >> i) & 1u);
+		const int wgt = (int)bptc_weight<IB>((uint32_t)(s >> (i * IB)) & ((1u << IB) - 1u));
+		uint32_t h[3];
+#pragma unroll
+		for (int c = 0; c < 3; c++) {
+			const int a = second ? a_c[NS - 1][c] : a_c[0][c], k = second ? k_c[NS - 1][c] : k_c[0][c];
+			const int v = (a + wgt * k) >> 6;		// InterpolateFloat, :97-108 (Q18)
+			if (SIGNED) {					// :577-613
+				const int mag = ((v < 0 ? -v : v) * 31) >> 5;
+				h[c] = (uint32_t)mag | ((v < 0 && mag != 0) ? 0x8000u : 0u);
+			}
+			else
+				h[c] = (uint32_t)((v * 31) >> 6);	// :616-621 (v >= 0)
+		}
+		px[2 * i] = (h[0] & 0xFFFFu) | (h[1] << 16);		// Q10: R | G<<16 | B<<32, X = 0
+		px[2 * i + 1] = h[2] & 0xFFFFu;
+	}
+}
+
+// 5-bit mode code -> detex mode number, -1 for the reserved codes (Q8,
+// decompress-bptc-float.c:23-33).
+__device__ __forceinline__ int bc6h_mode(uint32_t w0) {
+	if ((w0 & 2u) == 0u)
+		return (int)(w0 & 1u);
+	// codes with bit 1 set: 2,6,10,14,18,22,26,30 -> 2..9; 3,7,11,15 -> 10..13
+	const uint32_t code = w0 & 0x1Fu;
+	if ((code & 1u) == 0u)
+		return 2 + (int)(code >> 2);
+	return code < 16u ? 10 + (int)(code >> 2) : -1;
+}
+
+template <bool SIGNED>
+__device__ __forceinline__ bool decode_bptc_float(const uint4 blk, uint32_t mode_mask, uint32_t,
+const BptcTables &tab, uint32_t (&px)[32]) {
+	const int mode = bc6h_mode(blk.x);
+	Bc6hRaw raw;
+	Bc6hModeInfo info = bc6h_mode_info(0);
+	switch (mode) {
+#define BC6H_CASE(M) case M: bc6h_scatter<M>(blk, raw); info = bc6h_mode_info(M); break;
+	BC6H_CASE(0) BC6H_CASE(1) BC6H_CASE(2) BC6H_CASE(3) BC6H_CASE(4) BC6H_CASE(5) BC6H_CASE(6)
+	BC6H_CASE(7) BC6H_CASE(8) BC6H_CASE(9) BC6H_CASE(10) BC6H_CASE(11) BC6H_CASE(12) BC6H_CASE(13)
+#undef BC6H_CASE
+	default: return false;
+	}
+	if (mode >= 10)
+		bc6h_finish<SIGNED, 1>(blk, raw, info.epb, info.dr, info.dg, info.db, tab, px);
+	else
+		bc6h_finish<SIGNED, 2>(blk, raw, info.epb, info.dr, info.dg, info.db, tab, px);
+	return (mode_mask >> mode) & 1u;		// :121
+}
+
+}  // namespace detexb200

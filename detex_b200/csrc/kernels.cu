@@ -1,0 +1,331 @@
+// Texture-level decode kernels for sm_100a and their host-side launcher.
+//
+// Replaces the two loops of reference texture.c: detexDecompressTextureTiled
+// (:77-98) and detexDecompressTextureLinear (:105-145).  The work is a pure map over
+// independent 8/16-byte blocks and is bound by HBM traffic (in + out bytes per block,
+// DESIGN.md), so the kernels are organised around the memory system:
+//   * one block per lane, fetched with one 64/128-bit non-coherent streaming load,
+//     32 lanes reading 256/512 contiguous bytes;
+//   * all 16 pixels of the block are produced in registers;
+//   * LINEAR layout: lane L of a warp owns block column bx0+L, so for every pixel row
+//     the warp's 32 row segments form one contiguous span of the image row and go out
+//     as full-width vector stores;
+//   * TILED layout: a block's pixels are contiguous (16*ps bytes), so a direct store
+//     would make every lane write 16 bytes at a 16*ps stride (half-empty sectors).
+//     Instead each warp transposes its 32 tiles through an XOR-swizzled,
+//     bank-conflict-free shared-memory buffer and writes 512 contiguous bytes per
+//     store instruction;
+//   * invalid blocks become zero pixels and raise one flag word per CTA (Q16).
+#include <cstdio>
+#include <atomic>
+
+#include "common.cuh"
+#include "decode_s3tc.cuh"
+#include "decode_etc.cuh"
+#include "decode_bptc.cuh"
+#include "decode_bptc_float.cuh"
+#include "launch.h"
+
+namespace detexb200 {
+
+// ---- per-format traits ---------------------------------------------------------------
+template <int F> struct FormatTraits;
+#define DETEX_TRAITS(F, BW, OW, TAB) \
+	template <> struct FormatTraits<F> { \
+		static constexpr int BLOCK_WORDS = BW;	/* compressed block size in 32-bit words */ \
+		static constexpr int OUT_WORDS = OW;	/* decoded tile size in 32-bit words */ \
+		static constexpr bool USES_TABLES = TAB; \
+	};
+DETEX_TRAITS(F_BC1, 2, 16, false)		DETEX_TRAITS(F_BC1A, 2, 16, false)
+DETEX_TRAITS(F_BC2, 4, 16, false)		DETEX_TRAITS(F_BC3, 4, 16, false)
+DETEX_TRAITS(F_RGTC1, 2, 4, false)		DETEX_TRAITS(F_SIGNED_RGTC1, 2, 8, false)
+DETEX_TRAITS(F_RGTC2, 4, 8, false)		DETEX_TRAITS(F_SIGNED_RGTC2, 4, 16, false)
+DETEX_TRAITS(F_BPTC_FLOAT, 4, 32, true)		DETEX_TRAITS(F_BPTC_SIGNED_FLOAT, 4, 32, true)
+DETEX_TRAITS(F_BPTC, 4, 16, true)		DETEX_TRAITS(F_ETC1, 2, 16, false)
+DETEX_TRAITS(F_ETC2, 2, 16, false)		DETEX_TRAITS(F_ETC2_PUNCHTHROUGH, 2, 16, false)
+DETEX_TRAITS(F_ETC2_EAC, 4, 16, false)		DETEX_TRAITS(F_EAC_R11, 2, 8, false)
+DETEX_TRAITS(F_EAC_SIGNED_R11, 2, 8, false)	DETEX_TRAITS(F_EAC_RG11, 4, 16, false)
+DETEX_TRAITS(F_EAC_SIGNED_RG11, 4, 16, false)
+#undef DETEX_TRAITS
+
+template <int BW> struct BlockReg;
+template <> struct BlockReg<2> {
+	using type = uint2;
+	static __device__ __forceinline__ uint2 load(const void *p) { return ld_stream_v2(p); }
+};
+template <> struct BlockReg<4> {
+	using type = uint4;
+	static __device__ __forceinline__ uint4 load(const void *p) { return ld_stream_v4(p); }
+};
+
+// One block: registers in, registers out.  Same role as the reference's function
+// table decompress_function[] (texture.c:27-48), resolved at compile time.
+template <int F>
+__device__ __forceinline__ bool decode_block(const typename BlockReg<FormatTraits<F>::BLOCK_WORDS>::type &blk,
+uint32_t mode_mask, uint32_t flags, const BptcTables *tab, uint32_t (&px)[FormatTraits<F>::OUT_WORDS]) {
+	if constexpr (F == F_BC1) return decode_bc1(blk, mode_mask, flags, px);
+	else if constexpr (F == F_BC1A) return decode_bc1a(blk, mode_mask, flags, px);
+	else if constexpr (F == F_BC2) return decode_bc2(blk, mode_mask, flags, px);
+	else if constexpr (F == F_BC3) return decode_bc3(blk, mode_mask, flags, px);
+	else if constexpr (F == F_RGTC1) return decode_rgtc1(blk, mode_mask, flags, px);
+	else if constexpr (F == F_SIGNED_RGTC1) return decode_signed_rgtc1(blk, mode_mask, flags, px);
+	else if constexpr (F == F_RGTC2) return decode_rgtc2(blk, mode_mask, flags, px);
+	else if constexpr (F == F_SIGNED_RGTC2) return decode_signed_rgtc2(blk, mode_mask, flags, px);
+	else if constexpr (F == F_BPTC_FLOAT) return decode_bptc_float<false>(blk, mode_mask, flags, *tab, px);
+	else if constexpr (F == F_BPTC_SIGNED_FLOAT) return decode_bptc_float<true>(blk, mode_mask, flags, *tab, px);
+	else if constexpr (F == F_BPTC) return decode_bptc(blk, mode_mask, flags, *tab, px);
+	else if constexpr (F == F_ETC1) return decode_etc1(blk, mode_mask, flags, px);
+	else if constexpr (F == F_ETC2) return decode_etc2(blk, mode_mask, flags, px);
+	else if constexpr (F == F_ETC2_PUNCHTHROUGH) return decode_etc2_punchthrough(blk, mode_mask, flags, px);
+	else if constexpr (F == F_ETC2_EAC) return decode_etc2_eac(blk, mode_mask, flags, px);
+	else if constexpr (F == F_EAC_R11) return decode_eac_r11<false>(blk, mode_mask, flags, px);
+	else if constexpr (F == F_EAC_SIGNED_R11) return decode_eac_r11<true>(blk, mode_mask, flags, px);
+	else if constexpr (F == F_EAC_RG11) return decode_eac_rg11<false>(blk, mode_mask, flags, px);
+	else return decode_eac_rg11<true>(blk, mode_mask, flags, px);
+}
+
+constexpr int CTA_THREADS = 256;
+constexpr int CTA_WARPS = CTA_THREADS / 32;
+
+// Raise the texture-level "some block was invalid" flag: one read-mostly probe and at
+// most one plain store per CTA (every writer stores the same value).
+__device__ __forceinline__ void report_invalid(bool any_bad_in_thread, uint32_t *invalid_flag) {
+	const int any = __syncthreads_or(any_bad_in_thread ? 1 : 0);
+	if (any && threadIdx.x == 0 && threadIdx.y == 0 && invalid_flag != nullptr)
+		if (*(volatile uint32_t *)invalid_flag == 0u)
+			*(volatile uint32_t *)invalid_flag = 1u;
+}
+
+// ---- TILED --------------------------------------------------------------------------------
+template <int F>
+__global__ void __launch_bounds__(CTA_THREADS)
+decode_tiled_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, uint32_t n_blocks,
+uint32_t mode_mask, uint32_t flags, uint32_t *invalid_flag) {
+	using T = FormatTraits<F>;
+	constexpr int BW = T::BLOCK_WORDS, OW = T::OUT_WORDS, CHUNKS = OW / 4;
+	__shared__ BptcTables tables;
+	__shared__ uint4 stage[CHUNKS > 1 ? CTA_WARPS * 32 * CHUNKS : 1];
+	if constexpr (T::USES_TABLES) {
+		bptc_tables_load(tables);
+		__syncthreads();
+	}
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const uint32_t n_tiles = (n_blocks + 31u) / 32u;		// a tile = 32 consecutive blocks
+	bool bad = false;
+	for (uint32_t tile = blockIdx.x * CTA_WARPS + warp; tile < n_tiles; tile += gridDim.x * CTA_WARPS) {
+		const uint32_t first = tile * 32u, i = first + lane;
+		uint32_t px[OW];
+		bool ok = true;
+		if (i < n_blocks) {
+			const auto blk = BlockReg<BW>::load(src + (size_t)i * (BW * 4));
+			ok = decode_block<F>(blk, mode_mask, flags, &tables, px);
+		}
+		if (!ok) {
+			bad = true;
+#pragma unroll
+			for (int k = 0; k < OW; k++)
+				px[k] = 0u;
+		}
+		uint8_t *tile_out = dst + (size_t)first * (OW * 4);
+		if constexpr (CHUNKS == 1) {
+			if (i < n_blocks)
+				st_stream_v4(tile_out + lane * 16, px[0], px[1], px[2], px[3]);
+		}
+		else {
+			// Transpose through shared memory: lane L parks chunk c of its tile at
+			// L*CHUNKS + (c ^ f(L)), f(L) = (L / (8/CHUNKS)) % CHUNKS, which makes both the
+			// 128-bit stores (fixed c, 8 consecutive lanes) and the 128-bit loads below
+			// (8 consecutive logical chunks) hit eight distinct 16-byte bank groups.
+			uint4 *buf = stage + warp * 32 * CHUNKS;
+			constexpr int GROUP = 8 / CHUNKS;
+			const int swz = (lane / GROUP) % CHUNKS;
+#pragma unroll
+			for (int c = 0; c < CHUNKS; c++)
+				buf[lane * CHUNKS + (c ^ swz)] = make_uint4(px[4 * c], px[4 * c + 1], px[4 * c + 2], px[4 * c + 3]);
+			__syncwarp();
+			const uint32_t valid_chunks = min(32u, n_blocks - first) * CHUNKS;
+#pragma unroll
+			for (int j = 0; j < CHUNKS; j++) {
+				const uint32_t q = j * 32 + lane;		// logical 16-byte chunk of the warp's output
+				const uint32_t b = q / CHUNKS, c = q % CHUNKS;
+				const uint4 v = buf[b * CHUNKS + (c ^ ((b / GROUP) % CHUNKS))];
+				if (q < valid_chunks)
+					st_stream_v4(tile_out + (size_t)q * 16, v.x, v.y, v.z, v.w);
+			}
+			__syncwarp();
+		}
+	}
+	report_invalid(bad, invalid_flag);
+}
+
+// ---- LINEAR, fast path: width % 4 == 0 and 16-byte aligned output ---------------------------
+// blockDim = (TX, TY): thread (x, y) decodes block (blockIdx.x*TX + x, by) with by
+// grid-strided over block rows.
+template <int F>
+__global__ void __launch_bounds__(CTA_THREADS)
+decode_linear_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, int width, int height,
+int wib, int hib, uint32_t mode_mask, uint32_t flags, uint32_t *invalid_flag) {
+	using T = FormatTraits<F>;
+	constexpr int BW = T::BLOCK_WORDS, OW = T::OUT_WORDS, ROW_WORDS = OW / 4, ROW_BYTES = OW;
+	__shared__ BptcTables tables;
+	if constexpr (T::USES_TABLES) {
+		for (int i = threadIdx.y * blockDim.x + threadIdx.x; i < 64; i += blockDim.x * blockDim.y) {
+			tables.two[i] = bptc_two_global[i];
+			tables.three[i] = bptc_three_global[i];
+		}
+		__syncthreads();
+	}
+	const int bx = blockIdx.x * blockDim.x + threadIdx.x;
+	const size_t pitch = (size_t)width * (ROW_BYTES / 4);		// bytes per image row
+	bool bad = false;
+	for (int by = blockIdx.y * blockDim.y + threadIdx.y; by < hib; by += gridDim.y * blockDim.y) {
+		if (bx >= wib)
+			continue;
+		const auto blk = BlockReg<BW>::load(src + ((size_t)by * wib + bx) * (BW * 4));
+		uint32_t px[OW];
+		if (!decode_block<F>(blk, mode_mask, flags, &tables, px)) {
+			bad = true;
+#pragma unroll
+			for (int k = 0; k < OW; k++)
+				px[k] = 0u;
+		}
+		uint8_t *out = dst + (size_t)by * 4 * pitch + (size_t)bx * ROW_BYTES;
+		const int rows = min(4, height - by * 4);		// clip the bottom edge (texture.c:117-120)
+#pragma unroll
+		for (int r = 0; r < 4; r++) {
+			if (r < rows) {
+				uint8_t *p = out + r * pitch;
+				if constexpr (ROW_WORDS == 1)
+					st_stream_u32(p, px[r]);
+				else if constexpr (ROW_WORDS == 2)
+					st_stream_v2(p, px[2 * r], px[2 * r + 1]);
+				else if constexpr (ROW_WORDS == 4)
+					st_stream_v4(p, px[4 * r], px[4 * r + 1], px[4 * r + 2], px[4 * r + 3]);
+				else {
+					st_stream_v4(p, px[8 * r], px[8 * r + 1], px[8 * r + 2], px[8 * r + 3]);
+					st_stream_v4(p + 16, px[8 * r + 4], px[8 * r + 5], px[8 * r + 6], px[8 * r + 7]);
+				}
+			}
+		}
+	}
+	report_invalid(bad, invalid_flag);
+}
+
+// ---- LINEAR, general path: any width / alignment, byte-granular clipped stores -------------
+template <int F>
+__global__ void __launch_bounds__(CTA_THREADS)
+decode_linear_clipped_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, int width, int height,
+int wib, int hib, uint32_t mode_mask, uint32_t flags, uint32_t *invalid_flag) {
+	using T = FormatTraits<F>;
+	constexpr int BW = T::BLOCK_WORDS, OW = T::OUT_WORDS, PS = OW / 4;	// PS = bytes per pixel
+	__shared__ BptcTables tables;
+	if constexpr (T::USES_TABLES) {
+		bptc_tables_load(tables);
+		__syncthreads();
+	}
+	const uint32_t n_blocks = (uint32_t)wib * (uint32_t)hib;
+	bool bad = false;
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_blocks; i += gridDim.x * blockDim.x) {
+		const int by = (int)(i / (uint32_t)wib), bx = (int)(i % (uint32_t)wib);
+		const auto blk = BlockReg<BW>::load(src + (size_t)i * (BW * 4));
+		uint32_t px[OW];
+		if (!decode_block<F>(blk, mode_mask, flags, &tables, px)) {
+			bad = true;
+#pragma unroll
+			for (int k = 0; k < OW; k++)
+				px[k] = 0u;
+		}
+		const int rows = min(4, height - by * 4), cols = min(4, width - bx * 4);
+#pragma unroll
+		for (int r = 0; r < 4; r++)
+#pragma unroll
+			for (int x = 0; x < 4; x++)
+				if (r < rows && x < cols) {
+					uint8_t *p = dst + ((size_t)(by * 4 + r) * width + (size_t)(bx * 4 + x)) * PS;
+#pragma unroll
+					for (int b = 0; b < PS; b++) {
+						const int byte_index = (r * 4 + x) * PS + b;
+						p[b] = (uint8_t)(px[byte_index >> 2] >> (8 * (byte_index & 3)));
+					}
+				}
+	}
+	report_invalid(bad, invalid_flag);
+}
+
+// ---- host-side launcher ---------------------------------------------------------------------
+static std::atomic<uint64_t> g_launches{0};
+
+uint64_t launch_count() { return g_launches.load(); }
+void count_launch() { g_launches.fetch_add(1); }
+
+static int g_sm_count = 0;
+static int sm_count() {
+	if (g_sm_count == 0) {
+		int dev = 0, n = 0;
+		if (cudaGetDevice(&dev) != cudaSuccess ||
+		    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+			n = 148;
+		g_sm_count = n;
+	}
+	return g_sm_count;
+}
+
+template <int F>
+static cudaError_t launch_format(const DecodeArgs &a, cudaStream_t stream) {
+	using T = FormatTraits<F>;
+	const uint64_t n_blocks = (uint64_t)a.wib * (uint64_t)a.hib;
+	if (n_blocks == 0)
+		return cudaSuccess;
+	const uint8_t *src = (const uint8_t *)a.blocks;
+	uint8_t *dst = (uint8_t *)a.pixels;
+	if (a.layout == LAYOUT_TILED) {
+		const uint64_t tiles = (n_blocks + 31) / 32;
+		// enough CTAs to cover the work once, capped at a few waves of resident CTAs
+		const uint64_t want = (tiles + CTA_WARPS - 1) / CTA_WARPS;
+		const uint64_t cap = (uint64_t)sm_count() * 8 * 16;
+		const unsigned grid = (unsigned)(want < cap ? want : cap);
+		decode_tiled_kernel<F><<<grid, CTA_THREADS, 0, stream>>>(src, dst, (uint32_t)n_blocks,
+			a.mode_mask, a.flags, a.invalid);
+	}
+	else {
+		const bool fast = (a.width % 4 == 0) && (((uintptr_t)dst & 15u) == 0);
+		if (fast) {
+			int tx = 32;
+			while (tx < CTA_THREADS && tx < a.wib)
+				tx *= 2;
+			const int ty = CTA_THREADS / tx;
+			dim3 block(tx, ty);
+			unsigned gy = (unsigned)((a.hib + ty - 1) / ty);
+			if (gy > 65535u)
+				gy = 65535u;
+			dim3 grid((unsigned)((a.wib + tx - 1) / tx), gy);
+			decode_linear_kernel<F><<<grid, block, 0, stream>>>(src, dst, a.width, a.height, a.wib, a.hib,
+				a.mode_mask, a.flags, a.invalid);
+		}
+		else {
+			const uint64_t want = (n_blocks + CTA_THREADS - 1) / CTA_THREADS;
+			const uint64_t cap = (uint64_t)sm_count() * 8 * 16;
+			const unsigned grid = (unsigned)(want < cap ? want : cap);
+			decode_linear_clipped_kernel<F><<<grid, CTA_THREADS, 0, stream>>>(src, dst, a.width, a.height,
+				a.wib, a.hib, a.mode_mask, a.flags, a.invalid);
+		}
+	}
+	count_launch();
+	(void)sizeof(T);
+	return cudaGetLastError();
+}
+
+cudaError_t launch_decode(int format_index, const DecodeArgs &a, cudaStream_t stream) {
+	switch (format_index) {
+#define DETEX_CASE(F) case F: return launch_format<F>(a, stream);
+	DETEX_CASE(F_BC1) DETEX_CASE(F_BC1A) DETEX_CASE(F_BC2) DETEX_CASE(F_BC3)
+	DETEX_CASE(F_RGTC1) DETEX_CASE(F_SIGNED_RGTC1) DETEX_CASE(F_RGTC2) DETEX_CASE(F_SIGNED_RGTC2)
+	DETEX_CASE(F_BPTC_FLOAT) DETEX_CASE(F_BPTC_SIGNED_FLOAT) DETEX_CASE(F_BPTC)
+	DETEX_CASE(F_ETC1) DETEX_CASE(F_ETC2) DETEX_CASE(F_ETC2_PUNCHTHROUGH) DETEX_CASE(F_ETC2_EAC)
+	DETEX_CASE(F_EAC_R11) DETEX_CASE(F_EAC_SIGNED_R11) DETEX_CASE(F_EAC_RG11) DETEX_CASE(F_EAC_SIGNED_RG11)
+#undef DETEX_CASE
+	default: return cudaErrorInvalidValue;
+	}
+}
+
+}  // namespace detexb200

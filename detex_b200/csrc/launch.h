@@ -1,0 +1,37 @@
+// Internal interface between the C-ABI layer (api.cu) and the kernels (kernels.cu, aux.cu).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace detexb200 {
+
+constexpr int LAYOUT_TILED = 0, LAYOUT_LINEAR = 1;
+
+struct DecodeArgs {
+	const void *blocks;	// device, wib*hib blocks
+	void *pixels;		// device
+	int width, height;	// pixels (LINEAR clipping)
+	int wib, hib;		// blocks
+	int layout;
+	uint32_t mode_mask, flags;
+	uint32_t *invalid;	// device flag word or nullptr
+};
+
+// Enqueue the decode of one texture in its native pixel format.  format_index = texture_format >> 24.
+cudaError_t launch_decode(int format_index, const DecodeArgs &args, cudaStream_t stream);
+
+// Pixel-format conversion on device (aux.cu); returns cudaErrorNotSupported for pairs
+// that are not implemented.
+bool convert_supported(uint32_t source_pixel_format, uint32_t target_pixel_format);
+cudaError_t launch_convert(const void *src, uint64_t nu_pixels, uint32_t source_pixel_format,
+	void *dst, uint32_t target_pixel_format, cudaStream_t stream);
+
+// Synthetic block generator and device-side hash (aux.cu).
+cudaError_t launch_generate(void *blocks, uint64_t n_blocks, int block_bytes, uint64_t seed,
+	uint64_t first_block, int force_modes, cudaStream_t stream);
+cudaError_t device_hash(const void *buf, uint64_t n_bytes, uint64_t *hash_out, cudaStream_t stream);
+
+uint64_t launch_count();
+void count_launch();
+
+}  // namespace detexb200

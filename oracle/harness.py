@@ -151,6 +151,29 @@ def fnv1a64(buf):
     return int(load_harness().cpu_harness_fnv1a64(a.ctypes.data, a.size))
 
 
+def tree_hash(buf, seg=4096):
+    """CPU statement of detexb200HashDevice (detex_b200/csrc/aux.cu): FNV-1a-64 every
+    4096-byte segment, treat the little-endian array of segment hashes as the next buffer,
+    repeat until one hash is left."""
+    a = np.ascontiguousarray(buf).view(np.uint8).reshape(-1)
+    while True:
+        n = a.size
+        n_seg = max(1, (n + seg - 1) // seg)
+        full = n // seg
+        h = np.full(n_seg, 0xcbf29ce484222325, dtype=np.uint64)
+        prime = np.uint64(0x100000001b3)
+        with np.errstate(over="ignore"):
+            if full:
+                m = a[:full * seg].reshape(full, seg)
+                for j in range(seg):
+                    h[:full] = (h[:full] ^ m[:, j].astype(np.uint64)) * prime
+            for j in range(full * seg, n):          # ragged last segment
+                h[-1] = (h[-1] ^ np.uint64(a[j])) * prime
+        if n_seg == 1:
+            return int(h[0])
+        a = h.view(np.uint8)
+
+
 def synth_blocks(fmt, n_blocks, seed=1, first_block=0):
     """Distribution U of SURVEY.md 8d: raw splitmix64 words, uint8[n_blocks*bs]."""
     bs = FORMATS[fmt][1]

@@ -1,0 +1,328 @@
+"""GPU parity tests: the CUDA path (through the C ABI of libdetex_b200.so) against the CPU
+checker -- the compiled reference oracle/_ref when it travelled to this box, else the oracle
+restatement -- on the same seeded inputs, bit-exact for every format (the BC6H formats emit
+half-float bit patterns through integer arithmetic, so their tolerance is 0 ULP as well).
+Also checks the committed golden vectors and the edge cases of the reference API
+(clipping, invalid blocks, flags / mode masks, error messages)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import detex_b200 as D
+from oracle import harness as H
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+
+@pytest.fixture(scope="module")
+def cpu():
+    lib, kind = H.best_cpu_decoder()
+    return lib
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_cuda_and_native_lib():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    assert D.load().detexb200DeviceCount() > 0, D.detexGetErrorMessage()
+
+
+def _cmp(fmt, blocks, w, h, cpu, linear, threads=4):
+    want, ok_w, _ = H.cpu_decode(cpu, fmt, blocks, w, h, linear=linear, threads=threads)
+    fn = D.detexDecompressTextureLinear if linear else D.detexDecompressTextureTiled
+    got, ok_g = fn(fmt, blocks, w, h)
+    assert ok_g == ok_w, (fmt, w, h, linear, D.detexGetErrorMessage())
+    if not np.array_equal(got, want):
+        ps = H.FORMATS[fmt][2]
+        bad = np.nonzero(got != want)[0]
+        raise AssertionError("%s %dx%d linear=%s: %d bytes differ, first at byte %d (pixel %d)" %
+                             (fmt, w, h, linear, bad.size, bad[0], bad[0] // ps))
+    return ok_g
+
+
+# ---- host-pointer API (reference signature), uniform random blocks ---------------------------
+@pytest.mark.parametrize("fmt", H.FORMAT_NAMES)
+def test_uniform_blocks_linear_and_tiled(fmt, cpu):
+    for seed in (1, 2):
+        b = H.synth_blocks(fmt, 65536, seed=seed)
+        _cmp(fmt, b, 1024, 1024, cpu, True)
+        _cmp(fmt, b, 1024, 1024, cpu, False)
+
+
+@pytest.mark.parametrize("fmt", H.FORMAT_NAMES)
+def test_golden_vectors(fmt, golden):
+    g = golden["uniform"][fmt]
+    b = H.synth_blocks(fmt, g["blocks"], seed=g["seed"])
+    lin, ok = D.detexDecompressTextureLinear(fmt, b, 256, 256)
+    til, ok2 = D.detexDecompressTextureTiled(fmt, b, 256, 256)
+    assert ok == g["ok"] and ok2 == g["ok"]
+    assert "%016x" % H.fnv1a64(lin) == g["linear"]
+    assert "%016x" % H.fnv1a64(til) == g["tiled"]
+    tiles = til.reshape(g["blocks"], g["tile_bytes"])
+    assert int((~tiles.any(axis=1)).sum()) >= g["invalid"]
+
+
+def test_bundled_fixtures(fixtures):
+    names = sorted({k.split("/")[0] for k in fixtures.files})
+    assert "BC1" in names and len(names) == 17
+    for name in names:
+        w, h, ok_ref = (int(v) for v in fixtures[name + "/meta"])
+        out, ok = D.detexDecompressTextureLinear(name, fixtures[name + "/blocks"], w, h)
+        assert ok == bool(ok_ref), name
+        assert np.array_equal(out, fixtures[name + "/pixels"]), name
+
+
+@pytest.mark.parametrize("fmt", ["BPTC", "BPTC_FLOAT", "BPTC_SIGNED_FLOAT"])
+def test_forced_modes(fmt, cpu, golden):
+    n_modes = 8 if fmt == "BPTC" else 14
+    base = H.synth_blocks(fmt, 16384, seed=3)
+    for m in list(range(n_modes)) + [None]:
+        b = H.force_modes(fmt, base, None if m is None else [m])
+        assert _cmp(fmt, b, 512, 512, cpu, True), (fmt, m)	# no invalid blocks in distribution M
+        _cmp(fmt, b, 512, 512, cpu, False)
+    for mode, g in golden["forced_modes"][fmt].items():
+        b = H.force_modes(fmt, H.synth_blocks(fmt, 4096, seed=g["seed"]), None if mode == "cycle" else [int(mode)])
+        out, ok = D.detexDecompressTextureLinear(fmt, b, 256, 256)
+        assert ok == g["ok"] and "%016x" % H.fnv1a64(out) == g["linear"], (fmt, mode)
+
+
+@pytest.mark.parametrize("fmt", ["BPTC", "BPTC_FLOAT", "BPTC_SIGNED_FLOAT"])
+def test_every_partition_and_anchor(fmt, cpu):
+    """All 64 partition sets x all modes: exercises every anchor position."""
+    n_modes = 8 if fmt == "BPTC" else 14
+    base = H.synth_blocks(fmt, 64 * n_modes * 8, seed=17).reshape(-1, 16)
+    blocks = H.force_modes(fmt, base.reshape(-1)).reshape(-1, 16)
+    # sweep the partition field: BC7 partition sits right after the mode bits; BC6H at bits 77-81
+    for i in range(blocks.shape[0]):
+        p = (i // n_modes) % 64
+        if fmt == "BPTC":
+            m = i % 8
+            nbits = [4, 6, 6, 6, 0, 0, 0, 6][m]
+            v = int.from_bytes(blocks[i].tobytes(), "little")
+            mask = ((1 << nbits) - 1) << (m + 1)
+            v = (v & ~mask) | ((p << (m + 1)) & mask)
+            blocks[i] = np.frombuffer(v.to_bytes(16, "little"), dtype=np.uint8)
+        else:
+            v = int.from_bytes(blocks[i].tobytes(), "little")
+            mask = 0x1F << 77
+            v = (v & ~mask) | ((p & 0x1F) << 77)
+            blocks[i] = np.frombuffer(v.to_bytes(16, "little"), dtype=np.uint8)
+    n = blocks.shape[0]
+    w = 64 * 4
+    h = (n // 64) * 4
+    _cmp(fmt, blocks.reshape(-1), w, h, cpu, True)
+
+
+@pytest.mark.parametrize("fmt", H.FORMAT_NAMES)
+def test_clipped_and_odd_sizes(fmt, cpu, golden):
+    for (w, h) in [(1021, 37), (5, 3), (1, 1), (130, 67), (64, 61), (4, 4), (12, 8), (36, 4), (124, 4)]:
+        b = H.synth_blocks(fmt, ((w + 3) // 4) * ((h + 3) // 4), seed=5)
+        _cmp(fmt, b, w, h, cpu, True, threads=1)
+        _cmp(fmt, b, w, h, cpu, False, threads=1)
+    for size, g in golden["clipped"][fmt].items():
+        w, h = (int(v) for v in size.split("x"))
+        b = H.synth_blocks(fmt, ((w + 3) // 4) * ((h + 3) // 4), seed=g["seed"])
+        out, ok = D.detexDecompressTextureLinear(fmt, b, w, h)
+        assert ok == g["ok"] and "%016x" % H.fnv1a64(out) == g["linear"], (fmt, size)
+
+
+def test_empty_texture():
+    out, ok = D.detexDecompressTextureLinear("BC1", np.zeros(0, dtype=np.uint8), 0, 0)
+    assert ok and out.size == 0
+    out, ok = D.detexDecompressTextureTiled("BPTC", np.zeros(0, dtype=np.uint8), 0, 0)
+    assert ok and out.size == 0
+
+
+def test_invalid_blocks_zero_tile_and_message(cpu):
+    # BC7 block with byte 0 == 0 is invalid (Q7); texture-level decode zero-fills it, carries
+    # on, returns false and leaves the reference's message (texture.c:62-66, 90-93).
+    b = H.synth_blocks("BPTC", 64, seed=4).reshape(64, 16).copy()
+    b[5, 0] = 0
+    b[63, 0] = 0
+    out, ok = D.detexDecompressTextureTiled("BPTC", b.reshape(-1), 32, 32)
+    assert not ok
+    assert "Decompress function for format 0x0B800334 returned error" in D.detexGetErrorMessage()
+    tiles = out.reshape(64, 64)
+    assert not tiles[5].any() and not tiles[63].any() and tiles[6].any()
+    want, ok_w, _ = H.cpu_decode(cpu, "BPTC", b.reshape(-1), 32, 32, linear=False)
+    assert not ok_w and np.array_equal(out, want)
+
+
+def test_uncompressed_texture_is_converted_not_decoded():
+    # texture.c:108-111: uncompressed formats go straight to detexConvertPixels
+    px = np.arange(4 * 4 * 4, dtype=np.uint8)
+    out, ok = D.detexDecompressTextureLinear(D.PIXEL_FORMATS["RGBA8"], px, 4, 4, pixel_format=D.PIXEL_FORMATS["RGBA8"])
+    assert ok and np.array_equal(out, px)
+    out, ok = D.detexDecompressTextureLinear(D.PIXEL_FORMATS["RGBA8"], px, 4, 4, pixel_format=D.PIXEL_FORMATS["BGRA8"])
+    assert ok and np.array_equal(out.reshape(-1, 4)[:, [2, 1, 0, 3]].reshape(-1), px)
+    out, ok = D.detexDecompressTextureTiled(D.PIXEL_FORMATS["RGBA8"], px, 4, 4, pixel_format=D.PIXEL_FORMATS["RGBA8"])
+    assert not ok and "Cannot handle uncompressed" in D.detexGetErrorMessage()
+
+
+# ---- per-block API with flags and mode masks ---------------------------------------------------
+@pytest.mark.parametrize("fmt", H.FORMAT_NAMES)
+def test_per_block_api_flags_and_masks(fmt, cpu):
+    bs = H.FORMATS[fmt][1]
+    b = H.synth_blocks(fmt, 24, seed=21)
+    if fmt in ("BPTC", "BPTC_FLOAT", "BPTC_SIGNED_FLOAT"):
+        b = H.force_modes(fmt, b)
+    f_ref = getattr(cpu, "detexDecompressBlock" + fmt)
+    o = np.zeros(256, dtype=np.uint8)
+    combos = [(0xFFFFFFFF, 0), (0xFFFFFFFF, 1), (0xFFFFFFFF, 2), (0xFFFFFFFF, 4), (0x1, 0), (0x2, 0),
+              (0x15, 0), (0xAA, 0), (0x1F00, 0)]
+    for mask, flags in combos:
+        for i in range(24):
+            blk = b[i * bs:(i + 1) * bs]
+            r = f_ref(blk.ctypes.data, mask, flags, o.ctypes.data)
+            got, ok = D.detexDecompressBlockFormat(fmt, blk, mask, flags)
+            assert ok == r, (fmt, mask, flags, i)
+            if r:
+                assert np.array_equal(got, o[:got.size]), (fmt, mask, flags, i)
+
+
+def test_generic_block_entry_point(cpu):
+    b = H.synth_blocks("ETC2_EAC", 4, seed=8)
+    tf = H.FORMATS["ETC2_EAC"][0]
+    o = np.zeros(64, dtype=np.uint8)
+    for i in range(4):
+        blk = b[i * 16:(i + 1) * 16]
+        r = cpu.detexDecompressBlock(blk.ctypes.data, tf, 0xFFFFFFFF, 0, o.ctypes.data, tf & 0xFFFF)
+        got, ok = D.detexDecompressBlock(blk, tf, 0xFFFFFFFF, 0, tf & 0xFFFF)
+        assert ok == r and np.array_equal(got, o)
+    got, ok = D.detexDecompressBlock(b[:16], 0x14800334, 0xFFFFFFFF, 0, 0x334)	# ASTC: no decoder
+    assert not ok and "no decompress function" in D.detexGetErrorMessage()
+
+
+# ---- device-pointer API -------------------------------------------------------------------------
+@pytest.mark.parametrize("fmt", H.FORMAT_NAMES)
+def test_device_api_and_generator(fmt, cpu):
+    tf, bs, ps = H.FORMATS[fmt]
+    n = 256 * 96
+    w, h = 1024, 384
+    d_blocks = torch.empty(n * bs, dtype=torch.uint8, device="cuda")
+    D.generate_blocks_device(d_blocks.data_ptr(), n, bs, seed=7)
+    host_blocks = H.synth_blocks(fmt, n, seed=7)
+    assert np.array_equal(d_blocks.cpu().numpy(), host_blocks)		# device generator == CPU generator
+    flag = torch.zeros(1, dtype=torch.int32, device="cuda")
+    for layout, linear in ((D.LAYOUT_LINEAR, True), (D.LAYOUT_TILED, False)):
+        d_out = torch.full((w * h * ps,), 0xCD, dtype=torch.uint8, device="cuda")
+        flag.zero_()
+        D.decode_device(fmt, d_blocks.data_ptr(), w, h, d_out.data_ptr(), layout=layout, d_invalid=flag.data_ptr())
+        torch.cuda.synchronize()
+        want, ok_w, _ = H.cpu_decode(cpu, fmt, host_blocks, w, h, linear=linear, threads=4)
+        assert np.array_equal(d_out.cpu().numpy(), want), (fmt, linear)
+        assert bool(flag.item() == 0) == ok_w
+
+
+def test_device_api_unaligned_output_and_odd_width(cpu):
+    # output pointer off by 4 bytes and width % 4 != 0 -> clipped general path
+    fmt = "BC3"
+    tf, bs, ps = H.FORMATS[fmt]
+    w, h = 203, 45
+    wib, hib = 51, 12
+    b = H.synth_blocks(fmt, wib * hib, seed=31)
+    d_blocks = torch.from_numpy(b.copy()).cuda()
+    d_out = torch.zeros(w * h * ps + 64, dtype=torch.uint8, device="cuda")
+    D.decode_device(fmt, d_blocks.data_ptr(), w, h, d_out.data_ptr() + 4, layout=D.LAYOUT_LINEAR)
+    torch.cuda.synchronize()
+    want, _, _ = H.cpu_decode(cpu, fmt, b, w, h, linear=True)
+    got = d_out.cpu().numpy()
+    assert np.array_equal(got[4:4 + want.size], want) and not got[:4].any() and not got[4 + want.size:].any()
+
+
+def test_forced_mode_generator_matches_host(cpu):
+    for fmt, nm in (("BPTC", 8), ("BPTC_FLOAT", 14)):
+        n = 4096
+        d = torch.empty(n * 16, dtype=torch.uint8, device="cuda")
+        D.generate_blocks_device(d.data_ptr(), n, 16, seed=3, force_modes=nm)
+        want = H.force_modes(fmt, H.synth_blocks(fmt, n, seed=3))
+        assert np.array_equal(d.cpu().numpy(), want)
+
+
+def test_device_hash_is_the_tree_hash():
+    for n in (0, 1, 4095, 4096, 4097, 1 << 20, (1 << 20) + 13):
+        a = np.random.default_rng(n).integers(0, 256, size=n, dtype=np.uint8)
+        d = torch.from_numpy(a).cuda() if n else torch.empty(0, dtype=torch.uint8, device="cuda")
+        assert D.hash_device(d.data_ptr() if n else 0, n) == H.tree_hash(a), n
+
+
+# ---- conversions fused behind the texture API ------------------------------------
+@pytest.mark.parametrize("fmt,target", [("BC1", "BGRX8"), ("BC1", "RGB8"), ("BC1", "RGBA8"), ("BC3", "BGRA8"),
+                                        ("BC1", "BGRA8"), ("BC3", "RGB8"), ("BC3", "BGRX8"),
+                                        ("BPTC", "BGRA8"), ("BPTC", "RGBX8"), ("ETC2", "RGB8"),
+                                        ("BPTC_FLOAT", "FLOAT_RGB16"), ("BPTC_FLOAT", "FLOAT_BGRX16")])
+def test_texture_decode_with_conversion(fmt, target, cpu):
+    # FLOAT_RGBX16 -> FLOAT_RGB16 writes through an uninitialised pointer in the reference
+    # (convert.c:707, undefined behaviour); the intended result (drop X) is what the oracle
+    # restates, so that pair is checked against the oracle.
+    if target == "FLOAT_RGB16":
+        cpu = H.load_oracle()
+    pf = D.PIXEL_FORMATS[target]
+    for (w, h) in ((256, 128), (61, 35)):
+        b = H.synth_blocks(fmt, ((w + 3) // 4) * ((h + 3) // 4), seed=13)
+        if fmt.startswith("BPTC"):
+            b = H.force_modes(fmt, b)
+        want, ok_w, _ = H.cpu_decode(cpu, fmt, b, w, h, linear=True, pixel_format=pf)
+        got, ok = D.detexDecompressTextureLinear(fmt, b, w, h, pixel_format=pf)
+        assert ok == ok_w and np.array_equal(got, want), (fmt, target, w, h)
+        want, ok_w, _ = H.cpu_decode(cpu, fmt, b, w, h, linear=False, pixel_format=pf)
+        got, ok = D.detexDecompressTextureTiled(fmt, b, w, h, pixel_format=pf)
+        assert ok == ok_w and np.array_equal(got, want), (fmt, target, w, h, "tiled")
+
+
+def test_unsupported_conversion_fails_loudly():
+    b = H.synth_blocks("BPTC_SIGNED_FLOAT", 16, seed=1)
+    out, ok = D.detexDecompressTextureLinear("BPTC_SIGNED_FLOAT", b, 16, 16, pixel_format=D.PIXEL_FORMATS["RGBA8"])
+    assert not ok and "conversion path" in D.detexGetErrorMessage()
+
+
+# ---- BASELINE.json configurations at full size ------------------------------------------------------
+def _full_size(fmt, w, h, cpu, forced=0, threads=None):
+    import os
+    threads = threads or min(64, os.cpu_count() or 1)
+    tf, bs, ps = H.FORMATS[fmt]
+    n = (w // 4) * (h // 4)
+    d_blocks = torch.empty(n * bs, dtype=torch.uint8, device="cuda")
+    D.generate_blocks_device(d_blocks.data_ptr(), n, bs, seed=1, force_modes=forced)
+    d_out = torch.empty(w * h * ps, dtype=torch.uint8, device="cuda")
+    flag = torch.zeros(1, dtype=torch.int32, device="cuda")
+    D.decode_device(fmt, d_blocks.data_ptr(), w, h, d_out.data_ptr(), layout=D.LAYOUT_LINEAR, d_invalid=flag.data_ptr())
+    torch.cuda.synchronize()
+    host_blocks = d_blocks.cpu().numpy()
+    want, ok_w, _ = H.cpu_decode(cpu, fmt, host_blocks, w, h, linear=True, threads=threads)
+    got = d_out.cpu().numpy()
+    assert bool(flag.item() == 0) == ok_w
+    assert np.array_equal(got, want), fmt
+    # the host-pointer API on the same texture (pipelined slabs) must agree too
+    got2, ok2 = D.detexDecompressTextureLinear(fmt, host_blocks, w, h)
+    assert ok2 == ok_w and np.array_equal(got2, want)
+
+
+def test_config_bc1_8192(cpu):
+    _full_size("BC1", 8192, 8192, cpu)
+
+
+def test_config_bc7_16384(cpu):
+    _full_size("BPTC", 16384, 16384, cpu, forced=8)
+
+
+def test_config_bc6h_8192(cpu):
+    _full_size("BPTC_FLOAT", 8192, 8192, cpu, forced=14)
+
+
+def test_config_mixed_tiled_reduced(cpu):
+    """configs[4] at 1/50 scale per format (2e6 blocks each), TILED layout, per-shard tree hashes
+    computed on the device against the same construction on the host."""
+    for fmt, seed in (("ETC2", 1), ("EAC_RG11", 2), ("RGTC2", 3)):
+        tf, bs, ps = H.FORMATS[fmt]
+        n = 2_000_000
+        d_blocks = torch.empty(n * bs, dtype=torch.uint8, device="cuda")
+        D.generate_blocks_device(d_blocks.data_ptr(), n, bs, seed=seed)
+        d_out = torch.empty(n * 16 * ps, dtype=torch.uint8, device="cuda")
+        D.decode_device(fmt, d_blocks.data_ptr(), 4 * 2000, 4 * 1000, d_out.data_ptr(), layout=D.LAYOUT_TILED, wib=2000, hib=1000)
+        torch.cuda.synchronize()
+        want, _, _ = H.cpu_decode(cpu, fmt, d_blocks.cpu().numpy(), 8000, 4000, linear=False, threads=16)
+        assert D.hash_device(d_out.data_ptr(), d_out.numel()) == H.tree_hash(want), fmt
+        assert np.array_equal(d_out.cpu().numpy(), want), fmt
