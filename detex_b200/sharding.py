@@ -1,0 +1,48 @@
+"""Index-range sharding of a block array over the ranks of one job.
+
+The decode is a pure map over independent blocks, so multi-GPU operation needs no data-path
+collective: rank g owns a contiguous range of blocks (TILED) or of block rows (LINEAR, so that
+its output is a contiguous span of image rows), decodes it locally, and only the 1-bit
+"all blocks valid" result is reduced across ranks.
+"""
+
+
+def tiled_shard(n_blocks, rank, world, align=1):
+    """[lo, hi) of rank over a flat block array; boundaries are multiples of `align` blocks
+    (2 for 8-byte formats keeps every shard 16-byte aligned)."""
+    if world < 1 or not 0 <= rank < world:
+        raise ValueError("bad rank/world %r/%r" % (rank, world))
+    lo = (n_blocks * rank // world) // align * align
+    hi = n_blocks if rank == world - 1 else (n_blocks * (rank + 1) // world) // align * align
+    return lo, hi
+
+
+def linear_shard(height_in_blocks, rank, world):
+    """[row_lo, row_hi) block rows of rank for a row-major image."""
+    if world < 1 or not 0 <= rank < world:
+        raise ValueError("bad rank/world %r/%r" % (rank, world))
+    return height_in_blocks * rank // world, height_in_blocks * (rank + 1) // world
+
+
+def linear_shard_view(width, height, width_in_blocks, height_in_blocks, block_bytes, pixel_bytes, rank, world):
+    """Byte offsets and sizes of rank's slab: dict(row_lo, rows, height, in_offset, in_bytes,
+    out_offset, out_bytes) -- the same view arithmetic as the CPU harness (oracle/cpu_harness.c)
+    and the host shim's slab pipeline (detex_b200/csrc/api.cu)."""
+    r0, r1 = linear_shard(height_in_blocks, rank, world)
+    h = max(0, min(height - r0 * 4, (r1 - r0) * 4))
+    return dict(row_lo=r0, rows=r1 - r0, height=h,
+                in_offset=r0 * width_in_blocks * block_bytes, in_bytes=(r1 - r0) * width_in_blocks * block_bytes,
+                out_offset=r0 * 4 * width * pixel_bytes, out_bytes=h * width * pixel_bytes)
+
+
+def all_valid(local_ok, group=None):
+    """AND-reduce the per-rank validity flag (the only cross-rank datum of the decode)."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return bool(local_ok)
+    t = torch.tensor([1 if local_ok else 0], dtype=torch.int32)
+    if dist.get_backend(group) == "nccl":
+        t = t.cuda()
+    dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+    return bool(t.item())
