@@ -6,9 +6,11 @@
 //     constants, so extraction is a funnel shift + mask per field;
 //   * endpoints are kept as two registers per endpoint with 16-bit lanes
 //     (R | B<<16 and G | A<<16) and interpolation is one IMAD per register:
-//     T = (64*E0 + 32) + w*(E1 - E0), evaluated on the packed word.  Each lane's true
-//     value lies in [32, 16352], so the packed integer identity holds without
-//     cross-lane borrows even though (E1 - E0) is negative in some lanes;
+//     T = 4*((64*E0 + 32) + w*(E1 - E0)), evaluated on the packed word.  Each lane's true
+//     value lies in [128, 65408], so the packed integer identity holds without
+//     cross-lane borrows even though (E1 - E0) is negative in some lanes; the wanted
+//     byte ((64*E0+32+w*(E1-E0)) >> 6) is then byte 1 of each lane, and one PRMT gathers
+//     R,G,B,A (and applies the mode 4/5 channel rotation for free);
 //   * the "anchor" pixels that carry one index bit less are handled once per block
 //     by inserting a zero bit into the 64-bit index stream (S += S & ~low(q) shifts
 //     everything from bit q upwards left by one), after which every pixel's index sits
@@ -49,13 +51,15 @@ __device__ __forceinline__ uint64_t insert_zero_bit(uint64_t s, uint32_t q) {
 
 // Interpolation weights aWeight2/3/4 (bptc-tables.c:192-201) in closed form:
 // {0,21,43,64} = 21i + (i>>1); {0,9,18,27,37,46,55,64} = 9i + (i>>2);
-// {0,4,9,13,...,60,64} = (273i + 32) >> 6.
+// {0,4,9,13,...,60,64} = (273i + 32) >> 6.  The 2- and 3-bit tables fit one / two registers
+// and are read with a single byte permute (selector = index; the unused selector nibbles pick
+// table byte 0, which is 0, so the result is the clean weight).
 template <int BITS>
 __device__ __forceinline__ uint32_t bptc_weight(uint32_t i) {
 	if constexpr (BITS == 2)
-		return i * 21u + (i >> 1);
+		return prmt(0x402B1500u, 0u, i);
 	else if constexpr (BITS == 3)
-		return i * 9u + (i >> 2);
+		return prmt(0x1B120900u, 0x40372E25u, i);
 	else
 		return (i * 273u + 32u) >> 6;
 }
@@ -137,14 +141,14 @@ __device__ __forceinline__ void bc7_decode_mode(const uint4 &w, const BptcTables
 		e_rb[e] = r | (b << 16);
 		e_ga[e] = g | (a << 16);
 	});
-	// Per subset: A = 64*E0 + 32 (per lane), K = E1 - E0 (packed integer difference).
+	// Per subset: A = 4*(64*E0 + 32) per lane, K = 4*(E1 - E0) (packed integer difference).
 	uint32_t a_rb[NS], k_rb[NS], a_ga[NS], k_ga[NS];
 #pragma unroll
 	for (int s = 0; s < NS; s++) {
-		a_rb[s] = e_rb[2 * s] * 64u + 0x00200020u;
-		k_rb[s] = e_rb[2 * s + 1] - e_rb[2 * s];
-		a_ga[s] = e_ga[2 * s] * 64u + 0x00200020u;
-		k_ga[s] = e_ga[2 * s + 1] - e_ga[2 * s];
+		a_rb[s] = e_rb[2 * s] * 256u + 0x00800080u;
+		k_rb[s] = (e_rb[2 * s + 1] - e_rb[2 * s]) * 4u;
+		a_ga[s] = e_ga[2 * s] * 256u + 0x00800080u;
+		k_ga[s] = (e_ga[2 * s + 1] - e_ga[2 * s]) * 4u;
 	}
 
 	// ---- partition / anchors
@@ -177,10 +181,11 @@ __device__ __forceinline__ void bc7_decode_mode(const uint4 &w, const BptcTables
 		const uint2 s2w = window64<P_IDX2>(w);
 		s2 = insert_zero_bit(((uint64_t)s2w.y << 32) | s2w.x, IB2 - 1);
 	}
-	// Rotation: swap A with R / G / B after interpolation (:497-508).
-	uint32_t rot_sel = 0x3210u;
+	// Gather selector: byte 1 / 3 of T_rb (R, B) and of T_ga (G, A) -> R G B A; the rotation of
+	// modes 4/5 (swap A with R / G / B after interpolation, :497-508) is folded into it.
+	uint32_t gather = 0x7351u;
 	if constexpr (I.rb > 0)
-		rot_sel = rotation == 0u ? 0x3210u : (rotation == 1u ? 0x0213u : (rotation == 2u ? 0x1230u : 0x2310u));
+		gather = rotation == 0u ? 0x7351u : (rotation == 1u ? 0x1357u : (rotation == 2u ? 0x5371u : 0x3751u));
 
 #pragma unroll
 	for (int i = 0; i < 16; i++) {
@@ -219,10 +224,7 @@ __device__ __forceinline__ void bc7_decode_mode(const uint4 &w, const BptcTables
 			const uint32_t ka = kga - kg;
 			t_ga = aga + wc * kg + wa * ka;
 		}
-		uint32_t p = ((t_rb >> 6) & 0x00FF00FFu) | ((t_ga << 2) & 0xFF00FF00u);
-		if constexpr (I.rb > 0)
-			p = prmt(p, 0u, rot_sel);
-		px[i] = p;
+		px[i] = prmt(t_rb, t_ga, gather);
 	}
 }
 

@@ -17,6 +17,7 @@
 //     store instruction;
 //   * invalid blocks become zero pixels and raise one flag word per CTA (Q16).
 #include <cstdio>
+#include <cstdlib>
 #include <atomic>
 
 #include "common.cuh"
@@ -252,6 +253,145 @@ int wib, int hib, uint32_t mode_mask, uint32_t flags, uint32_t *invalid_flag) {
 	report_invalid(bad, invalid_flag);
 }
 
+// ---- mode-sorted kernel for the multi-mode formats (BC7, BC6H) ---------------------------------
+// These decoders are instruction-bound, not HBM-bound, and every mode runs different code:
+// with one block per lane in index order a warp serialises over every mode present in its 32
+// blocks (8 for BC7 distribution M).  Here a CTA takes a tile of 1024 consecutive blocks,
+// counting-sorts them by mode through shared memory (warp-aggregated shared atomics, bins
+// padded to whole warps), and each warp then decodes 32 blocks of ONE mode: the mode switch
+// inside decode_block<F> becomes warp-uniform.  Results are stored straight to each block's own
+// place (16-byte row segments; L2 merges the half sectors of horizontally adjacent blocks).
+template <int F> struct SortTraits { static constexpr bool ENABLED = false; static constexpr int NUM_BINS = 1; };
+template <> struct SortTraits<F_BPTC> {
+	static constexpr bool ENABLED = true;
+	static constexpr int NUM_BINS = 9;		// modes 0-7 + invalid
+	static __device__ __forceinline__ int bin_of(const uint4 &b, uint32_t mode_mask, uint32_t flags) {
+		const int m = __ffs((int)(b.x & 0xFFu)) - 1;
+		const bool ok = m >= 0 && ((mode_mask >> m) & 1u) && !(m >= 4 && (flags & FLAG_OPAQUE_ONLY)) &&
+			!(m < 4 && (flags & FLAG_NON_OPAQUE_ONLY));
+		return ok ? m : 8;
+	}
+};
+struct SortTraitsBc6h {
+	static constexpr bool ENABLED = true;
+	static constexpr int NUM_BINS = 15;		// detex modes 0-13 + invalid
+	static __device__ __forceinline__ int bin_of(const uint4 &b, uint32_t mode_mask, uint32_t) {
+		const int m = bc6h_mode(b.x);
+		return (m >= 0 && ((mode_mask >> m) & 1u)) ? m : 14;
+	}
+};
+template <> struct SortTraits<F_BPTC_FLOAT> : SortTraitsBc6h {};
+template <> struct SortTraits<F_BPTC_SIGNED_FLOAT> : SortTraitsBc6h {};
+
+constexpr int SORT_TILE = 1024;
+
+template <int F, int LAYOUT>
+__global__ void __launch_bounds__(CTA_THREADS)
+decode_sorted_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, uint32_t n_blocks, int width,
+int height, int wib, uint32_t mode_mask, uint32_t flags, uint32_t *invalid_flag) {
+	using T = FormatTraits<F>;
+	using S = SortTraits<F>;
+	constexpr int OW = T::OUT_WORDS, NB = S::NUM_BINS, PER = SORT_TILE / CTA_THREADS, CAP = SORT_TILE + NB * 32;
+	static_assert(T::BLOCK_WORDS == 4, "sorted kernel handles 16-byte blocks");
+	__shared__ BptcTables tables;
+	__shared__ uint4 s_blk[CAP];
+	__shared__ uint16_t s_id[CAP];
+	__shared__ int s_count[16], s_start[17];
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const uint32_t tile0 = blockIdx.x * (uint32_t)SORT_TILE;
+	if (tid < 16)
+		s_count[tid] = 0;
+	bptc_tables_load(tables);
+	__syncthreads();
+
+	// 1. coalesced load of the tile, PER blocks per thread, and classification by mode
+	uint4 blk[PER];
+	int bin[PER], off[PER];
+#pragma unroll
+	for (int k = 0; k < PER; k++) {
+		const uint32_t i = tile0 + k * CTA_THREADS + tid;
+		bin[k] = -1;
+		if (i < n_blocks) {
+			blk[k] = ld_stream_v4(src + (size_t)i * 16);
+			bin[k] = S::bin_of(blk[k], mode_mask, flags);
+		}
+	}
+	// 2. histogram with warp-aggregated shared atomics; off = this block's slot within its bin
+#pragma unroll
+	for (int k = 0; k < PER; k++) {
+		const unsigned peers = __match_any_sync(0xFFFFFFFFu, bin[k]);
+		const int leader = __ffs((int)peers) - 1;
+		int base = 0;
+		if (lane == leader && bin[k] >= 0)
+			base = atomicAdd(&s_count[bin[k]], __popc(peers));
+		base = __shfl_sync(0xFFFFFFFFu, base, leader);
+		off[k] = base + __popc(peers & ((1u << lane) - 1u));
+	}
+	__syncthreads();
+	// 3. bin starts, each bin padded to a whole number of warps
+	if (tid == 0) {
+		int acc = 0;
+		for (int b = 0; b < NB; b++) {
+			s_start[b] = acc;
+			acc += (s_count[b] + 31) & ~31;
+		}
+		s_start[NB] = acc;
+	}
+	__syncthreads();
+	// 4. scatter blocks (and their tile-local ids) to their sorted slots
+#pragma unroll
+	for (int k = 0; k < PER; k++)
+		if (bin[k] >= 0) {
+			const int pos = s_start[bin[k]] + off[k];
+			s_blk[pos] = blk[k];
+			s_id[pos] = (uint16_t)(k * CTA_THREADS + tid);
+		}
+	__syncthreads();
+	// 5. every warp decodes groups of 32 same-mode blocks
+	const int total = s_start[NB];
+	bool bad = false;
+	for (int g = warp * 32; g < total; g += CTA_WARPS * 32) {
+		int b = 0;
+#pragma unroll
+		for (int j = 1; j < NB; j++)
+			b += (g >= s_start[j]) ? 1 : 0;
+		const int pos = g + lane;
+		if (pos < s_start[b] + s_count[b]) {
+			const uint4 w = s_blk[pos];
+			const uint32_t i = tile0 + s_id[pos];
+			uint32_t px[OW];
+			if (!decode_block<F>(w, mode_mask, flags, &tables, px)) {
+				bad = true;
+#pragma unroll
+				for (int k = 0; k < OW; k++)
+					px[k] = 0u;
+			}
+			if (LAYOUT == LAYOUT_TILED) {
+				uint8_t *out = dst + (size_t)i * (OW * 4);
+#pragma unroll
+				for (int c = 0; c < OW / 4; c++)
+					st_stream_v4(out + 16 * c, px[4 * c], px[4 * c + 1], px[4 * c + 2], px[4 * c + 3]);
+			}
+			else {
+				constexpr int ROW_BYTES = OW;
+				const uint32_t by = i / (uint32_t)wib, bx = i - by * (uint32_t)wib;
+				const size_t pitch = (size_t)width * (ROW_BYTES / 4);
+				uint8_t *out = dst + (size_t)by * 4 * pitch + (size_t)bx * ROW_BYTES;
+				const int rows = min(4, height - (int)by * 4);
+#pragma unroll
+				for (int r = 0; r < 4; r++)
+					if (r < rows) {
+#pragma unroll
+						for (int c = 0; c < ROW_BYTES / 16; c++)
+							st_stream_v4(out + r * pitch + 16 * c, px[(ROW_BYTES / 4) * r + 4 * c], px[(ROW_BYTES / 4) * r + 4 * c + 1],
+								px[(ROW_BYTES / 4) * r + 4 * c + 2], px[(ROW_BYTES / 4) * r + 4 * c + 3]);
+					}
+			}
+		}
+	}
+	report_invalid(bad, invalid_flag);
+}
+
 // ---- host-side launcher ---------------------------------------------------------------------
 static std::atomic<uint64_t> g_launches{0};
 
@@ -270,6 +410,13 @@ static int sm_count() {
 	return g_sm_count;
 }
 
+// DETEXB200_UNSORTED=1 in the environment forces the plain one-block-per-lane kernels
+// (A/B measurements of the mode sort).
+static bool force_unsorted() {
+	static const bool v = [] { const char *e = getenv("DETEXB200_UNSORTED"); return e && e[0] == '1'; }();
+	return v;
+}
+
 template <int F>
 static cudaError_t launch_format(const DecodeArgs &a, cudaStream_t stream) {
 	using T = FormatTraits<F>;
@@ -278,6 +425,22 @@ static cudaError_t launch_format(const DecodeArgs &a, cudaStream_t stream) {
 		return cudaSuccess;
 	const uint8_t *src = (const uint8_t *)a.blocks;
 	uint8_t *dst = (uint8_t *)a.pixels;
+	const bool aligned_out = (((uintptr_t)dst & 15u) == 0);
+	if constexpr (SortTraits<F>::ENABLED) {
+		// multi-mode formats: mode-sorted kernel whenever there is enough work to sort
+		const bool linear_ok = a.layout == LAYOUT_TILED || (a.width % 4 == 0);
+		if (n_blocks >= (uint64_t)SORT_TILE && aligned_out && linear_ok && !force_unsorted()) {
+			const unsigned grid = (unsigned)((n_blocks + SORT_TILE - 1) / SORT_TILE);
+			if (a.layout == LAYOUT_TILED)
+				decode_sorted_kernel<F, LAYOUT_TILED><<<grid, CTA_THREADS, 0, stream>>>(src, dst, (uint32_t)n_blocks,
+					a.width, a.height, a.wib, a.mode_mask, a.flags, a.invalid);
+			else
+				decode_sorted_kernel<F, LAYOUT_LINEAR><<<grid, CTA_THREADS, 0, stream>>>(src, dst, (uint32_t)n_blocks,
+					a.width, a.height, a.wib, a.mode_mask, a.flags, a.invalid);
+			count_launch();
+			return cudaGetLastError();
+		}
+	}
 	if (a.layout == LAYOUT_TILED) {
 		const uint64_t tiles = (n_blocks + 31) / 32;
 		// enough CTAs to cover the work once, capped at a few waves of resident CTAs
@@ -288,7 +451,7 @@ static cudaError_t launch_format(const DecodeArgs &a, cudaStream_t stream) {
 			a.mode_mask, a.flags, a.invalid);
 	}
 	else {
-		const bool fast = (a.width % 4 == 0) && (((uintptr_t)dst & 15u) == 0);
+		const bool fast = (a.width % 4 == 0) && aligned_out;
 		if (fast) {
 			int tx = 32;
 			while (tx < CTA_THREADS && tx < a.wib)
