@@ -52,101 +52,133 @@ __device__ __forceinline__ uint32_t pack_rgb(int r, int g, int b) {
 	return (uint32_t)r | ((uint32_t)g << 8) | ((uint32_t)b << 16);
 }
 
-// Individual / differential sub-block modes (decompress-etc.c:89-180); PUNCH = the
-// non-opaque punch-through variant (modifier 0 for selectors 0 and 2, selector 2 is
-// a fully transparent black pixel, Q13, decompress-etc.c:472-499).
-template <bool PUNCH>
-__device__ __forceinline__ void etc_subblocks(uint32_t w0, uint32_t idx, bool differential, uint32_t (&px)[16]) {
-	int base[2][3];
-#pragma unroll
-	for (int c = 0; c < 3; c++) {
-		const uint32_t byte = (w0 >> (8 * c)) & 0xFFu;
-		if (differential) {
-			const int v1 = (int)(byte & 0xF8u), v2 = etc_diff_sum(byte);
-			base[0][c] = v1 | (v1 >> 5);
-			base[1][c] = v2 | ((v2 & 0xE0) >> 5);
-		}
-		else {
-			base[0][c] = (int)((byte & 0xF0u) | (byte >> 4));
-			base[1][c] = (int)((byte & 0x0Fu) | ((byte & 0x0Fu) << 4));
-		}
-	}
-	const uint32_t b3 = w0 >> 24;
-	const bool flip = b3 & 1u;
-	int small_[2], large_[2];
-	small_[0] = PUNCH ? 0 : (int)etc_small(b3 >> 5);
-	large_[0] = (int)etc_large(b3 >> 5);
-	small_[1] = PUNCH ? 0 : (int)etc_small((b3 >> 2) & 7u);
-	large_[1] = (int)etc_large((b3 >> 2) & 7u);
-#pragma unroll
-	for (int i = 0; i < 16; i++) {
-		// flip 0: columns 0-1 | 2-3 (i >= 8); flip 1: rows 0-1 | 2-3 ((i & 3) >= 2)
-		const bool second = flip ? ((i & 3) >= 2) : (i >= 8);
-		const uint32_t sel = etc_selector(idx, i);
-		int m = (sel & 1u) ? (second ? large_[1] : large_[0]) : (second ? small_[1] : small_[0]);
-		if (sel & 2u)
-			m = -m;
-		const int r = clamp255((second ? base[1][0] : base[0][0]) + m);
-		const int g = clamp255((second ? base[1][1] : base[0][1]) + m);
-		const int b = clamp255((second ? base[1][2] : base[0][2]) + m);
-		uint32_t p = pack_rgb(r, g, b) | 0xFF000000u;
-		if (PUNCH && sel == 2u)
-			p = 0u;
-		px[etc_dest(i)] = p;
-	}
+// ---- palette engine shared by the individual, differential, T and H modes ----------------------
+// In all four modes a pixel is one of at most eight colours, chosen by (sub-block g, 2-bit
+// selector s): clamp(B[g][s] + M[g][s]) with
+//   individual / differential: B = base colour of sub-block g, M = {a, b, -a, -b} of its table
+//                              (decompress-etc.c:25-34, :72-85)
+//   T: B = {c1, c2, c2, c2}, M = {0, d, 0, -d}                       (decompress-etc.c:209-237)
+//   H: B = {c1, c1, c2, c2}, M = {d, -d, d, -d}                      (decompress-etc.c:238-273)
+// The eight colours are computed once per block with 16-bit SIMD add-clamp instructions
+// (VIADDMNMX.S16x2.RELU), laid out as per-channel byte tables (two registers per channel), and
+// every pixel row is then four table look-ups by byte permute plus a 4x4 byte transpose --
+// identical instruction stream for all four modes, so mixed warps do not diverge here.
+// Colours are kept as two registers with 16-bit lanes: rb = R | B<<16, ga = G | A<<16.
+
+// packed bytes (x, y, z, *) -> lanes x | z<<16 and y | 255<<16
+__device__ __forceinline__ void etc_lanes(uint32_t rgb, uint32_t &rb, uint32_t &ga) {
+	rb = prmt(rgb, 0u, 0x4240);
+	ga = prmt(rgb, 0xFFu, 0x5451);
+}
+// clamp(colour + m) on R, G, B (alpha lane untouched)
+__device__ __forceinline__ void etc_add_clamp(uint32_t rb, uint32_t ga, int m, uint32_t &orb, uint32_t &oga) {
+	const uint32_t m2 = prmt((uint32_t)m, 0u, 0x1010), m1 = (uint32_t)m & 0xFFFFu;
+	orb = __viaddmin_s16x2_relu(rb, m2, 0x00FF00FFu);
+	oga = __viaddmin_s16x2_relu(ga, m1, 0x00FF00FFu);
 }
 
-__device__ __forceinline__ int nibble8(uint32_t v) { return (int)((v << 4) | v); }
-
-// T and H modes (decompress-etc.c:202-285, punch-through variant :565-649).
-template <bool PUNCH>
-__device__ __forceinline__ void etc2_t_or_h(uint32_t w0, uint32_t idx, bool h_mode, uint32_t (&px)[16]) {
+// mode: ETC_INDIVIDUAL / ETC_DIFFERENTIAL / ETC_T / ETC_H.  punch: non-opaque punch-through
+// block (modifier 0 for selectors 0 and 2, selector 2 -> transparent black, Q13).
+template <bool ALPHA>
+__device__ __forceinline__ void etc_palette_pixels(uint32_t w0, uint32_t idx, uint32_t mode, bool punch, uint32_t (&px)[16]) {
 	const uint32_t b0 = w0 & 0xFFu, b1 = (w0 >> 8) & 0xFFu, b2 = (w0 >> 16) & 0xFFu, b3 = w0 >> 24;
-	int c1[3], c2[3];
-	uint32_t paint[4];
-	if (!h_mode) {
-		c1[0] = nibble8(((b0 & 0x18u) >> 1) | (b0 & 0x3u));
-		c1[1] = nibble8(b1 >> 4);
-		c1[2] = nibble8(b1 & 0xFu);
-		c2[0] = nibble8(b2 >> 4);
-		c2[1] = nibble8(b2 & 0xFu);
-		c2[2] = nibble8(b3 >> 4);
-		const int d = (int)etc2_distance(((b3 & 0x0Cu) >> 1) | (b3 & 1u));
-		paint[0] = pack_rgb(c1[0], c1[1], c1[2]);
-		paint[1] = pack_rgb(clamp255(c2[0] + d), clamp255(c2[1] + d), clamp255(c2[2] + d));
-		paint[2] = pack_rgb(c2[0], c2[1], c2[2]);
-		paint[3] = pack_rgb(clamp255(c2[0] - d), clamp255(c2[1] - d), clamp255(c2[2] - d));
+	const bool is_t = mode == ETC_T, is_h = mode == ETC_H, is_th = is_t || is_h;
+	// -- sub-block base colours as packed bytes R, G, B (three channels at once)
+	const uint32_t w = w0 & 0x00FFFFFFu;
+	uint32_t base0, base1;
+	if (mode == ETC_DIFFERENTIAL) {
+		// 5-bit base + 3-bit signed delta per byte.  The byte-parallel sum is evaluated modulo 2^32;
+		// whenever this mode is really selected no channel overflows (every byte of the true
+		// result is in [0,248]), so carries between bytes cancel and the word is exact.
+		const uint32_t v1 = w & 0xF8F8F8u, d3 = w & 0x070707u;
+		const uint32_t v2 = v1 + (d3 << 3) - ((d3 & 0x040404u) << 4);
+		base0 = v1 | ((v1 >> 5) & 0x070707u);
+		base1 = v2 | ((v2 >> 5) & 0x070707u);
 	}
 	else {
-		c1[0] = nibble8((b0 & 0x78u) >> 3);
-		c1[1] = nibble8(((b0 & 0x07u) << 1) | ((b1 & 0x10u) >> 4));
-		c1[2] = nibble8((b1 & 0x08u) | ((b1 & 0x03u) << 1) | (b2 >> 7));
-		c2[0] = nibble8((b2 & 0x78u) >> 3);
-		c2[1] = nibble8(((b2 & 0x07u) << 1) | (b3 >> 7));
-		c2[2] = nibble8((b3 & 0x78u) >> 3);
-		const int v1 = (c1[0] << 16) + (c1[1] << 8) + c1[2], v2 = (c2[0] << 16) + (c2[1] << 8) + c2[2];
-		const int d = (int)etc2_distance((b3 & 0x04u) | ((b3 & 0x01u) << 1) | (v1 >= v2 ? 1u : 0u));
-		paint[0] = pack_rgb(clamp255(c1[0] + d), clamp255(c1[1] + d), clamp255(c1[2] + d));
-		paint[1] = pack_rgb(clamp255(c1[0] - d), clamp255(c1[1] - d), clamp255(c1[2] - d));
-		paint[2] = pack_rgb(clamp255(c2[0] + d), clamp255(c2[1] + d), clamp255(c2[2] + d));
-		paint[3] = pack_rgb(clamp255(c2[0] - d), clamp255(c2[1] - d), clamp255(c2[2] - d));
+		base0 = (w & 0xF0F0F0u) | ((w >> 4) & 0x0F0F0Fu);
+		base1 = (w & 0x0F0F0Fu) * 17u;
 	}
-	paint[0] |= 0xFF000000u;
-	paint[1] |= 0xFF000000u;
-	paint[2] = PUNCH ? 0u : (paint[2] | 0xFF000000u);	// Q13
-	paint[3] |= 0xFF000000u;
+	// -- T / H base colours (4-bit channels replicated to 8 bits) and distance
+	uint32_t c1, c2, dist;
+	if (is_h) {
+		const uint32_t r1 = (b0 & 0x78u) >> 3, g1 = ((b0 & 0x07u) << 1) | ((b1 & 0x10u) >> 4);
+		const uint32_t bl1 = (b1 & 0x08u) | ((b1 & 0x03u) << 1) | (b2 >> 7);
+		const uint32_t r2 = (b2 & 0x78u) >> 3, g2 = ((b2 & 0x07u) << 1) | (b3 >> 7), bl2 = (b3 & 0x78u) >> 3;
+		// ordering of the replicated 24-bit colours == ordering of the 12-bit nibble triples
+		const bool ge = ((r1 << 8) | (g1 << 4) | bl1) >= ((r2 << 8) | (g2 << 4) | bl2);
+		dist = etc2_distance((b3 & 0x04u) | ((b3 & 0x01u) << 1) | (ge ? 1u : 0u));
+		c1 = (r1 | (g1 << 8) | (bl1 << 16)) * 17u;
+		c2 = (r2 | (g2 << 8) | (bl2 << 16)) * 17u;
+	}
+	else {
+		const uint32_t r1 = ((b0 & 0x18u) >> 1) | (b0 & 0x3u);
+		dist = etc2_distance(((b3 & 0x0Cu) >> 1) | (b3 & 1u));
+		c1 = (r1 | ((b1 >> 4) << 8) | ((b1 & 0xFu) << 16)) * 17u;
+		c2 = ((b2 >> 4) | ((b2 & 0xFu) << 8) | ((b3 >> 4) << 16)) * 17u;
+	}
+	// -- the eight palette colours -> per-channel byte tables (entry n = g*4 + s)
+	uint32_t tab_rb[2][2], tab_ga[2][2];	// [g][pair]: bytes (R_s, R_s+1, B_s, B_s+1) / (G.., A..)
 #pragma unroll
-	for (int i = 0; i < 16; i++) {
-		const bool s0 = (idx >> i) & 1u, s1 = (idx >> (16 + i)) & 1u;
-		const uint32_t lo = s0 ? paint[1] : paint[0], hi = s0 ? paint[3] : paint[2];
-		px[etc_dest(i)] = s1 ? hi : lo;
+	for (int g = 0; g < 2; g++) {
+		const uint32_t cw = g == 0 ? (b3 >> 5) : ((b3 >> 2) & 7u);
+		const int sm = punch ? 0 : (int)etc_small(cw), lg = (int)etc_large(cw), d = (int)dist;
+		const uint32_t x = is_th ? c1 : (g == 0 ? base0 : base1);
+		const uint32_t y = is_th ? c2 : (g == 0 ? base0 : base1);
+		const int m0 = is_th ? (is_h ? d : 0) : sm;
+		const int m1 = is_th ? (is_h ? -d : d) : lg;
+		const int m2 = is_th ? (is_h ? d : 0) : -sm;
+		const int m3 = is_th ? -d : -lg;
+		uint32_t xrb, xga, yrb, yga;
+		etc_lanes(x, xrb, xga);
+		etc_lanes(y, yrb, yga);
+		uint32_t erb[4], ega[4];
+		etc_add_clamp(xrb, xga, m0, erb[0], ega[0]);
+		etc_add_clamp(is_t ? yrb : xrb, is_t ? yga : xga, m1, erb[1], ega[1]);
+		etc_add_clamp(yrb, yga, m2, erb[2], ega[2]);
+		etc_add_clamp(yrb, yga, m3, erb[3], ega[3]);
+		if (ALPHA && punch) {			// selector 2 is a fully transparent black pixel
+			erb[2] = 0u;
+			ega[2] = 0u;
+		}
+		tab_rb[g][0] = prmt(erb[0], erb[1], 0x6240);	// R0 R1 B0 B1
+		tab_rb[g][1] = prmt(erb[2], erb[3], 0x6240);	// R2 R3 B2 B3
+		tab_ga[g][0] = prmt(ega[0], ega[1], 0x6240);	// G0 G1 A0 A1
+		tab_ga[g][1] = prmt(ega[2], ega[3], 0x6240);
+	}
+	uint32_t tr[2], tg[2], tb[2], ta[2];		// [g]: bytes = entries s = 0..3
+#pragma unroll
+	for (int g = 0; g < 2; g++) {
+		tr[g] = prmt(tab_rb[g][0], tab_rb[g][1], 0x5410);
+		tb[g] = prmt(tab_rb[g][0], tab_rb[g][1], 0x7632);
+		tg[g] = prmt(tab_ga[g][0], tab_ga[g][1], 0x5410);
+		ta[g] = prmt(tab_ga[g][0], tab_ga[g][1], 0x7632);
+	}
+	// -- pixels: output row y holds stream pixels i = 4x + y (Q12); selector nibble = s | g<<2
+	const bool flip = b3 & 1u;
+#pragma unroll
+	for (int y = 0; y < 4; y++) {
+		// LSBs of the four selectors sit at bits y, y+4, y+8, y+12 of idx, MSBs 16 higher:
+		// exactly nibble spacing.  Sub-block: flip 0 -> columns 2,3 (nibbles 2,3), flip 1 -> rows 2,3.
+		const uint32_t gsel = flip ? (y >= 2 ? 0x4444u : 0u) : 0x4400u;
+		const uint32_t sel = ((idx >> y) & 0x1111u) | ((idx >> (15 + y)) & 0x2222u) | gsel;
+		const uint32_t rq = prmt(tr[0], tr[1], sel), gq = prmt(tg[0], tg[1], sel), bq = prmt(tb[0], tb[1], sel);
+		const uint32_t aq = ALPHA ? prmt(ta[0], ta[1], sel) : 0xFFFFFFFFu;
+		const uint32_t rg01 = prmt(rq, gq, 0x5140), rg23 = prmt(rq, gq, 0x7362);
+		const uint32_t ba01 = prmt(bq, aq, 0x5140), ba23 = prmt(bq, aq, 0x7362);
+		px[4 * y + 0] = prmt(rg01, ba01, 0x5410);
+		px[4 * y + 1] = prmt(rg01, ba01, 0x7632);
+		px[4 * y + 2] = prmt(rg23, ba23, 0x5410);
+		px[4 * y + 3] = prmt(rg23, ba23, 0x7632);
 	}
 }
 
-// Planar mode (decompress-etc.c:287-317): 6-7-6 O/H/V colours, bilinear ramp.
+// Planar mode (decompress-etc.c:287-317): 6-7-6 O/H/V colours, bilinear ramp
+// clamp((x(H-O) + y(V-O) + 4O + 2) >> 2), evaluated with 16-bit SIMD lanes (R | B<<16 and G):
+// clamp(t >> 2, 0, 255) == clamp(t, 0, 1023) >> 2, and the >> 2 + byte extraction is done by
+// scaling with 64 so that the wanted byte is byte 1 of each lane.
 __device__ __forceinline__ void etc2_planar(uint32_t w0, uint32_t w1, uint32_t (&px)[16]) {
 	const uint32_t hi = bswap32(w0), lo = bswap32(w1);	// big-endian halves: hi = stream bits 63..32
-	int o[3], h[3], v[3];
 	const uint32_t ro = (hi >> 25) & 0x3Fu;
 	const uint32_t go = (((hi >> 24) & 1u) << 6) | ((hi >> 17) & 0x3Fu);
 	const uint32_t bo = (((hi >> 16) & 1u) << 5) | (((hi >> 11) & 3u) << 3) | ((hi >> 7) & 7u);
@@ -156,25 +188,28 @@ __device__ __forceinline__ void etc2_planar(uint32_t w0, uint32_t w1, uint32_t (
 	const uint32_t rv = (lo >> 13) & 0x3Fu;
 	const uint32_t gv = (lo >> 6) & 0x7Fu;
 	const uint32_t bv = lo & 0x3Fu;
-	o[0] = (int)((ro << 2) | (ro >> 4));	o[1] = (int)((go << 1) | (go >> 6));	o[2] = (int)((bo << 2) | (bo >> 4));
-	h[0] = (int)((rh << 2) | (rh >> 4));	h[1] = (int)((gh << 1) | (gh >> 6));	h[2] = (int)((bh << 2) | (bh >> 4));
-	v[0] = (int)((rv << 2) | (rv >> 4));	v[1] = (int)((gv << 1) | (gv >> 6));	v[2] = (int)((bv << 2) | (bv >> 4));
-	int dx[3], dy[3], base[3];
+	const uint32_t o_r = (ro << 2) | (ro >> 4), o_g = (go << 1) | (go >> 6), o_b = (bo << 2) | (bo >> 4);
+	const uint32_t h_r = (rh << 2) | (rh >> 4), h_g = (gh << 1) | (gh >> 6), h_b = (bh << 2) | (bh >> 4);
+	const uint32_t v_r = (rv << 2) | (rv >> 4), v_g = (gv << 1) | (gv >> 6), v_b = (bv << 2) | (bv >> 4);
+	// per-lane signed 16-bit quantities (R low lane, B high lane; G alone)
+	const uint32_t o_rb = o_r | (o_b << 16), h_rb = h_r | (h_b << 16), v_rb = v_r | (v_b << 16);
+	const uint32_t dx_rb = __vsub2(h_rb, o_rb), dy_rb = __vsub2(v_rb, o_rb);
+	const uint32_t dx_g = (h_g - o_g) & 0xFFFFu, dy_g = (v_g - o_g) & 0xFFFFu;
+	uint32_t row_rb = o_rb * 4u + 0x00020002u, row_g = o_g * 4u + 2u;		// 4*O + 2 (<= 1022 per lane)
 #pragma unroll
-	for (int c = 0; c < 3; c++) {
-		dx[c] = h[c] - o[c];
-		dy[c] = v[c] - o[c];
-		base[c] = 4 * o[c] + 2;
-	}
-#pragma unroll
-	for (int y = 0; y < 4; y++)
+	for (int y = 0; y < 4; y++) {
+		uint32_t t_rb = row_rb, t_g = row_g;
 #pragma unroll
 		for (int x = 0; x < 4; x++) {
-			const int r = clamp255((x * dx[0] + y * dy[0] + base[0]) >> 2);
-			const int g = clamp255((x * dx[1] + y * dy[1] + base[1]) >> 2);
-			const int b = clamp255((x * dx[2] + y * dy[2] + base[2]) >> 2);
-			px[y * 4 + x] = pack_rgb(r, g, b) | 0xFF000000u;
+			const uint32_t c_rb = __vimin_s16x2_relu(t_rb, 0x03FF03FFu) * 64u;	// byte 1 / 3 = (t >> 2)
+			const uint32_t c_g = __vimin_s16x2_relu(t_g, 0x03FF03FFu) * 64u;
+			px[4 * y + x] = prmt(c_rb, c_g, 0x7351) | 0xFF000000u;
+			t_rb = __vadd2(t_rb, dx_rb);
+			t_g = __vadd2(t_g, dx_g);
 		}
+		row_rb = __vadd2(row_rb, dy_rb);
+		row_g = __vadd2(row_g, dy_g);
+	}
 }
 
 // ETC1 -> RGBX8.  Differential overflow is an error in this format only (Q11).
@@ -183,7 +218,7 @@ __device__ __forceinline__ bool decode_etc1(const uint2 blk, uint32_t mode_mask,
 	bool ok = mode_mask & (differential ? ETC_DIFFERENTIAL : ETC_INDIVIDUAL);
 	if (differential)
 		ok = ok && etc2_mode(blk.x) == ETC_DIFFERENTIAL;
-	etc_subblocks<false>(blk.x, bswap32(blk.y), differential, px);
+	etc_palette_pixels<false>(blk.x, bswap32(blk.y), differential ? (uint32_t)ETC_DIFFERENTIAL : (uint32_t)ETC_INDIVIDUAL, false, px);
 	return ok;
 }
 
@@ -192,12 +227,10 @@ __device__ __forceinline__ bool decode_etc2(const uint2 blk, uint32_t mode_mask,
 	const uint32_t idx = bswap32(blk.y);
 	const bool differential_bit = (blk.x >> 24) & 2u;
 	const uint32_t mode = differential_bit ? etc2_mode(blk.x) : (uint32_t)ETC_INDIVIDUAL;
-	if (mode == ETC_T || mode == ETC_H)
-		etc2_t_or_h<false>(blk.x, idx, mode == ETC_H, px);
-	else if (mode == ETC_PLANAR)
+	if (mode == ETC_PLANAR)
 		etc2_planar(blk.x, blk.y, px);
 	else
-		etc_subblocks<false>(blk.x, idx, differential_bit, px);
+		etc_palette_pixels<false>(blk.x, idx, mode, false, px);
 	return (mode_mask & mode) != 0u;
 }
 
@@ -210,22 +243,12 @@ uint32_t (&px)[16]) {
 	const uint32_t mode = etc2_mode(blk.x);
 	bool ok = (mode_mask & mode) != 0u;
 	ok = ok && !(opaque && (flags & FLAG_NON_OPAQUE_ONLY)) && !(!opaque && (flags & FLAG_OPAQUE_ONLY));
-	if (mode == ETC_T || mode == ETC_H) {
-		if (opaque)
-			etc2_t_or_h<false>(blk.x, idx, mode == ETC_H, px);
-		else
-			etc2_t_or_h<true>(blk.x, idx, mode == ETC_H, px);
-	}
-	else if (mode == ETC_PLANAR) {
+	if (mode == ETC_PLANAR) {
 		ok = ok && !(flags & FLAG_NON_OPAQUE_ONLY);		// :695-697
 		etc2_planar(blk.x, blk.y, px);
 	}
-	else {
-		if (opaque)
-			etc_subblocks<false>(blk.x, idx, true, px);
-		else
-			etc_subblocks<true>(blk.x, idx, true, px);
-	}
+	else
+		etc_palette_pixels<true>(blk.x, idx, mode, !opaque, px);
 	return ok;
 }
 

@@ -283,33 +283,66 @@ struct SortTraitsBc6h {
 template <> struct SortTraits<F_BPTC_FLOAT> : SortTraitsBc6h {};
 template <> struct SortTraits<F_BPTC_SIGNED_FLOAT> : SortTraitsBc6h {};
 
-constexpr int SORT_TILE = 1024;
+// Tile size: the staged output of one tile is 64 KiB (1024 BC7 blocks, 512 BC6H blocks).
+template <int F> constexpr int sort_tile() { return 65536 / (FormatTraits<F>::OUT_WORDS * 4); }
 
+constexpr int SORT_THREADS = 512, SORT_WARPS = SORT_THREADS / 32;
+
+// Physical 16-byte slot of chunk c of the block with tile-local index id in the staging buffer:
+// plane c, position id with its low three bits XOR-hashed by the next three bits of id and by
+// a chunk-dependent constant.  Both access patterns are then bank-conflict free (eight lanes
+// of a 128-bit access must hit eight distinct 16-byte bank groups):
+//   * decode writes: fixed c, lanes hold arbitrary ids -- including the adversarial case of
+//     distribution M where all ids of a group are congruent mod 8 (block i has mode i % 8);
+//   * copy-out reads: consecutive logical chunks (TILED: one or two ids x all c; LINEAR:
+//     consecutive ids / halves of one pixel row).
+template <int TB, int CHUNKS>
+__device__ __forceinline__ uint32_t stage_slot(uint32_t id, uint32_t c) {
+	const uint32_t fc = CHUNKS == 8 ? (((c & 1u) << 2) | (c >> 1)) : (2u * c);
+	return c * TB + (id ^ (((id >> 3) ^ fc) & 7u));
+}
+
+template <int F>
+struct SortedSmem {
+	static constexpr int TB = sort_tile<F>(), NB = SortTraits<F>::NUM_BINS, CAP = TB + NB * 32;
+	static constexpr int CHUNKS = FormatTraits<F>::OUT_WORDS / 4;	// 16-byte chunks per decoded tile
+	uint4 out[TB * CHUNKS];		// staged pixels, mirrors the global layout of the tile's region
+	uint4 blk[CAP];			// blocks in sorted order
+	uint16_t id[CAP];		// tile-local index of the block in each sorted slot
+	int count[16], start[17];
+	BptcTables tables;
+};
+
+// 5 phases per CTA: (1) coalesced load + classify, (2) warp-aggregated histogram, (3) scatter
+// blocks to sorted slots, (4) decode warp-uniform groups, pixels parked in shared memory in
+// the tile's own output layout, (5) cooperative, fully coalesced copy-out (512 contiguous
+// bytes per warp store instruction in both layouts).
 template <int F, int LAYOUT>
-__global__ void __launch_bounds__(CTA_THREADS)
+__global__ void __launch_bounds__(SORT_THREADS, 2)
 decode_sorted_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, uint32_t n_blocks, int width,
 int height, int wib, uint32_t mode_mask, uint32_t flags, uint32_t *invalid_flag) {
 	using T = FormatTraits<F>;
 	using S = SortTraits<F>;
-	constexpr int OW = T::OUT_WORDS, NB = S::NUM_BINS, PER = SORT_TILE / CTA_THREADS, CAP = SORT_TILE + NB * 32;
+	using SM = SortedSmem<F>;
+	constexpr int OW = T::OUT_WORDS, NB = S::NUM_BINS, TB = SM::TB, PER = TB / SORT_THREADS, CHUNKS = SM::CHUNKS;
+	constexpr int CPR = CHUNKS / 4;			// 16-byte chunks per pixel row of one block
 	static_assert(T::BLOCK_WORDS == 4, "sorted kernel handles 16-byte blocks");
-	__shared__ BptcTables tables;
-	__shared__ uint4 s_blk[CAP];
-	__shared__ uint16_t s_id[CAP];
-	__shared__ int s_count[16], s_start[17];
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	SM &sm = *reinterpret_cast<SM *>(smem_raw);
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	const uint32_t tile0 = blockIdx.x * (uint32_t)SORT_TILE;
+	const uint32_t tile0 = blockIdx.x * (uint32_t)TB;
 	if (tid < 16)
-		s_count[tid] = 0;
-	bptc_tables_load(tables);
+		sm.count[tid] = 0;
+	bptc_tables_load(sm.tables);
 	__syncthreads();
+	static_assert(TB % SORT_THREADS == 0 && NB <= 16, "tile / bin limits");
 
 	// 1. coalesced load of the tile, PER blocks per thread, and classification by mode
 	uint4 blk[PER];
 	int bin[PER], off[PER];
 #pragma unroll
 	for (int k = 0; k < PER; k++) {
-		const uint32_t i = tile0 + k * CTA_THREADS + tid;
+		const uint32_t i = tile0 + k * SORT_THREADS + tid;
 		bin[k] = -1;
 		if (i < n_blocks) {
 			blk[k] = ld_stream_v4(src + (size_t)i * 16);
@@ -323,68 +356,85 @@ int height, int wib, uint32_t mode_mask, uint32_t flags, uint32_t *invalid_flag)
 		const int leader = __ffs((int)peers) - 1;
 		int base = 0;
 		if (lane == leader && bin[k] >= 0)
-			base = atomicAdd(&s_count[bin[k]], __popc(peers));
+			base = atomicAdd(&sm.count[bin[k]], __popc(peers));
 		base = __shfl_sync(0xFFFFFFFFu, base, leader);
 		off[k] = base + __popc(peers & ((1u << lane) - 1u));
 	}
 	__syncthreads();
-	// 3. bin starts, each bin padded to a whole number of warps
-	if (tid == 0) {
-		int acc = 0;
-		for (int b = 0; b < NB; b++) {
-			s_start[b] = acc;
-			acc += (s_count[b] + 31) & ~31;
+	// bin starts (exclusive scan over at most 16 bins by one warp), bins padded to whole warps
+	if (warp == 0) {
+		const int padded = lane < NB ? ((sm.count[lane] + 31) & ~31) : 0;
+		int incl = padded;
+#pragma unroll
+		for (int d = 1; d < 16; d *= 2) {
+			const int t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+			if (lane >= d)
+				incl += t;
 		}
-		s_start[NB] = acc;
+		if (lane <= NB)
+			sm.start[lane] = incl - padded;
 	}
 	__syncthreads();
-	// 4. scatter blocks (and their tile-local ids) to their sorted slots
+	// 3. scatter blocks (and their tile-local ids) to their sorted slots
 #pragma unroll
 	for (int k = 0; k < PER; k++)
 		if (bin[k] >= 0) {
-			const int pos = s_start[bin[k]] + off[k];
-			s_blk[pos] = blk[k];
-			s_id[pos] = (uint16_t)(k * CTA_THREADS + tid);
+			const int pos = sm.start[bin[k]] + off[k];
+			sm.blk[pos] = blk[k];
+			sm.id[pos] = (uint16_t)(k * SORT_THREADS + tid);
 		}
 	__syncthreads();
-	// 5. every warp decodes groups of 32 same-mode blocks
-	const int total = s_start[NB];
+	// 4. every warp decodes groups of 32 same-mode blocks
+	const int total = sm.start[NB];
 	bool bad = false;
-	for (int g = warp * 32; g < total; g += CTA_WARPS * 32) {
+	for (int g = warp * 32; g < total; g += SORT_WARPS * 32) {
 		int b = 0;
 #pragma unroll
 		for (int j = 1; j < NB; j++)
-			b += (g >= s_start[j]) ? 1 : 0;
+			b += (g >= sm.start[j]) ? 1 : 0;
 		const int pos = g + lane;
-		if (pos < s_start[b] + s_count[b]) {
-			const uint4 w = s_blk[pos];
-			const uint32_t i = tile0 + s_id[pos];
+		if (pos < sm.start[b] + sm.count[b]) {
+			const uint4 w = sm.blk[pos];
+			const uint32_t id = sm.id[pos];
 			uint32_t px[OW];
-			if (!decode_block<F>(w, mode_mask, flags, &tables, px)) {
+			if (!decode_block<F>(w, mode_mask, flags, &sm.tables, px)) {
 				bad = true;
 #pragma unroll
 				for (int k = 0; k < OW; k++)
 					px[k] = 0u;
 			}
-			if (LAYOUT == LAYOUT_TILED) {
-				uint8_t *out = dst + (size_t)i * (OW * 4);
 #pragma unroll
-				for (int c = 0; c < OW / 4; c++)
-					st_stream_v4(out + 16 * c, px[4 * c], px[4 * c + 1], px[4 * c + 2], px[4 * c + 3]);
-			}
-			else {
-				constexpr int ROW_BYTES = OW;
+			for (int c = 0; c < CHUNKS; c++)
+				sm.out[stage_slot<TB, CHUNKS>(id, c)] = make_uint4(px[4 * c], px[4 * c + 1], px[4 * c + 2], px[4 * c + 3]);
+		}
+	}
+	__syncthreads();
+	// 5. copy-out
+	const uint32_t n_here = min((uint32_t)TB, n_blocks - tile0);
+	if (LAYOUT == LAYOUT_TILED) {
+		uint8_t *out = dst + (size_t)tile0 * (OW * 4);
+		for (uint32_t q = tid; q < n_here * CHUNKS; q += SORT_THREADS) {
+			const uint4 v = sm.out[stage_slot<TB, CHUNKS>(q / CHUNKS, q % CHUNKS)];
+			st_stream_v4(out + (size_t)q * 16, v.x, v.y, v.z, v.w);
+		}
+	}
+	else {
+		constexpr int ROW_BYTES = OW;			// bytes of one pixel row of one block
+		const size_t pitch = (size_t)width * (ROW_BYTES / 4);
+		// thread t owns row positions p = t, t+512, ... (p = id*CPR + half) for all 4 pixel rows
+#pragma unroll
+		for (int j = 0; j < TB * CPR / SORT_THREADS; j++) {
+			const uint32_t p = j * SORT_THREADS + tid, id = p / CPR, half = p % CPR;
+			if (id < n_here) {
+				const uint32_t i = tile0 + id;
 				const uint32_t by = i / (uint32_t)wib, bx = i - by * (uint32_t)wib;
-				const size_t pitch = (size_t)width * (ROW_BYTES / 4);
-				uint8_t *out = dst + (size_t)by * 4 * pitch + (size_t)bx * ROW_BYTES;
+				uint8_t *out = dst + (size_t)by * 4 * pitch + (size_t)bx * ROW_BYTES + half * 16;
 				const int rows = min(4, height - (int)by * 4);
 #pragma unroll
 				for (int r = 0; r < 4; r++)
 					if (r < rows) {
-#pragma unroll
-						for (int c = 0; c < ROW_BYTES / 16; c++)
-							st_stream_v4(out + r * pitch + 16 * c, px[(ROW_BYTES / 4) * r + 4 * c], px[(ROW_BYTES / 4) * r + 4 * c + 1],
-								px[(ROW_BYTES / 4) * r + 4 * c + 2], px[(ROW_BYTES / 4) * r + 4 * c + 3]);
+						const uint4 v = sm.out[stage_slot<TB, CHUNKS>(id, r * CPR + half)];
+						st_stream_v4(out + r * pitch, v.x, v.y, v.z, v.w);
 					}
 			}
 		}
@@ -429,13 +479,21 @@ static cudaError_t launch_format(const DecodeArgs &a, cudaStream_t stream) {
 	if constexpr (SortTraits<F>::ENABLED) {
 		// multi-mode formats: mode-sorted kernel whenever there is enough work to sort
 		const bool linear_ok = a.layout == LAYOUT_TILED || (a.width % 4 == 0);
-		if (n_blocks >= (uint64_t)SORT_TILE && aligned_out && linear_ok && !force_unsorted()) {
-			const unsigned grid = (unsigned)((n_blocks + SORT_TILE - 1) / SORT_TILE);
+		constexpr int TB = sort_tile<F>();
+		if (n_blocks >= (uint64_t)TB && aligned_out && linear_ok && !force_unsorted()) {
+			const unsigned grid = (unsigned)((n_blocks + TB - 1) / TB);
+			const size_t smem = sizeof(SortedSmem<F>);
+			static bool configured = false;		// per template instantiation
+			if (!configured) {
+				cudaFuncSetAttribute(decode_sorted_kernel<F, LAYOUT_TILED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+				cudaFuncSetAttribute(decode_sorted_kernel<F, LAYOUT_LINEAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+				configured = true;
+			}
 			if (a.layout == LAYOUT_TILED)
-				decode_sorted_kernel<F, LAYOUT_TILED><<<grid, CTA_THREADS, 0, stream>>>(src, dst, (uint32_t)n_blocks,
+				decode_sorted_kernel<F, LAYOUT_TILED><<<grid, SORT_THREADS, smem, stream>>>(src, dst, (uint32_t)n_blocks,
 					a.width, a.height, a.wib, a.mode_mask, a.flags, a.invalid);
 			else
-				decode_sorted_kernel<F, LAYOUT_LINEAR><<<grid, CTA_THREADS, 0, stream>>>(src, dst, (uint32_t)n_blocks,
+				decode_sorted_kernel<F, LAYOUT_LINEAR><<<grid, SORT_THREADS, smem, stream>>>(src, dst, (uint32_t)n_blocks,
 					a.width, a.height, a.wib, a.mode_mask, a.flags, a.invalid);
 			count_launch();
 			return cudaGetLastError();
