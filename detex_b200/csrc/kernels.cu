@@ -306,17 +306,32 @@ template <int F>
 struct SortedSmem {
 	static constexpr int TB = sort_tile<F>(), NB = SortTraits<F>::NUM_BINS, CAP = TB + NB * 32;
 	static constexpr int CHUNKS = FormatTraits<F>::OUT_WORDS / 4;	// 16-byte chunks per decoded tile
-	uint4 out[TB * CHUNKS];		// staged pixels, mirrors the global layout of the tile's region
-	uint4 blk[CAP];			// blocks in sorted order
-	uint16_t id[CAP];		// tile-local index of the block in each sorted slot
-	int count[16], start[17];
+	uint4 out[TB * CHUNKS];		// staged pixels (stage_slot layout)
+	uint4 raw[2][TB];		// double-buffered compressed tile, filled by cp.async
+	uint16_t id[CAP];		// tile-local block index in each sorted slot
+	int count[2][16];		// per-mode histogram, double-buffered across tiles
 	BptcTables tables;
 };
 
-// 5 phases per CTA: (1) coalesced load + classify, (2) warp-aggregated histogram, (3) scatter
-// blocks to sorted slots, (4) decode warp-uniform groups, pixels parked in shared memory in
-// the tile's own output layout, (5) cooperative, fully coalesced copy-out (512 contiguous
-// bytes per warp store instruction in both layouts).
+__device__ __forceinline__ void cp_async_16(void *smem_dst, const void *gmem_src) {
+	const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_and_wait_all() {
+	asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+// slot of block id inside a raw tile buffer: low three bits hashed with the next three, so that
+// a group whose ids are all congruent mod 8 (distribution M) still reads eight distinct banks
+__device__ __forceinline__ uint32_t raw_slot(uint32_t id) { return id ^ ((id >> 3) & 7u); }
+
+// Persistent CTAs (two per SM), each looping over tiles of TB consecutive blocks:
+//   top     wait for this tile's cp.async data, barrier, start the NEXT tile's cp.async into the
+//           other buffer (in flight during everything below)
+//   sort    classify own blocks (mode = f(first word)), warp-aggregated histogram, barrier, every
+//           warp derives the padded bin starts with a shuffle scan (kept in registers: lane b
+//           holds start[b]), ids scattered to their sorted slots, barrier
+//   decode  each warp takes groups of 32 same-mode blocks -> pixels parked in shared memory
+//   store   barrier, cooperative copy-out, 512 contiguous bytes per warp store instruction
 template <int F, int LAYOUT>
 __global__ void __launch_bounds__(SORT_THREADS, 2)
 decode_sorted_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, uint32_t n_blocks, int width,
@@ -327,115 +342,128 @@ int height, int wib, uint32_t mode_mask, uint32_t flags, uint32_t *invalid_flag)
 	constexpr int OW = T::OUT_WORDS, NB = S::NUM_BINS, TB = SM::TB, PER = TB / SORT_THREADS, CHUNKS = SM::CHUNKS;
 	constexpr int CPR = CHUNKS / 4;			// 16-byte chunks per pixel row of one block
 	static_assert(T::BLOCK_WORDS == 4, "sorted kernel handles 16-byte blocks");
+	static_assert(TB % SORT_THREADS == 0 && NB <= 16, "tile / bin limits");
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	SM &sm = *reinterpret_cast<SM *>(smem_raw);
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	const uint32_t tile0 = blockIdx.x * (uint32_t)TB;
-	if (tid < 16)
-		sm.count[tid] = 0;
+	const uint32_t n_tiles = (n_blocks + TB - 1) / TB;
+	if (tid < 32)
+		(&sm.count[0][0])[tid] = 0;
 	bptc_tables_load(sm.tables);
-	__syncthreads();
-	static_assert(TB % SORT_THREADS == 0 && NB <= 16, "tile / bin limits");
 
-	// 1. coalesced load of the tile, PER blocks per thread, and classification by mode
-	uint4 blk[PER];
-	int bin[PER], off[PER];
+	auto issue_tile_load = [&](uint32_t tile, int buf) {
 #pragma unroll
-	for (int k = 0; k < PER; k++) {
-		const uint32_t i = tile0 + k * SORT_THREADS + tid;
-		bin[k] = -1;
-		if (i < n_blocks) {
-			blk[k] = ld_stream_v4(src + (size_t)i * 16);
-			bin[k] = S::bin_of(blk[k], mode_mask, flags);
+		for (int k = 0; k < PER; k++) {
+			const uint32_t id = k * SORT_THREADS + tid, i = tile * TB + id;
+			if (i < n_blocks)
+				cp_async_16(&sm.raw[buf][raw_slot(id)], src + (size_t)i * 16);
 		}
-	}
-	// 2. histogram with warp-aggregated shared atomics; off = this block's slot within its bin
+	};
+	bool bad = false;
+	int cur = 0;
+	if (blockIdx.x < n_tiles)
+		issue_tile_load(blockIdx.x, 0);
+	for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, cur ^= 1) {
+		const uint32_t tile0 = tile * TB, n_here = min((uint32_t)TB, n_blocks - tile0);
+		cp_async_commit_and_wait_all();
+		__syncthreads();		// raw[cur] complete; previous copy-out done; count[cur] is zero
+		if (tile + gridDim.x < n_tiles)
+			issue_tile_load(tile + gridDim.x, cur ^ 1);
+		if (tid < 16)
+			sm.count[cur ^ 1][tid] = 0;
+		// ---- sort: classify, histogram
+		int bin[PER], off[PER];
 #pragma unroll
-	for (int k = 0; k < PER; k++) {
-		const unsigned peers = __match_any_sync(0xFFFFFFFFu, bin[k]);
-		const int leader = __ffs((int)peers) - 1;
-		int base = 0;
-		if (lane == leader && bin[k] >= 0)
-			base = atomicAdd(&sm.count[bin[k]], __popc(peers));
-		base = __shfl_sync(0xFFFFFFFFu, base, leader);
-		off[k] = base + __popc(peers & ((1u << lane) - 1u));
-	}
-	__syncthreads();
-	// bin starts (exclusive scan over at most 16 bins by one warp), bins padded to whole warps
-	if (warp == 0) {
-		const int padded = lane < NB ? ((sm.count[lane] + 31) & ~31) : 0;
-		int incl = padded;
+		for (int k = 0; k < PER; k++) {
+			const uint32_t id = k * SORT_THREADS + tid;
+			bin[k] = -1;
+			if (id < n_here)
+				bin[k] = S::bin_of(sm.raw[cur][raw_slot(id)], mode_mask, flags);
+		}
+#pragma unroll
+		for (int k = 0; k < PER; k++) {
+			const unsigned peers = __match_any_sync(0xFFFFFFFFu, bin[k]);
+			const int leader = __ffs((int)peers) - 1;
+			int base = 0;
+			if (lane == leader && bin[k] >= 0)
+				base = atomicAdd(&sm.count[cur][bin[k]], __popc(peers));
+			base = __shfl_sync(0xFFFFFFFFu, base, leader);
+			off[k] = base + __popc(peers & ((1u << lane) - 1u));
+		}
+		__syncthreads();
+		// padded exclusive scan of the bin counts, redundantly in every warp: lane b <- start[b]
+		const int my_count = lane < NB ? sm.count[cur][lane] : 0;
+		const int padded = (my_count + 31) & ~31;
+		int start = padded;
 #pragma unroll
 		for (int d = 1; d < 16; d *= 2) {
-			const int t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+			const int t = __shfl_up_sync(0xFFFFFFFFu, start, d);
 			if (lane >= d)
-				incl += t;
+				start += t;
 		}
-		if (lane <= NB)
-			sm.start[lane] = incl - padded;
-	}
-	__syncthreads();
-	// 3. scatter blocks (and their tile-local ids) to their sorted slots
+		start -= padded;		// lane NB holds the padded total
+		const int total = __shfl_sync(0xFFFFFFFFu, start, NB);
 #pragma unroll
-	for (int k = 0; k < PER; k++)
-		if (bin[k] >= 0) {
-			const int pos = sm.start[bin[k]] + off[k];
-			sm.blk[pos] = blk[k];
-			sm.id[pos] = (uint16_t)(k * SORT_THREADS + tid);
+		for (int k = 0; k < PER; k++) {
+			const int st = __shfl_sync(0xFFFFFFFFu, start, bin[k] & 31);
+			if (bin[k] >= 0)
+				sm.id[st + off[k]] = (uint16_t)(k * SORT_THREADS + tid);
 		}
-	__syncthreads();
-	// 4. every warp decodes groups of 32 same-mode blocks
-	const int total = sm.start[NB];
-	bool bad = false;
-	for (int g = warp * 32; g < total; g += SORT_WARPS * 32) {
-		int b = 0;
+		__syncthreads();
+		// ---- decode: groups of 32 same-mode blocks
+		for (int g = warp * 32; g < total; g += SORT_WARPS * 32) {
+			// bin of this group = number of non-empty-prefix starts <= g, minus one
+			const unsigned le = __ballot_sync(0xFFFFFFFFu, lane < NB && start <= g);
+			const int b = 31 - __clz((int)le);
+			const int b_start = __shfl_sync(0xFFFFFFFFu, start, b), b_count = __shfl_sync(0xFFFFFFFFu, my_count, b);
+			const int pos = g + lane;
+			if (pos < b_start + b_count) {
+				const uint32_t id = sm.id[pos];
+				const uint4 w = sm.raw[cur][raw_slot(id)];
+				uint32_t px[OW];
+				if (!decode_block<F>(w, mode_mask, flags, &sm.tables, px)) {
+					bad = true;
 #pragma unroll
-		for (int j = 1; j < NB; j++)
-			b += (g >= sm.start[j]) ? 1 : 0;
-		const int pos = g + lane;
-		if (pos < sm.start[b] + sm.count[b]) {
-			const uint4 w = sm.blk[pos];
-			const uint32_t id = sm.id[pos];
-			uint32_t px[OW];
-			if (!decode_block<F>(w, mode_mask, flags, &sm.tables, px)) {
-				bad = true;
+					for (int k = 0; k < OW; k++)
+						px[k] = 0u;
+				}
 #pragma unroll
-				for (int k = 0; k < OW; k++)
-					px[k] = 0u;
+				for (int c = 0; c < CHUNKS; c++)
+					sm.out[stage_slot<TB, CHUNKS>(id, c)] = make_uint4(px[4 * c], px[4 * c + 1], px[4 * c + 2], px[4 * c + 3]);
 			}
-#pragma unroll
-			for (int c = 0; c < CHUNKS; c++)
-				sm.out[stage_slot<TB, CHUNKS>(id, c)] = make_uint4(px[4 * c], px[4 * c + 1], px[4 * c + 2], px[4 * c + 3]);
 		}
-	}
-	__syncthreads();
-	// 5. copy-out
-	const uint32_t n_here = min((uint32_t)TB, n_blocks - tile0);
-	if (LAYOUT == LAYOUT_TILED) {
-		uint8_t *out = dst + (size_t)tile0 * (OW * 4);
-		for (uint32_t q = tid; q < n_here * CHUNKS; q += SORT_THREADS) {
-			const uint4 v = sm.out[stage_slot<TB, CHUNKS>(q / CHUNKS, q % CHUNKS)];
-			st_stream_v4(out + (size_t)q * 16, v.x, v.y, v.z, v.w);
+		__syncthreads();
+		// ---- store
+		if (LAYOUT == LAYOUT_TILED) {
+			uint8_t *out = dst + (size_t)tile0 * (OW * 4);
+			for (uint32_t q = tid; q < n_here * CHUNKS; q += SORT_THREADS) {
+				const uint4 v = sm.out[stage_slot<TB, CHUNKS>(q / CHUNKS, q % CHUNKS)];
+				st_stream_v4(out + (size_t)q * 16, v.x, v.y, v.z, v.w);
+			}
 		}
-	}
-	else {
-		constexpr int ROW_BYTES = OW;			// bytes of one pixel row of one block
-		const size_t pitch = (size_t)width * (ROW_BYTES / 4);
-		// thread t owns row positions p = t, t+512, ... (p = id*CPR + half) for all 4 pixel rows
+		else {
+			constexpr int ROW_BYTES = OW;		// bytes of one pixel row of one block
+			const size_t pitch = (size_t)width * (ROW_BYTES / 4);
+			const uint32_t by0 = tile0 / (uint32_t)wib, bx0 = tile0 - by0 * (uint32_t)wib;	// uniform
+			// thread t owns row positions p = t, t+512, ... (p = id*CPR + half) for all 4 pixel rows
 #pragma unroll
-		for (int j = 0; j < TB * CPR / SORT_THREADS; j++) {
-			const uint32_t p = j * SORT_THREADS + tid, id = p / CPR, half = p % CPR;
-			if (id < n_here) {
-				const uint32_t i = tile0 + id;
-				const uint32_t by = i / (uint32_t)wib, bx = i - by * (uint32_t)wib;
-				uint8_t *out = dst + (size_t)by * 4 * pitch + (size_t)bx * ROW_BYTES + half * 16;
-				const int rows = min(4, height - (int)by * 4);
-#pragma unroll
-				for (int r = 0; r < 4; r++)
-					if (r < rows) {
-						const uint4 v = sm.out[stage_slot<TB, CHUNKS>(id, r * CPR + half)];
-						st_stream_v4(out + r * pitch, v.x, v.y, v.z, v.w);
+			for (int j = 0; j < TB * CPR / SORT_THREADS; j++) {
+				const uint32_t p = j * SORT_THREADS + tid, id = p / CPR, half = p % CPR;
+				if (id < n_here) {
+					uint32_t bx = bx0 + id, by = by0;
+					while (bx >= (uint32_t)wib) {	// tiles may wrap over block rows (0-1 turns unless wib < TB)
+						bx -= (uint32_t)wib;
+						by++;
 					}
+					uint8_t *out = dst + (size_t)by * 4 * pitch + (size_t)bx * ROW_BYTES + half * 16;
+					const int rows = min(4, height - (int)by * 4);
+#pragma unroll
+					for (int r = 0; r < 4; r++)
+						if (r < rows) {
+							const uint4 v = sm.out[stage_slot<TB, CHUNKS>(id, r * CPR + half)];
+							st_stream_v4(out + r * pitch, v.x, v.y, v.z, v.w);
+						}
+				}
 			}
 		}
 	}
@@ -481,7 +509,9 @@ static cudaError_t launch_format(const DecodeArgs &a, cudaStream_t stream) {
 		const bool linear_ok = a.layout == LAYOUT_TILED || (a.width % 4 == 0);
 		constexpr int TB = sort_tile<F>();
 		if (n_blocks >= (uint64_t)TB && aligned_out && linear_ok && !force_unsorted()) {
-			const unsigned grid = (unsigned)((n_blocks + TB - 1) / TB);
+			const uint64_t tiles = (n_blocks + TB - 1) / TB;
+			const uint64_t resident = (uint64_t)sm_count() * 2;		// persistent: two CTAs per SM
+			const unsigned grid = (unsigned)(tiles < resident ? tiles : resident);
 			const size_t smem = sizeof(SortedSmem<F>);
 			static bool configured = false;		// per template instantiation
 			if (!configured) {
