@@ -361,7 +361,11 @@ def main():
         dom = max(parts, key=lambda p: p["n"] * ALGO_BYTES[p["fmt"]])
         per_launch_ms = ms_max / args.steps * (dom["n"] * ALGO_BYTES[dom["fmt"]]) / step_bytes
         achieved = dom["n"] * ALGO_BYTES[dom["fmt"]] / (per_launch_ms / 1e3) / 1e9
-        kname = "decode_%s_kernel<%s>" % ("linear" if dom["layout"] == D.LAYOUT_LINEAR else "tiled", dom["fmt"])
+        lname = "linear" if dom["layout"] == D.LAYOUT_LINEAR else "tiled"
+        if dom["fmt"] in ("BPTC", "BPTC_FLOAT", "BPTC_SIGNED_FLOAT"):       # mode-sorted persistent kernel
+            kname = "decode_sorted_kernel<%s,%s>" % (dom["fmt"], lname)
+        else:
+            kname = "decode_%s_kernel<%s>" % (lname, dom["fmt"])
         line = {
             "metric": "4x4 blocks/s", "value": value, "unit": "blocks/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,

@@ -9,7 +9,7 @@ LIB = os.path.join(HERE, "libdetex_b200.so")
 SOURCES = ["kernels.cu", "aux.cu", "api.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-    "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC,-fvisibility=hidden", "-shared",
+    "--expt-relaxed-constexpr", "-diag-suppress", "177", "-Xcompiler", "-fPIC,-fvisibility=hidden", "-shared",
 ]
 
 

@@ -44,9 +44,31 @@ __device__ __forceinline__ void static_for(F &&f) {
 	}
 }
 
-// Insert a zero bit at position q of a 64-bit stream (bits >= q move up by one).
+// Insert a zero bit at position q of an index stream (bits >= q move up by one): adding the
+// part above q to the stream doubles it, i.e. shifts it left by one.
 __device__ __forceinline__ uint64_t insert_zero_bit(uint64_t s, uint32_t q) {
 	return s + (s & ~((1ull << q) - 1ull));
+}
+__device__ __forceinline__ uint32_t insert_zero_bit(uint32_t s, uint32_t q) {
+	return s + (s & ~((1u << q) - 1u));
+}
+// Sixteen BITS-bit indices fit one 32-bit word when BITS == 2, else they need 64 bits.
+template <int BITS> struct IndexWord { using type = uint64_t; };
+template <> struct IndexWord<2> { using type = uint32_t; };
+template <int POS, int BITS>
+__device__ __forceinline__ typename IndexWord<BITS>::type index_window(const uint4 &w) {
+	if constexpr (BITS == 2)
+		return field128<POS, (POS + 32 <= 128 ? 32 : 128 - POS)>(w);
+	else {
+		const uint2 v = window64<POS>(w);
+		return ((uint64_t)v.y << 32) | v.x;
+	}
+}
+// a*b + c, pinned to the integer multiply-add (FMA pipe) instead of a compiler-chosen select
+__device__ __forceinline__ uint32_t mad_u32(uint32_t a, uint32_t b, uint32_t c) {
+	uint32_t d;
+	asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+	return d;
 }
 
 // Interpolation weights aWeight2/3/4 (bptc-tables.c:192-201) in closed form:
@@ -110,36 +132,49 @@ __device__ __forceinline__ void bc7_decode_mode(const uint4 &w, const BptcTables
 	const uint32_t rotation = field128<P_ROT, I.rb>(w);
 	const uint32_t isb = field128<P_ISB, I.isb>(w);
 
-	// ---- endpoints: component-major fields (decompress-bptc.c:82-87) -> packed lanes
-	constexpr int CP = CB + ((I.epb || I.spb) ? 1 : 0);	// precision incl. p-bit
+	// ---- endpoints: component-major fields (decompress-bptc.c:82-87) -> packed lanes.
+	// Fields are packed two to a register first (R | B<<16, G | A<<16) so that the p-bit append
+	// and the widening to 8 bits (left-align + MSB replication, :160-175) run once per register.
+	constexpr int CP = CB + ((I.epb || I.spb) ? 1 : 0);	// colour precision incl. p-bit
 	uint32_t e_rb[NE], e_ga[NE];
 	static_for<0, NE>([&](auto e_) {
 		constexpr int e = decltype(e_)::value;
 		constexpr Bc7ModeInfo J = bc7_mode_info(M);	// (constexpr locals of the enclosing scope are not usable here)
-		uint32_t r = field128<P_COL + (0 * NE + e) * CB, CB>(w);
-		uint32_t g = field128<P_COL + (1 * NE + e) * CB, CB>(w);
-		uint32_t b = field128<P_COL + (2 * NE + e) * CB, CB>(w);
-		uint32_t a = field128<P_ALPHA + e * AB, AB>(w);
+		constexpr int CPJ = J.cb + ((J.epb || J.spb) ? 1 : 0), APJ = J.ab + (J.epb ? 1 : 0);
+		const uint32_t r = field128<P_COL + (0 * NE + e) * CB, CB>(w);
+		const uint32_t g = field128<P_COL + (1 * NE + e) * CB, CB>(w);
+		const uint32_t b = field128<P_COL + (2 * NE + e) * CB, CB>(w);
+		const uint32_t a = field128<P_ALPHA + e * AB, AB>(w);
+		uint32_t rb = r | (b << 16), ga = g | (a << 16);
 		if constexpr (J.epb != 0) {
 			// Q6: mode 6 keeps its two p-bits at stream bits 63 and 64 but the
 			// reference reads both from data0 >> 63, so the second is always 0
 			// (decompress-bptc.c:142-158).
 			const uint32_t p = (M == 6 && e == 1) ? 0u : field128<P_PBIT + e, 1>(w);
-			r = (r << 1) | p;	g = (g << 1) | p;	b = (b << 1) | p;	a = (a << 1) | p;
+			const uint32_t p2 = p * 0x00010001u;
+			rb = (rb << 1) | p2;
+			ga = (ga << 1) | p2;
 		}
 		else if constexpr (J.spb != 0) {	// mode 1: one p-bit per subset, colour only (:297-306)
 			const uint32_t p = field128<P_PBIT + e / 2, 1>(w);
-			r = (r << 1) | p;	g = (g << 1) | p;	b = (b << 1) | p;
+			rb = (rb << 1) | (p * 0x00010001u);
+			ga = (ga << 1) | p;
 		}
-		r = widen8<CP>(r);
-		g = widen8<CP>(g);
-		b = widen8<CP>(b);
-		if constexpr (J.ab > 0)
-			a = widen8<J.ab + (J.epb ? 1 : 0)>(a);
-		else
-			a = 0xFFu;					// modes 0-3: alpha 255 (:176-179)
-		e_rb[e] = r | (b << 16);
-		e_ga[e] = g | (a << 16);
+		if constexpr (CPJ < 8)
+			rb = ((rb << (8 - CPJ)) | (rb >> (2 * CPJ - 8))) & 0x00FF00FFu;
+		if constexpr (J.ab == 0) {				// modes 0-3: alpha 255 (:176-179)
+			if constexpr (CPJ < 8)
+				ga = ((ga << (8 - CPJ)) | (ga >> (2 * CPJ - 8))) & 0x000000FFu;
+			ga = (ga & 0xFFu) | 0x00FF0000u;
+		}
+		else if constexpr (APJ == CPJ) {
+			if constexpr (CPJ < 8)
+				ga = ((ga << (8 - CPJ)) | (ga >> (2 * CPJ - 8))) & 0x00FF00FFu;
+		}
+		else						// modes 4, 5: alpha has its own precision
+			ga = widen8<CPJ>(ga & 0xFFFFu) | (widen8<APJ>(ga >> 16) << 16);
+		e_rb[e] = rb;
+		e_ga[e] = ga;
 	});
 	// Per subset: A = 4*(64*E0 + 32) per lane, K = 4*(E1 - E0) (packed integer difference).
 	uint32_t a_rb[NS], k_rb[NS], a_ga[NS], k_ga[NS];
@@ -165,9 +200,10 @@ __device__ __forceinline__ void bc7_decode_mode(const uint4 &w, const BptcTables
 		anchor_c = t.y >> 8;
 	}
 
-	// ---- index streams, anchors expanded to full width (decompress-bptc.c:409-420)
-	const uint2 s1w = window64<P_IDX>(w);
-	uint64_t s1 = ((uint64_t)s1w.y << 32) | s1w.x;
+	// ---- index streams, anchors expanded to full width (decompress-bptc.c:409-420).  With 2-bit
+	// indices the expanded stream is exactly 32 bits, otherwise 48 or 64.
+	using Stream1 = typename IndexWord<IB>::type;
+	Stream1 s1 = index_window<P_IDX, IB>(w);
 	s1 = insert_zero_bit(s1, IB - 1);
 	if constexpr (NS == 2)
 		s1 = insert_zero_bit(s1, anchor_b * IB + (IB - 1));
@@ -176,33 +212,49 @@ __device__ __forceinline__ void bc7_decode_mode(const uint4 &w, const BptcTables
 		const uint32_t qb = max(anchor_b, anchor_c) * IB + (IB - 1);
 		s1 = insert_zero_bit(insert_zero_bit(s1, qa), qb);
 	}
-	uint64_t s2 = 0;
-	if constexpr (IB2 > 0) {
-		const uint2 s2w = window64<P_IDX2>(w);
-		s2 = insert_zero_bit(((uint64_t)s2w.y << 32) | s2w.x, IB2 - 1);
-	}
+	using Stream2 = typename IndexWord<IB2 ? IB2 : 2>::type;
+	Stream2 s2 = 0;
+	if constexpr (IB2 > 0)
+		s2 = insert_zero_bit(index_window<P_IDX2, IB2>(w), IB2 - 1);
 	// Gather selector: byte 1 / 3 of T_rb (R, B) and of T_ga (G, A) -> R G B A; the rotation of
 	// modes 4/5 (swap A with R / G / B after interpolation, :497-508) is folded into it.
 	uint32_t gather = 0x7351u;
 	if constexpr (I.rb > 0)
 		gather = rotation == 0u ? 0x7351u : (rotation == 1u ? 0x1357u : (rotation == 2u ? 0x5371u : 0x3751u));
+	// Subset membership as one bit per pixel (bit i of m1: pixel i is in subset 1; m2: subset 2),
+	// and the per-subset differences of A and K: the endpoint pair of a pixel is then picked with
+	// multiply-adds (X0 + m1*(X1-X0) + m2*(X2-X0)) that issue on the FMA pipe, leaving the ALU
+	// pipe -- the busier one in this kernel -- to the bit-field work.
+	uint32_t m1 = 0u, m2 = 0u;
+	uint32_t d1[4] = { 0u, 0u, 0u, 0u }, d2[4] = { 0u, 0u, 0u, 0u };
+	if constexpr (NS == 2)
+		m1 = subset_bits;
+	else if constexpr (NS == 3) {
+		const uint32_t lo = subset_bits & 0x55555555u, hi = (subset_bits >> 1) & 0x55555555u;
+		m1 = lo & ~hi;		// 2-bit fields: bit 2i
+		m2 = hi & ~lo;
+	}
+	if constexpr (NS >= 2) {
+		d1[0] = a_rb[1] - a_rb[0];	d1[1] = k_rb[1] - k_rb[0];	d1[2] = a_ga[1] - a_ga[0];	d1[3] = k_ga[1] - k_ga[0];
+	}
+	if constexpr (NS == 3) {
+		d2[0] = a_rb[NS - 1] - a_rb[0];	d2[1] = k_rb[NS - 1] - k_rb[0];	d2[2] = a_ga[NS - 1] - a_ga[0];	d2[3] = k_ga[NS - 1] - k_ga[0];
+	}
+	// mode 4/5: K_ga split into its green lane (sign-extended) and its alpha lane
+	const uint32_t kg0 = (uint32_t)(int)(int16_t)(k_ga[0] & 0xFFFFu), ka0 = k_ga[0] - kg0;
 
 #pragma unroll
 	for (int i = 0; i < 16; i++) {
-		// endpoints of this pixel's subset
 		uint32_t arb = a_rb[0], krb = k_rb[0], aga = a_ga[0], kga = k_ga[0];
-		if constexpr (NS == 2) {
-			if ((subset_bits >> i) & 1u) {
-				arb = a_rb[1];	krb = k_rb[1];	aga = a_ga[1];	kga = k_ga[1];
-			}
-		}
-		else if constexpr (NS == 3) {
-			const uint32_t s = (subset_bits >> (2 * i)) & 3u;
-			if (s == 1u) {
-				arb = a_rb[1];	krb = k_rb[1];	aga = a_ga[1];	kga = k_ga[1];
-			}
-			if (s == 2u) {
-				arb = a_rb[NS - 1];	krb = k_rb[NS - 1];	aga = a_ga[NS - 1];	kga = k_ga[NS - 1];
+		if constexpr (NS >= 2) {
+			constexpr int STEP = NS == 2 ? 1 : 2;
+			const uint32_t b1 = (m1 >> (STEP * i)) & 1u;
+			arb = mad_u32(b1, d1[0], arb);	krb = mad_u32(b1, d1[1], krb);
+			aga = mad_u32(b1, d1[2], aga);	kga = mad_u32(b1, d1[3], kga);
+			if constexpr (NS == 3) {
+				const uint32_t b2 = (m2 >> (2 * i)) & 1u;
+				arb = mad_u32(b2, d2[0], arb);	krb = mad_u32(b2, d2[1], krb);
+				aga = mad_u32(b2, d2[2], aga);	kga = mad_u32(b2, d2[3], kga);
 			}
 		}
 		const uint32_t i1 = (uint32_t)(s1 >> (i * IB)) & ((1u << IB) - 1u);
@@ -219,10 +271,7 @@ __device__ __forceinline__ void bc7_decode_mode(const uint4 &w, const BptcTables
 			const uint32_t w1 = bptc_weight<IB>(i1), w2 = bptc_weight<IB2>(i2);
 			const uint32_t wc = isb ? w2 : w1, wa = isb ? w1 : w2;
 			t_rb = arb + wc * krb;
-			// split K_ga into its green lane (sign-extended) and its alpha lane
-			const uint32_t kg = (uint32_t)(int)(int16_t)(kga & 0xFFFFu);
-			const uint32_t ka = kga - kg;
-			t_ga = aga + wc * kg + wa * ka;
+			t_ga = aga + wc * kg0 + wa * ka0;
 		}
 		px[i] = prmt(t_rb, t_ga, gather);
 	}

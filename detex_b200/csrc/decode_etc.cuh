@@ -222,20 +222,27 @@ __device__ __forceinline__ bool decode_etc1(const uint2 blk, uint32_t mode_mask,
 	return ok;
 }
 
+// Which of the two code paths of an ETC2-family decoder gets compiled in: the texture kernels
+// decode palette-mode blocks in their main pass and the (rare) planar blocks in a deferred
+// pass, so each pass only carries the code it can reach.
+enum EtcPaths : int { ETC_PATHS_ALL = 0, ETC_PATHS_NO_PLANAR = 1, ETC_PATHS_PLANAR_ONLY = 2 };
+
 // ETC2 -> RGBX8.  decompress-etc.c:321-367.
+template <int PATHS = ETC_PATHS_ALL>
 __device__ __forceinline__ bool decode_etc2(const uint2 blk, uint32_t mode_mask, uint32_t, uint32_t (&px)[16]) {
 	const uint32_t idx = bswap32(blk.y);
 	const bool differential_bit = (blk.x >> 24) & 2u;
 	const uint32_t mode = differential_bit ? etc2_mode(blk.x) : (uint32_t)ETC_INDIVIDUAL;
-	if (mode == ETC_PLANAR)
+	if (PATHS != ETC_PATHS_NO_PLANAR && (PATHS == ETC_PATHS_PLANAR_ONLY || mode == ETC_PLANAR))
 		etc2_planar(blk.x, blk.y, px);
-	else
+	else if (PATHS != ETC_PATHS_PLANAR_ONLY)
 		etc_palette_pixels<false>(blk.x, idx, mode, false, px);
 	return (mode_mask & mode) != 0u;
 }
 
 // ETC2 punch-through -> RGBA8.  Bit 1 of byte 3 is the opaque flag
 // (decompress-etc.c:653-717).
+template <int PATHS = ETC_PATHS_ALL>
 __device__ __forceinline__ bool decode_etc2_punchthrough(const uint2 blk, uint32_t mode_mask, uint32_t flags,
 uint32_t (&px)[16]) {
 	const uint32_t idx = bswap32(blk.y);
@@ -243,91 +250,121 @@ uint32_t (&px)[16]) {
 	const uint32_t mode = etc2_mode(blk.x);
 	bool ok = (mode_mask & mode) != 0u;
 	ok = ok && !(opaque && (flags & FLAG_NON_OPAQUE_ONLY)) && !(!opaque && (flags & FLAG_OPAQUE_ONLY));
-	if (mode == ETC_PLANAR) {
+	if (PATHS != ETC_PATHS_NO_PLANAR && (PATHS == ETC_PATHS_PLANAR_ONLY || mode == ETC_PLANAR)) {
 		ok = ok && !(flags & FLAG_NON_OPAQUE_ONLY);		// :695-697
 		etc2_planar(blk.x, blk.y, px);
 	}
-	else
+	else if (PATHS != ETC_PATHS_PLANAR_ONLY)
 		etc_palette_pixels<true>(blk.x, idx, mode, !opaque, px);
 	return ok;
 }
 
 // ---- EAC ---------------------------------------------------------------------------
-// eac_modifier_table (decompress-eac.c:21-38), one row of eight int8 per 64-bit entry.
-__device__ __constant__ unsigned long long eac_modifier_rows[16] = {
-	0x0E080502F1F7FAFDull, 0x0C090602F3F6F9FDull, 0x0C070401F3F8FBFEull, 0x0C050301F3FAFCFEull,
-	0x0B070502F4F8FAFDull, 0x0A080602F5F7F9FDull, 0x0A070603F5F8F9FCull, 0x0A070402F5F8FBFDull,
-	0x09070501F6F8FAFEull, 0x09070401F6F8FBFEull, 0x09070301F6F8FCFEull, 0x09060401F6F9FBFEull,
-	0x09060302F6F9FCFDull, 0x09020100F6FDFEFFull, 0x08070503F7F8FAFCull, 0x08060402F7F9FBFDull,
+// eac_modifier_table (decompress-eac.c:21-38).  Every row is {-a,-b,-c,-d, a-1,b-1,c-1,d-1};
+// the magnitudes a..d of the 16 rows are kept as packed bytes.
+// (global memory + read-only cache: the 64-byte table is one line, so a warp's 32 differently
+// indexed reads are a single L1 wavefront; __constant__ would serialise them per distinct row)
+__device__ __align__(64) const uint32_t eac_magnitudes[16] = {
+	0x0F090603u, 0x0D0A0703u, 0x0D080502u, 0x0D060402u, 0x0C080603u, 0x0B090703u, 0x0B080704u, 0x0B080503u,
+	0x0A080602u, 0x0A080502u, 0x0A080402u, 0x0A070502u, 0x0A070403u, 0x0A030201u, 0x09080604u, 0x09070503u,
 };
 
-// Modifier (sign-extended) of 3-bit selector sel from table row {lo, hi}.
-__device__ __forceinline__ int eac_modifier(uint32_t lo, uint32_t hi, uint32_t sel) {
-	return (int)(int8_t)(prmt(lo, hi, sel) & 0xFFu);
-}
-
-// 3-bit selector of stream pixel i: bits 47-3i .. 45-3i of the big-endian qword whose
-// halves are hi (bits 63..32) and lo (bits 31..0)  (decompress-eac.c:46, :121).
-__device__ __forceinline__ uint32_t eac_selector(uint32_t hi, uint32_t lo, int i) {
-	const int sh = 45 - 3 * i;
-	const uint32_t v = sh >= 32 ? (hi >> (sh - 32)) : __funnelshift_r(lo, hi, sh);
-	return v & 7u;
+// A pixel of an EAC channel takes one of eight values (3-bit selector), so -- as for the
+// ETC palette -- the eight results are computed once per block, stored as byte tables and
+// looked up four pixels at a time with byte permutes.
+//
+// Selector nibbles of output row y, REVERSED in x (nibble 0 = pixel x=3 ... nibble 3 = x=0):
+// stream pixel i = 4x + y has its selector at bits 47-3i..45-3i of the big-endian qword
+// {hi, lo}; after shifting right by 9-3y the four selectors sit 12 bits apart.
+__device__ __forceinline__ uint32_t eac_row_selector_rev(uint32_t hi, uint32_t lo, int y) {
+	const int sh = 9 - 3 * y;			// 9, 6, 3, 0
+	const uint32_t q_lo = sh ? __funnelshift_r(lo, hi, sh) : lo, q_hi = hi >> sh;
+	return (q_lo & 0x7u) | ((q_lo >> 8) & 0x70u) | ((q_lo >> 16) & 0x700u) | (__funnelshift_r(q_lo, q_hi, 24) & 0x7000u);
 }
 
 // ETC2_EAC -> RGBA8: ETC2 colour in bytes 8..15, EAC alpha in bytes 0..7
-// (decompress-eac.c:54-86).  Multiplier 0 is legal on decode (Q15).
+// (decompress-eac.c:54-86): alpha = clamp(base + modifier * multiplier, 0, 255).
+// Multiplier 0 is legal on decode (Q15).
+template <int PATHS = ETC_PATHS_ALL>
 __device__ __forceinline__ bool decode_etc2_eac(const uint4 blk, uint32_t mode_mask, uint32_t flags,
 uint32_t (&px)[16]) {
-	const bool ok_colour = decode_etc2(make_uint2(blk.z, blk.w), mode_mask, flags, px);
+	const bool ok_colour = decode_etc2<PATHS>(make_uint2(blk.z, blk.w), mode_mask, flags, px);
 	const uint32_t hi = bswap32(blk.x), lo = bswap32(blk.y);
-	const int base = (int)(hi >> 24), mult = (int)((hi >> 20) & 0xFu);
-	const unsigned long long row = eac_modifier_rows[(hi >> 16) & 0xFu];
-	const uint32_t rlo = (uint32_t)row, rhi = (uint32_t)(row >> 32);
+	const uint32_t base = hi >> 24, mult = (hi >> 20) & 0xFu;
+	const uint32_t mag = __ldg(&eac_magnitudes[(hi >> 16) & 0xFu]);
+	// eight alpha values in 16-bit lanes: entries k and k+1 per register
+	const uint32_t mag01 = prmt(mag, 0u, 0x4140), mag23 = prmt(mag, 0u, 0x4342);	// a | b<<16, c | d<<16
+	const uint32_t base2 = base * 0x00010001u, mult2 = mult * 0x00010001u;
+	const uint32_t p01 = mag01 * mult, p23 = mag23 * mult;				// <= 15*15 per lane
+	const uint32_t up = __vsub2(base2, mult2);					// base - mult (entries 4..7: + mag*mult)
+	const uint32_t e01 = __vimin_s16x2_relu(__vsub2(base2, p01), 0x00FF00FFu);
+	const uint32_t e23 = __vimin_s16x2_relu(__vsub2(base2, p23), 0x00FF00FFu);
+	const uint32_t e45 = __viaddmin_s16x2_relu(up, p01, 0x00FF00FFu);
+	const uint32_t e67 = __viaddmin_s16x2_relu(up, p23, 0x00FF00FFu);
+	const uint32_t t_lo = prmt(e01, e23, 0x6420), t_hi = prmt(e45, e67, 0x6420);	// byte k = entry k
 #pragma unroll
-	for (int i = 0; i < 16; i++) {
-		const int a = clamp255(base + eac_modifier(rlo, rhi, eac_selector(hi, lo, i)) * mult);
-		px[etc_dest(i)] = (px[etc_dest(i)] & 0x00FFFFFFu) | ((uint32_t)a << 24);
+	for (int y = 0; y < 4; y++) {
+		const uint32_t a4 = prmt(t_lo, t_hi, eac_row_selector_rev(hi, lo, y));	// byte 3-x = alpha of pixel x
+		px[4 * y + 0] = prmt(px[4 * y + 0], a4, 0x7210);
+		px[4 * y + 1] = prmt(px[4 * y + 1], a4, 0x6210);
+		px[4 * y + 2] = prmt(px[4 * y + 2], a4, 0x5210);
+		px[4 * y + 3] = prmt(px[4 * y + 3], a4, 0x4210);
 	}
-	return ok_colour && !(mult == 0 && (flags & FLAG_ENCODE));
+	return ok_colour && !(mult == 0u && (flags & FLAG_ENCODE));
 }
 
-// One 11-bit EAC channel -> sixteen 16-bit values (row-major order).
+// One 11-bit EAC channel -> the four pixel rows as pairs of words (two 16-bit pixels each).
 // Unsigned: clamp(base*8+4 + mod*mult8, 0, 2047), replicated (v<<5)|(v>>6);
 // signed: base int8 (-128 invalid), clamp(base*8 + mod*mult8, +-1023), magnitude
 // replicated (m<<5)|(m>>5) then re-signed; multiplier 0 means x1 (Q14;
-// decompress-eac.c:111-128, :167-202).
+// decompress-eac.c:111-128, :167-202).  rows[y][0] = pixels x=0,1, rows[y][1] = x=2,3.
 template <bool SIGNED>
-__device__ __forceinline__ bool eac11_channel(uint32_t w0, uint32_t w1, uint32_t (&out16)[16]) {
+__device__ __forceinline__ bool eac11_channel(uint32_t w0, uint32_t w1, uint32_t (&rows)[4][2]) {
 	const uint32_t hi = bswap32(w0), lo = bswap32(w1);
-	const unsigned long long row = eac_modifier_rows[(hi >> 16) & 0xFu];
-	const uint32_t rlo = (uint32_t)row, rhi = (uint32_t)(row >> 32);
-	int mult8 = (int)((hi >> 20) & 0xFu) * 8;
-	if (mult8 == 0)
-		mult8 = 1;
-	int base;
+	const uint32_t mag = __ldg(&eac_magnitudes[(hi >> 16) & 0xFu]);
+	uint32_t mult8 = ((hi >> 20) & 0xFu) * 8u;
+	if (mult8 == 0u)
+		mult8 = 1u;
 	bool ok = true;
-	if (SIGNED) {
-		base = (int)(int8_t)(hi >> 24);
-		ok = base != -128;
-		base *= 8;
+	uint32_t e01, e23, e45, e67;			// the eight 16-bit results, two per register
+	if (!SIGNED) {
+		const uint32_t base2 = ((hi >> 24) * 8u + 4u) * 0x00010001u, mult2 = mult8 * 0x00010001u;
+		const uint32_t mag01 = prmt(mag, 0u, 0x4140), mag23 = prmt(mag, 0u, 0x4342);
+		const uint32_t p01 = mag01 * mult8, p23 = mag23 * mult8;			// <= 15*120 per lane
+		const uint32_t up = __vsub2(base2, mult2);
+		const uint32_t v01 = __vimin_s16x2_relu(__vsub2(base2, p01), 0x07FF07FFu);
+		const uint32_t v23 = __vimin_s16x2_relu(__vsub2(base2, p23), 0x07FF07FFu);
+		const uint32_t v45 = __viaddmin_s16x2_relu(up, p01, 0x07FF07FFu);
+		const uint32_t v67 = __viaddmin_s16x2_relu(up, p23, 0x07FF07FFu);
+		e01 = (v01 << 5) | ((v01 >> 6) & 0x001F001Fu);
+		e23 = (v23 << 5) | ((v23 >> 6) & 0x001F001Fu);
+		e45 = (v45 << 5) | ((v45 >> 6) & 0x001F001Fu);
+		e67 = (v67 << 5) | ((v67 >> 6) & 0x001F001Fu);
 	}
-	else
-		base = (int)(hi >> 24) * 8 + 4;
+	else {
+		const int base = (int)(int8_t)(hi >> 24);
+		ok = base != -128;
+		uint32_t e[8];
 #pragma unroll
-	for (int i = 0; i < 16; i++) {
-		int v = base + eac_modifier(rlo, rhi, eac_selector(hi, lo, i)) * mult8;
-		uint32_t o;
-		if (SIGNED) {
+		for (int k = 0; k < 8; k++) {
+			const int m = (int)((mag >> (8 * (k & 3))) & 0xFFu);
+			int v = base * 8 + (k < 4 ? -m : m - 1) * (int)mult8;
 			v = min(max(v, -1023), 1023);
-			const int mag = abs(v);
-			const int rep = (mag << 5) | (mag >> 5);
-			o = (uint32_t)(v < 0 ? -rep : rep) & 0xFFFFu;
+			const int a = abs(v), rep = (a << 5) | (a >> 5);
+			e[k] = (uint32_t)(v < 0 ? -rep : rep) & 0xFFFFu;
 		}
-		else {
-			v = min(max(v, 0), 2047);
-			o = (uint32_t)((v << 5) | (v >> 6));
-		}
-		out16[etc_dest(i)] = o;
+		e01 = e[0] | (e[1] << 16);	e23 = e[2] | (e[3] << 16);
+		e45 = e[4] | (e[5] << 16);	e67 = e[6] | (e[7] << 16);
+	}
+	// low-byte and high-byte tables, byte k = entry k
+	const uint32_t l_lo = prmt(e01, e23, 0x6420), l_hi = prmt(e45, e67, 0x6420);
+	const uint32_t h_lo = prmt(e01, e23, 0x7531), h_hi = prmt(e45, e67, 0x7531);
+#pragma unroll
+	for (int y = 0; y < 4; y++) {
+		const uint32_t sel = eac_row_selector_rev(hi, lo, y);
+		const uint32_t l4 = prmt(l_lo, l_hi, sel), h4 = prmt(h_lo, h_hi, sel);	// byte 3-x = pixel x
+		rows[y][0] = prmt(l4, h4, 0x6273);		// pixel 0 | pixel 1 << 16
+		rows[y][1] = prmt(l4, h4, 0x4051);		// pixel 2 | pixel 3 << 16
 	}
 	return ok;
 }
@@ -335,23 +372,29 @@ __device__ __forceinline__ bool eac11_channel(uint32_t w0, uint32_t w1, uint32_t
 // EAC_R11 / EAC_SIGNED_R11 -> R16 / SIGNED_R16 (8 words).
 template <bool SIGNED>
 __device__ __forceinline__ bool decode_eac_r11(const uint2 blk, uint32_t, uint32_t, uint32_t (&px)[8]) {
-	uint32_t h[16];
-	const bool ok = eac11_channel<SIGNED>(blk.x, blk.y, h);
+	uint32_t rows[4][2];
+	const bool ok = eac11_channel<SIGNED>(blk.x, blk.y, rows);
 #pragma unroll
-	for (int i = 0; i < 8; i++)
-		px[i] = h[2 * i] | (h[2 * i + 1] << 16);
+	for (int y = 0; y < 4; y++) {
+		px[2 * y] = rows[y][0];
+		px[2 * y + 1] = rows[y][1];
+	}
 	return ok;
 }
 
 // EAC_RG11 / EAC_SIGNED_RG11 -> RG16 / SIGNED_RG16 (16 words, R in the low half).
 template <bool SIGNED>
 __device__ __forceinline__ bool decode_eac_rg11(const uint4 blk, uint32_t, uint32_t, uint32_t (&px)[16]) {
-	uint32_t r[16], g[16];
+	uint32_t r[4][2], g[4][2];
 	const bool ok_r = eac11_channel<SIGNED>(blk.x, blk.y, r);
 	const bool ok_g = eac11_channel<SIGNED>(blk.z, blk.w, g);
 #pragma unroll
-	for (int i = 0; i < 16; i++)
-		px[i] = r[i] | (g[i] << 16);
+	for (int y = 0; y < 4; y++) {
+		px[4 * y + 0] = prmt(r[y][0], g[y][0], 0x5410);
+		px[4 * y + 1] = prmt(r[y][0], g[y][0], 0x7632);
+		px[4 * y + 2] = prmt(r[y][1], g[y][1], 0x5410);
+		px[4 * y + 3] = prmt(r[y][1], g[y][1], 0x7632);
+	}
 	return ok_r && ok_g;
 }
 

@@ -61,7 +61,7 @@ template <> struct BlockReg<4> {
 
 // One block: registers in, registers out.  Same role as the reference's function
 // table decompress_function[] (texture.c:27-48), resolved at compile time.
-template <int F>
+template <int F, int PATHS = ETC_PATHS_ALL>
 __device__ __forceinline__ bool decode_block(const typename BlockReg<FormatTraits<F>::BLOCK_WORDS>::type &blk,
 uint32_t mode_mask, uint32_t flags, const BptcTables *tab, uint32_t (&px)[FormatTraits<F>::OUT_WORDS]) {
 	if constexpr (F == F_BC1) return decode_bc1(blk, mode_mask, flags, px);
@@ -76,9 +76,9 @@ uint32_t mode_mask, uint32_t flags, const BptcTables *tab, uint32_t (&px)[Format
 	else if constexpr (F == F_BPTC_SIGNED_FLOAT) return decode_bptc_float<true>(blk, mode_mask, flags, *tab, px);
 	else if constexpr (F == F_BPTC) return decode_bptc(blk, mode_mask, flags, *tab, px);
 	else if constexpr (F == F_ETC1) return decode_etc1(blk, mode_mask, flags, px);
-	else if constexpr (F == F_ETC2) return decode_etc2(blk, mode_mask, flags, px);
-	else if constexpr (F == F_ETC2_PUNCHTHROUGH) return decode_etc2_punchthrough(blk, mode_mask, flags, px);
-	else if constexpr (F == F_ETC2_EAC) return decode_etc2_eac(blk, mode_mask, flags, px);
+	else if constexpr (F == F_ETC2) return decode_etc2<PATHS>(blk, mode_mask, flags, px);
+	else if constexpr (F == F_ETC2_PUNCHTHROUGH) return decode_etc2_punchthrough<PATHS>(blk, mode_mask, flags, px);
+	else if constexpr (F == F_ETC2_EAC) return decode_etc2_eac<PATHS>(blk, mode_mask, flags, px);
 	else if constexpr (F == F_EAC_R11) return decode_eac_r11<false>(blk, mode_mask, flags, px);
 	else if constexpr (F == F_EAC_SIGNED_R11) return decode_eac_r11<true>(blk, mode_mask, flags, px);
 	else if constexpr (F == F_EAC_RG11) return decode_eac_rg11<false>(blk, mode_mask, flags, px);
@@ -97,29 +97,90 @@ __device__ __forceinline__ void report_invalid(bool any_bad_in_thread, uint32_t 
 			*(volatile uint32_t *)invalid_flag = 1u;
 }
 
+// ---- rare-mode deferral ------------------------------------------------------------------------
+// ETC2's planar mode is rare (2.7 % of uniformly random blocks) but runs completely different
+// code from the four palette modes; with one block per lane almost every warp contains a
+// planar block and would execute the planar instruction stream for one or two active lanes.
+// Instead a lane that meets a planar block only queues the block's index in shared memory; after
+// a CTA barrier the queued blocks are decoded together, 32 per warp pass.
+constexpr int DEFER_ITERS = 8;		// blocks per thread between two drains of the queue
+template <int F> struct DeferTraits { static constexpr bool ENABLED = false; };
+struct DeferEtc2 {
+	static constexpr bool ENABLED = true;
+	// word holding bytes 0..3 of the colour block; ETC2: planar needs the differential bit set
+	static __device__ __forceinline__ bool planar(uint32_t w0, bool needs_diff_bit) {
+		return (!needs_diff_bit || ((w0 >> 24) & 2u)) && etc2_mode(w0) == ETC_PLANAR;
+	}
+};
+template <> struct DeferTraits<F_ETC2> : DeferEtc2 {
+	static __device__ __forceinline__ bool is_rare(const uint2 &b) { return planar(b.x, true); }
+};
+template <> struct DeferTraits<F_ETC2_PUNCHTHROUGH> : DeferEtc2 {
+	static __device__ __forceinline__ bool is_rare(const uint2 &b) { return planar(b.x, false); }
+};
+template <> struct DeferTraits<F_ETC2_EAC> : DeferEtc2 {
+	static __device__ __forceinline__ bool is_rare(const uint4 &b) { return planar(b.z, true); }
+};
+
+// pixel rows of one block into a LINEAR image (fast path: rows are whole vector stores)
+template <int OW>
+__device__ __forceinline__ void store_linear_rows(uint8_t *dst, size_t pitch, int bx, int by, int height, const uint32_t (&px)[OW]) {
+	constexpr int ROW_WORDS = OW / 4, ROW_BYTES = OW;
+	uint8_t *out = dst + (size_t)by * 4 * pitch + (size_t)bx * ROW_BYTES;
+	const int rows = min(4, height - by * 4);		// clip the bottom edge (texture.c:117-120)
+#pragma unroll
+	for (int r = 0; r < 4; r++) {
+		if (r < rows) {
+			uint8_t *p = out + r * pitch;
+			if constexpr (ROW_WORDS == 1)
+				st_stream_u32(p, px[r]);
+			else if constexpr (ROW_WORDS == 2)
+				st_stream_v2(p, px[2 * r], px[2 * r + 1]);
+			else if constexpr (ROW_WORDS == 4)
+				st_stream_v4(p, px[4 * r], px[4 * r + 1], px[4 * r + 2], px[4 * r + 3]);
+			else {
+				st_stream_v4(p, px[8 * r], px[8 * r + 1], px[8 * r + 2], px[8 * r + 3]);
+				st_stream_v4(p + 16, px[8 * r + 4], px[8 * r + 5], px[8 * r + 6], px[8 * r + 7]);
+			}
+		}
+	}
+}
+
 // ---- TILED --------------------------------------------------------------------------------
 template <int F>
 __global__ void __launch_bounds__(CTA_THREADS)
 decode_tiled_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, uint32_t n_blocks,
 uint32_t mode_mask, uint32_t flags, uint32_t *invalid_flag) {
 	using T = FormatTraits<F>;
+	using D = DeferTraits<F>;
 	constexpr int BW = T::BLOCK_WORDS, OW = T::OUT_WORDS, CHUNKS = OW / 4;
 	__shared__ BptcTables tables;
 	__shared__ uint4 stage[CHUNKS > 1 ? CTA_WARPS * 32 * CHUNKS : 1];
-	if constexpr (T::USES_TABLES) {
+	__shared__ uint32_t queue[D::ENABLED ? CTA_THREADS * DEFER_ITERS : 1];
+	__shared__ int queue_n;
+	if constexpr (T::USES_TABLES)
 		bptc_tables_load(tables);
+	if (threadIdx.x == 0)
+		queue_n = 0;
+	if constexpr (T::USES_TABLES || D::ENABLED)
 		__syncthreads();
-	}
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const uint32_t n_tiles = (n_blocks + 31u) / 32u;		// a tile = 32 consecutive blocks
 	bool bad = false;
-	for (uint32_t tile = blockIdx.x * CTA_WARPS + warp; tile < n_tiles; tile += gridDim.x * CTA_WARPS) {
+	int it = 0;
+	// the loop bound is uniform over the CTA (needed for the barriers of the deferral pass)
+	for (uint32_t tile_base = blockIdx.x * CTA_WARPS; tile_base < n_tiles; tile_base += gridDim.x * CTA_WARPS, it++) {
+		const uint32_t tile = tile_base + warp;
 		const uint32_t first = tile * 32u, i = first + lane;
+		const bool active = tile < n_tiles && i < n_blocks;
 		uint32_t px[OW];
-		bool ok = true;
-		if (i < n_blocks) {
+		bool ok = true, rare = false;
+		if (active) {
 			const auto blk = BlockReg<BW>::load(src + (size_t)i * (BW * 4));
-			ok = decode_block<F>(blk, mode_mask, flags, &tables, px);
+			if constexpr (D::ENABLED)
+				rare = D::is_rare(blk);
+			if (!rare)
+				ok = decode_block<F, D::ENABLED ? ETC_PATHS_NO_PLANAR : ETC_PATHS_ALL>(blk, mode_mask, flags, &tables, px);
 		}
 		if (!ok) {
 			bad = true;
@@ -127,33 +188,65 @@ uint32_t mode_mask, uint32_t flags, uint32_t *invalid_flag) {
 			for (int k = 0; k < OW; k++)
 				px[k] = 0u;
 		}
-		uint8_t *tile_out = dst + (size_t)first * (OW * 4);
-		if constexpr (CHUNKS == 1) {
-			if (i < n_blocks)
-				st_stream_v4(tile_out + lane * 16, px[0], px[1], px[2], px[3]);
-		}
-		else {
-			// Transpose through shared memory: lane L parks chunk c of its tile at
-			// L*CHUNKS + (c ^ f(L)), f(L) = (L / (8/CHUNKS)) % CHUNKS, which makes both the
-			// 128-bit stores (fixed c, 8 consecutive lanes) and the 128-bit loads below
-			// (8 consecutive logical chunks) hit eight distinct 16-byte bank groups.
-			uint4 *buf = stage + warp * 32 * CHUNKS;
-			constexpr int GROUP = 8 / CHUNKS;
-			const int swz = (lane / GROUP) % CHUNKS;
-#pragma unroll
-			for (int c = 0; c < CHUNKS; c++)
-				buf[lane * CHUNKS + (c ^ swz)] = make_uint4(px[4 * c], px[4 * c + 1], px[4 * c + 2], px[4 * c + 3]);
-			__syncwarp();
-			const uint32_t valid_chunks = min(32u, n_blocks - first) * CHUNKS;
-#pragma unroll
-			for (int j = 0; j < CHUNKS; j++) {
-				const uint32_t q = j * 32 + lane;		// logical 16-byte chunk of the warp's output
-				const uint32_t b = q / CHUNKS, c = q % CHUNKS;
-				const uint4 v = buf[b * CHUNKS + (c ^ ((b / GROUP) % CHUNKS))];
-				if (q < valid_chunks)
-					st_stream_v4(tile_out + (size_t)q * 16, v.x, v.y, v.z, v.w);
+		const unsigned rare_mask = D::ENABLED ? __ballot_sync(0xFFFFFFFFu, rare) : 0u;
+		if (tile < n_tiles) {
+			uint8_t *tile_out = dst + (size_t)first * (OW * 4);
+			if constexpr (CHUNKS == 1) {
+				if (active && !rare)
+					st_stream_v4(tile_out + lane * 16, px[0], px[1], px[2], px[3]);
 			}
-			__syncwarp();
+			else {
+				// Transpose through shared memory: lane L parks chunk c of its tile at
+				// L*CHUNKS + (c ^ f(L)), f(L) = (L / (8/CHUNKS)) % CHUNKS, which makes both the
+				// 128-bit stores (fixed c, 8 consecutive lanes) and the 128-bit loads below
+				// (8 consecutive logical chunks) hit eight distinct 16-byte bank groups.
+				uint4 *buf = stage + warp * 32 * CHUNKS;
+				constexpr int GROUP = 8 / CHUNKS;
+				const int swz = (lane / GROUP) % CHUNKS;
+#pragma unroll
+				for (int c = 0; c < CHUNKS; c++)
+					buf[lane * CHUNKS + (c ^ swz)] = make_uint4(px[4 * c], px[4 * c + 1], px[4 * c + 2], px[4 * c + 3]);
+				__syncwarp();
+				const uint32_t valid_chunks = min(32u, n_blocks - first) * CHUNKS;
+#pragma unroll
+				for (int j = 0; j < CHUNKS; j++) {
+					const uint32_t q = j * 32 + lane;		// logical 16-byte chunk of the warp's output
+					const uint32_t b = q / CHUNKS, c = q % CHUNKS;
+					const uint4 v = buf[b * CHUNKS + (c ^ ((b / GROUP) % CHUNKS))];
+					if (q < valid_chunks && !((rare_mask >> b) & 1u))
+						st_stream_v4(tile_out + (size_t)q * 16, v.x, v.y, v.z, v.w);
+				}
+				__syncwarp();
+			}
+		}
+		if constexpr (D::ENABLED) {
+			if (rare)
+				queue[atomicAdd(&queue_n, 1)] = i;
+			// drain the queue every DEFER_ITERS iterations and after the last one
+			const bool last = tile_base + gridDim.x * CTA_WARPS >= n_tiles;
+			if ((it + 1) % DEFER_ITERS != 0 && !last)
+				continue;
+			__syncthreads();
+			const int n_rare = queue_n;
+			for (int e = threadIdx.x; e < n_rare; e += CTA_THREADS) {
+				const uint32_t j = queue[e];
+				const auto blk = BlockReg<BW>::load(src + (size_t)j * (BW * 4));
+				uint32_t qx[OW];
+				if (!decode_block<F, ETC_PATHS_PLANAR_ONLY>(blk, mode_mask, flags, &tables, qx)) {
+					bad = true;
+#pragma unroll
+					for (int k = 0; k < OW; k++)
+						qx[k] = 0u;
+				}
+				uint8_t *out = dst + (size_t)j * (OW * 4);
+#pragma unroll
+				for (int c = 0; c < CHUNKS; c++)
+					st_stream_v4(out + 16 * c, qx[4 * c], qx[4 * c + 1], qx[4 * c + 2], qx[4 * c + 3]);
+			}
+			__syncthreads();
+			if (threadIdx.x == 0)
+				queue_n = 0;
+			__syncthreads();
 		}
 	}
 	report_invalid(bad, invalid_flag);
@@ -167,46 +260,72 @@ __global__ void __launch_bounds__(CTA_THREADS)
 decode_linear_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, int width, int height,
 int wib, int hib, uint32_t mode_mask, uint32_t flags, uint32_t *invalid_flag) {
 	using T = FormatTraits<F>;
-	constexpr int BW = T::BLOCK_WORDS, OW = T::OUT_WORDS, ROW_WORDS = OW / 4, ROW_BYTES = OW;
+	using D = DeferTraits<F>;
+	constexpr int BW = T::BLOCK_WORDS, OW = T::OUT_WORDS, ROW_BYTES = OW;
 	__shared__ BptcTables tables;
+	__shared__ uint32_t queue[D::ENABLED ? CTA_THREADS * DEFER_ITERS : 1];
+	__shared__ int queue_n;
+	const int tid = threadIdx.y * blockDim.x + threadIdx.x;
 	if constexpr (T::USES_TABLES) {
-		for (int i = threadIdx.y * blockDim.x + threadIdx.x; i < 64; i += blockDim.x * blockDim.y) {
+		for (int i = tid; i < 64; i += CTA_THREADS) {
 			tables.two[i] = bptc_two_global[i];
 			tables.three[i] = bptc_three_global[i];
 		}
-		__syncthreads();
 	}
+	if (tid == 0)
+		queue_n = 0;
+	if constexpr (T::USES_TABLES || D::ENABLED)
+		__syncthreads();
 	const int bx = blockIdx.x * blockDim.x + threadIdx.x;
 	const size_t pitch = (size_t)width * (ROW_BYTES / 4);		// bytes per image row
 	bool bad = false;
-	for (int by = blockIdx.y * blockDim.y + threadIdx.y; by < hib; by += gridDim.y * blockDim.y) {
-		if (bx >= wib)
-			continue;
-		const auto blk = BlockReg<BW>::load(src + ((size_t)by * wib + bx) * (BW * 4));
-		uint32_t px[OW];
-		if (!decode_block<F>(blk, mode_mask, flags, &tables, px)) {
-			bad = true;
-#pragma unroll
-			for (int k = 0; k < OW; k++)
-				px[k] = 0u;
-		}
-		uint8_t *out = dst + (size_t)by * 4 * pitch + (size_t)bx * ROW_BYTES;
-		const int rows = min(4, height - by * 4);		// clip the bottom edge (texture.c:117-120)
-#pragma unroll
-		for (int r = 0; r < 4; r++) {
-			if (r < rows) {
-				uint8_t *p = out + r * pitch;
-				if constexpr (ROW_WORDS == 1)
-					st_stream_u32(p, px[r]);
-				else if constexpr (ROW_WORDS == 2)
-					st_stream_v2(p, px[2 * r], px[2 * r + 1]);
-				else if constexpr (ROW_WORDS == 4)
-					st_stream_v4(p, px[4 * r], px[4 * r + 1], px[4 * r + 2], px[4 * r + 3]);
+	// CTA (bx tile, g) owns the ITERS strips of TY block rows starting at g*ITERS*TY; g grid-strides.
+	constexpr int ITERS = D::ENABLED ? DEFER_ITERS : 1;
+	const int rows_per_group = ITERS * blockDim.y;
+	for (int g = blockIdx.y; g * rows_per_group < hib; g += gridDim.y) {
+#pragma unroll 1
+		for (int k = 0; k < ITERS; k++) {
+			const int by = g * rows_per_group + k * blockDim.y + threadIdx.y;
+			if (bx < wib && by < hib) {
+				const auto blk = BlockReg<BW>::load(src + ((size_t)by * wib + bx) * (BW * 4));
+				bool rare = false;
+				if constexpr (D::ENABLED)
+					rare = D::is_rare(blk);
+				if (rare)
+					queue[atomicAdd(&queue_n, 1)] = (uint32_t)by * (uint32_t)wib + (uint32_t)bx;
 				else {
-					st_stream_v4(p, px[8 * r], px[8 * r + 1], px[8 * r + 2], px[8 * r + 3]);
-					st_stream_v4(p + 16, px[8 * r + 4], px[8 * r + 5], px[8 * r + 6], px[8 * r + 7]);
+					uint32_t px[OW];
+					if (!decode_block<F, D::ENABLED ? ETC_PATHS_NO_PLANAR : ETC_PATHS_ALL>(blk, mode_mask, flags, &tables, px)) {
+						bad = true;
+#pragma unroll
+						for (int j = 0; j < OW; j++)
+							px[j] = 0u;
+					}
+					store_linear_rows<OW>(dst, pitch, bx, by, height, px);
 				}
 			}
+		}
+		if constexpr (D::ENABLED) {
+			// drain the queue of rare (planar) blocks collected over the last ITERS strips
+			__syncthreads();
+			const int n_rare = queue_n;
+			for (int e = tid; e < n_rare; e += CTA_THREADS) {
+				const uint32_t j = queue[e];
+				const int qy = (int)(j / (uint32_t)wib), qx_ = (int)(j - (uint32_t)qy * (uint32_t)wib);
+				const auto blk = BlockReg<BW>::load(src + (size_t)j * (BW * 4));
+				uint32_t qp[OW];
+				if (!decode_block<F, ETC_PATHS_PLANAR_ONLY>(blk, mode_mask, flags, &tables, qp)) {
+					bad = true;
+#pragma unroll
+					for (int jj = 0; jj < OW; jj++)
+						qp[jj] = 0u;
+				}
+				store_linear_rows<OW>(dst, pitch, qx_, qy, height, qp);
+			}
+			__syncthreads();
+			if (tid == 0)
+				queue_n = 0;
+			__syncthreads();
 		}
 	}
 	report_invalid(bad, invalid_flag);
@@ -532,7 +651,8 @@ static cudaError_t launch_format(const DecodeArgs &a, cudaStream_t stream) {
 	if (a.layout == LAYOUT_TILED) {
 		const uint64_t tiles = (n_blocks + 31) / 32;
 		// enough CTAs to cover the work once, capped at a few waves of resident CTAs
-		const uint64_t want = (tiles + CTA_WARPS - 1) / CTA_WARPS;
+		const uint64_t per_cta = (uint64_t)CTA_WARPS * (DeferTraits<F>::ENABLED ? DEFER_ITERS : 1);
+		const uint64_t want = (tiles + per_cta - 1) / per_cta;
 		const uint64_t cap = (uint64_t)sm_count() * 8 * 16;
 		const unsigned grid = (unsigned)(want < cap ? want : cap);
 		decode_tiled_kernel<F><<<grid, CTA_THREADS, 0, stream>>>(src, dst, (uint32_t)n_blocks,
@@ -546,7 +666,8 @@ static cudaError_t launch_format(const DecodeArgs &a, cudaStream_t stream) {
 				tx *= 2;
 			const int ty = CTA_THREADS / tx;
 			dim3 block(tx, ty);
-			unsigned gy = (unsigned)((a.hib + ty - 1) / ty);
+			const int rows_per_cta = ty * (DeferTraits<F>::ENABLED ? DEFER_ITERS : 1);
+			unsigned gy = (unsigned)((a.hib + rows_per_cta - 1) / rows_per_cta);
 			if (gy > 65535u)
 				gy = 65535u;
 			dim3 grid((unsigned)((a.wib + tx - 1) / tx), gy);
