@@ -127,8 +127,11 @@ uint32_t pf, int layout, uint32_t mode_mask, uint32_t flags, uint32_t *d_invalid
 	a.mode_mask = mode_mask;
 	a.flags = flags;
 	a.invalid = d_invalid;
+	a.post_op = 0;
 	cudaError_t e;
-	if (pf == native) {
+	const int fuse = pf == native ? 1 : convert_fusable(native, pf);
+	if (fuse) {		// native layout, or an R<->B swap done in the kernels' store epilogue
+		a.post_op = fuse == 2 ? 1u : 0u;
 		a.pixels = d_pixels;
 		if ((e = launch_decode((int)(tf >> 24), a, stream)) != cudaSuccess)
 			return cuda_fail("decode kernel launch", e);
@@ -194,7 +197,7 @@ bool decode_texture_host(const detexTexture *t, uint8_t *pixel_buffer, uint32_t 
 	const int bb = block_bytes(tf), ps = pixel_size(pf), ps_native = pixel_size(native);
 	const size_t in_bytes = n_blocks * bb;
 	const size_t out_bytes = layout == DETEXB200_LAYOUT_LINEAR ? (size_t)t->width * t->height * ps : n_blocks * 16 * ps;
-	const size_t tmp_bytes = pf == native ? 0 : n_blocks * 16 * ps_native;
+	const size_t tmp_bytes = (pf == native || convert_fusable(native, pf)) ? 0 : n_blocks * 16 * ps_native;
 	if (!c.reserve(&c.d_in, &c.cap_in, in_bytes) || !c.reserve(&c.d_out, &c.cap_out, out_bytes + 16) ||
 	    (tmp_bytes && !c.reserve(&c.d_tmp, &c.cap_tmp, tmp_bytes)))
 		return false;
@@ -324,11 +327,11 @@ void *d_pixels, uint32_t pf, int layout, uint32_t mode_mask, uint32_t flags, uin
 	const uint32_t native = tf & 0xFFFF;
 	void *tmp = nullptr;
 	cudaStream_t s = (cudaStream_t)stream;
-	if (pf != native) {
-		if (!convert_supported(native, pf)) {
-			set_error("detexConvertPixels: Unable to find conversion path (0x%04X -> 0x%04X on device)", native, pf);
-			return DETEXB200_EUNSUPPORTED;
-		}
+	if (pf != native && !convert_supported(native, pf)) {
+		set_error("detexConvertPixels: Unable to find conversion path (0x%04X -> 0x%04X on device)", native, pf);
+		return DETEXB200_EUNSUPPORTED;
+	}
+	if (pf != native && !convert_fusable(native, pf)) {
 		cudaError_t e = cudaMallocAsync(&tmp, (size_t)wib * hib * 16 * pixel_size(native) + 16, s);
 		if (e != cudaSuccess)
 			return cuda_fail("cudaMallocAsync", e);

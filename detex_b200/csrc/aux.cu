@@ -33,6 +33,14 @@ static ConvertOp convert_op(uint32_t s, uint32_t d) {
 	return OP_NONE;
 }
 
+int convert_fusable(uint32_t s, uint32_t d) {
+	switch (convert_op(s, d)) {
+	case OP_COPY32: return 1;
+	case OP_SWAP32: case OP_SWAP64: return 2;
+	default: return 0;
+	}
+}
+
 bool convert_supported(uint32_t s, uint32_t d) {
 	return s == d || convert_op(s, d) != OP_NONE;
 }

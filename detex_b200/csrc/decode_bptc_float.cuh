@@ -177,7 +177,8 @@ const BptcTables &tab, uint32_t (&px)[32]) {
 				if (epb >= 16)
 					unq = x;
 				else {
-					unq = ((ax << 15) + 0x4000) >> (epb - 1);
+					// ((ax << 15) + 0x4000) >> (epb - 1) == (2*ax + 1) << (15 - epb) for epb <= 15
+					unq = (2 * ax + 1) << (15 - epb);
 					if (ax == 0)
 						unq = 0;
 					if (ax >= (1 << (epb - 1)) - 1)
@@ -187,7 +188,8 @@ const BptcTables &tab, uint32_t (&px)[32]) {
 				}
 			}
 			else {				// Unquantize, :52-62 (mode 13 <=> epb 16)
-				unq = ((x << 15) + 0x4000) >> (epb - 1);
+				// ((x << 15) + 0x4000) >> (epb - 1) == (2x + 1) << (15 - epb) for epb <= 15
+				unq = (int)((2u * (uint32_t)x + 1u) << ((15 - epb) & 31));
 				if (x == 0)
 					unq = 0;
 				if ((uint32_t)x == epmask)
@@ -212,14 +214,27 @@ const BptcTables &tab, uint32_t (&px)[32]) {
 		subset_bits = t & 0xFFFFu;
 		s = insert_zero_bit(s, (t >> 16) * IB + (IB - 1));
 	}
+	// endpoint pair of a pixel: X0 + bit*(X1 - X0) with multiply-adds (FMA pipe), as in the BC7 decoder
+	uint32_t da[3] = { 0u, 0u, 0u }, dk[3] = { 0u, 0u, 0u };
+	if constexpr (NS == 2) {
+#pragma unroll
+		for (int c = 0; c < 3; c++) {
+			da[c] = (uint32_t)(a_c[NS - 1][c] - a_c[0][c]);
+			dk[c] = (uint32_t)(k_c[NS - 1][c] - k_c[0][c]);
+		}
+	}
 #pragma unroll
 	for (int i = 0; i < 16; i++) {
-		const bool second = NS == 2 && ((subset_bits >> i) & 1u);
+		const uint32_t bit = NS == 2 ? ((subset_bits >> i) & 1u) : 0u;
 		const int wgt = (int)bptc_weight<IB>((uint32_t)(s >> (i * IB)) & ((1u << IB) - 1u));
 		uint32_t h[3];
 #pragma unroll
 		for (int c = 0; c < 3; c++) {
-			const int a = second ? a_c[NS - 1][c] : a_c[0][c], k = second ? k_c[NS - 1][c] : k_c[0][c];
+			int a = a_c[0][c], k = k_c[0][c];
+			if constexpr (NS == 2) {
+				a = (int)mad_u32(bit, da[c], (uint32_t)a);
+				k = (int)mad_u32(bit, dk[c], (uint32_t)k);
+			}
 			const int v = (a + wgt * k) >> 6;		// InterpolateFloat, :97-108 (Q18)
 			if (SIGNED) {					// :577-613
 				const int mag = ((v < 0 ? -v : v) * 31) >> 5;

@@ -31,13 +31,11 @@ __device__ __forceinline__ bool etc_overflow(int sum) { return (uint32_t)sum > 2
 
 // Mode selected by a block whose differential bit is set (decompress-etc.c:328-360).
 __device__ __forceinline__ uint32_t etc2_mode(uint32_t w0) {
-	if (etc_overflow(etc_diff_sum(w0 & 0xFFu)))
-		return ETC_T;
-	if (etc_overflow(etc_diff_sum((w0 >> 8) & 0xFFu)))
-		return ETC_H;
-	if (etc_overflow(etc_diff_sum((w0 >> 16) & 0xFFu)))
-		return ETC_PLANAR;
-	return ETC_DIFFERENTIAL;
+	// select chain, no control flow (see etc_palette_pixels)
+	const bool ov_r = etc_overflow(etc_diff_sum(w0 & 0xFFu));
+	const bool ov_g = etc_overflow(etc_diff_sum((w0 >> 8) & 0xFFu));
+	const bool ov_b = etc_overflow(etc_diff_sum((w0 >> 16) & 0xFFu));
+	return ov_r ? (uint32_t)ETC_T : (ov_g ? (uint32_t)ETC_H : (ov_b ? (uint32_t)ETC_PLANAR : (uint32_t)ETC_DIFFERENTIAL));
 }
 
 // 2-bit selector of stream pixel i: LSB = bit i, MSB = bit 16+i of the big-endian
@@ -81,42 +79,38 @@ __device__ __forceinline__ void etc_add_clamp(uint32_t rb, uint32_t ga, int m, u
 // block (modifier 0 for selectors 0 and 2, selector 2 -> transparent black, Q13).
 template <bool ALPHA>
 __device__ __forceinline__ void etc_palette_pixels(uint32_t w0, uint32_t idx, uint32_t mode, bool punch, uint32_t (&px)[16]) {
+	// Opaque to the optimiser: a caller that knows the mode on one of its paths (e.g. "differential
+	// bit clear -> individual") would otherwise get a specialised clone of this whole function on
+	// that path, and warps holding both kinds of block would execute both clones.
+	asm volatile("" : "+r"(mode));
 	const uint32_t b0 = w0 & 0xFFu, b1 = (w0 >> 8) & 0xFFu, b2 = (w0 >> 16) & 0xFFu, b3 = w0 >> 24;
 	const bool is_t = mode == ETC_T, is_h = mode == ETC_H, is_th = is_t || is_h;
+	// Everything below is straight-line code: both variants of every mode-dependent quantity are
+	// computed and one is picked with a select, so a warp with mixed modes runs it exactly once.
+	// (With if/else on the mode the compiler clones the whole pixel loop per branch and a mixed
+	// warp then executes it once per mode present -- measured 2.7x the instructions.)
 	// -- sub-block base colours as packed bytes R, G, B (three channels at once)
 	const uint32_t w = w0 & 0x00FFFFFFu;
-	uint32_t base0, base1;
-	if (mode == ETC_DIFFERENTIAL) {
-		// 5-bit base + 3-bit signed delta per byte.  The byte-parallel sum is evaluated modulo 2^32;
-		// whenever this mode is really selected no channel overflows (every byte of the true
-		// result is in [0,248]), so carries between bytes cancel and the word is exact.
-		const uint32_t v1 = w & 0xF8F8F8u, d3 = w & 0x070707u;
-		const uint32_t v2 = v1 + (d3 << 3) - ((d3 & 0x040404u) << 4);
-		base0 = v1 | ((v1 >> 5) & 0x070707u);
-		base1 = v2 | ((v2 >> 5) & 0x070707u);
-	}
-	else {
-		base0 = (w & 0xF0F0F0u) | ((w >> 4) & 0x0F0F0Fu);
-		base1 = (w & 0x0F0F0Fu) * 17u;
-	}
+	// differential: 5-bit base + 3-bit signed delta per byte.  The byte-parallel sum is evaluated
+	// modulo 2^32; whenever this mode is really selected no channel overflows (every byte of the
+	// true result is in [0,248]), so carries between bytes cancel and the word is exact.
+	const uint32_t v1 = w & 0xF8F8F8u, d3 = w & 0x070707u;
+	const uint32_t v2 = v1 + (d3 << 3) - ((d3 & 0x040404u) << 4);
+	const bool differential = mode == ETC_DIFFERENTIAL;
+	const uint32_t base0 = differential ? (v1 | ((v1 >> 5) & 0x070707u)) : ((w & 0xF0F0F0u) | ((w >> 4) & 0x0F0F0Fu));
+	const uint32_t base1 = differential ? (v2 | ((v2 >> 5) & 0x070707u)) : ((w & 0x0F0F0Fu) * 17u);
 	// -- T / H base colours (4-bit channels replicated to 8 bits) and distance
-	uint32_t c1, c2, dist;
-	if (is_h) {
-		const uint32_t r1 = (b0 & 0x78u) >> 3, g1 = ((b0 & 0x07u) << 1) | ((b1 & 0x10u) >> 4);
-		const uint32_t bl1 = (b1 & 0x08u) | ((b1 & 0x03u) << 1) | (b2 >> 7);
-		const uint32_t r2 = (b2 & 0x78u) >> 3, g2 = ((b2 & 0x07u) << 1) | (b3 >> 7), bl2 = (b3 & 0x78u) >> 3;
-		// ordering of the replicated 24-bit colours == ordering of the 12-bit nibble triples
-		const bool ge = ((r1 << 8) | (g1 << 4) | bl1) >= ((r2 << 8) | (g2 << 4) | bl2);
-		dist = etc2_distance((b3 & 0x04u) | ((b3 & 0x01u) << 1) | (ge ? 1u : 0u));
-		c1 = (r1 | (g1 << 8) | (bl1 << 16)) * 17u;
-		c2 = (r2 | (g2 << 8) | (bl2 << 16)) * 17u;
-	}
-	else {
-		const uint32_t r1 = ((b0 & 0x18u) >> 1) | (b0 & 0x3u);
-		dist = etc2_distance(((b3 & 0x0Cu) >> 1) | (b3 & 1u));
-		c1 = (r1 | ((b1 >> 4) << 8) | ((b1 & 0xFu) << 16)) * 17u;
-		c2 = ((b2 >> 4) | ((b2 & 0xFu) << 8) | ((b3 >> 4) << 16)) * 17u;
-	}
+	const uint32_t h_r1 = (b0 & 0x78u) >> 3, h_g1 = ((b0 & 0x07u) << 1) | ((b1 & 0x10u) >> 4);
+	const uint32_t h_b1 = (b1 & 0x08u) | ((b1 & 0x03u) << 1) | (b2 >> 7);
+	const uint32_t h_r2 = (b2 & 0x78u) >> 3, h_g2 = ((b2 & 0x07u) << 1) | (b3 >> 7), h_b2 = (b3 & 0x78u) >> 3;
+	// ordering of the replicated 24-bit colours == ordering of the 12-bit nibble triples
+	const uint32_t h_ge = ((h_r1 << 8) | (h_g1 << 4) | h_b1) >= ((h_r2 << 8) | (h_g2 << 4) | h_b2) ? 1u : 0u;
+	const uint32_t t_r1 = ((b0 & 0x18u) >> 1) | (b0 & 0x3u);
+	const uint32_t dist_index = is_h ? ((b3 & 0x04u) | ((b3 & 0x01u) << 1) | h_ge) : (((b3 & 0x0Cu) >> 1) | (b3 & 1u));
+	const uint32_t dist = etc2_distance(dist_index);
+	const uint32_t n1 = is_h ? (h_r1 | (h_g1 << 8) | (h_b1 << 16)) : (t_r1 | ((b1 >> 4) << 8) | ((b1 & 0xFu) << 16));
+	const uint32_t n2 = is_h ? (h_r2 | (h_g2 << 8) | (h_b2 << 16)) : ((b2 >> 4) | ((b2 & 0xFu) << 8) | ((b3 >> 4) << 16));
+	const uint32_t c1 = n1 * 17u, c2 = n2 * 17u;
 	// -- the eight palette colours -> per-channel byte tables (entry n = g*4 + s)
 	uint32_t tab_rb[2][2], tab_ga[2][2];	// [g][pair]: bytes (R_s, R_s+1, B_s, B_s+1) / (G.., A..)
 #pragma unroll
@@ -232,7 +226,8 @@ template <int PATHS = ETC_PATHS_ALL>
 __device__ __forceinline__ bool decode_etc2(const uint2 blk, uint32_t mode_mask, uint32_t, uint32_t (&px)[16]) {
 	const uint32_t idx = bswap32(blk.y);
 	const bool differential_bit = (blk.x >> 24) & 2u;
-	const uint32_t mode = differential_bit ? etc2_mode(blk.x) : (uint32_t)ETC_INDIVIDUAL;
+	const uint32_t mode_if_diff = etc2_mode(blk.x);
+	const uint32_t mode = differential_bit ? mode_if_diff : (uint32_t)ETC_INDIVIDUAL;
 	if (PATHS != ETC_PATHS_NO_PLANAR && (PATHS == ETC_PATHS_PLANAR_ONLY || mode == ETC_PLANAR))
 		etc2_planar(blk.x, blk.y, px);
 	else if (PATHS != ETC_PATHS_PLANAR_ONLY)

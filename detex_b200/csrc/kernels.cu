@@ -85,6 +85,29 @@ uint32_t mode_mask, uint32_t flags, const BptcTables *tab, uint32_t (&px)[Format
 	else return decode_eac_rg11<true>(blk, mode_mask, flags, px);
 }
 
+// Output-format conversion fused into the store epilogue: R <-> B swap of
+// 32-bit RGBA8/RGBX8 pixels (-> BGRA8/BGRX8, reference convert.c:37-52) or of 64-bit
+// FLOAT_RGBX16 pixels (-> FLOAT_BGRX16, convert.c:54-70).  post_op is uniform over the launch.
+constexpr uint32_t POST_NONE = 0, POST_SWAP_RB = 1;
+template <int OW>
+__device__ __forceinline__ void apply_post_op(uint32_t (&px)[OW], uint32_t post_op) {
+	if (post_op == POST_SWAP_RB) {
+		if constexpr (OW == 16) {
+#pragma unroll
+			for (int k = 0; k < 16; k++)
+				px[k] = prmt(px[k], 0u, 0x3012);
+		}
+		else if constexpr (OW == 32) {
+#pragma unroll
+			for (int k = 0; k < 16; k++) {
+				const uint32_t lo = px[2 * k], hi = px[2 * k + 1];		// R|G<<16, B|X<<16
+				px[2 * k] = prmt(lo, hi, 0x3254);				// B|G<<16
+				px[2 * k + 1] = prmt(lo, hi, 0x7610);				// R|X<<16
+			}
+		}
+	}
+}
+
 constexpr int CTA_THREADS = 256;
 constexpr int CTA_WARPS = CTA_THREADS / 32;
 
@@ -150,7 +173,7 @@ __device__ __forceinline__ void store_linear_rows(uint8_t *dst, size_t pitch, in
 template <int F>
 __global__ void __launch_bounds__(CTA_THREADS)
 decode_tiled_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, uint32_t n_blocks,
-uint32_t mode_mask, uint32_t flags, uint32_t *invalid_flag) {
+uint32_t mode_mask, uint32_t flags, uint32_t post_op, uint32_t *invalid_flag) {
 	using T = FormatTraits<F>;
 	using D = DeferTraits<F>;
 	constexpr int BW = T::BLOCK_WORDS, OW = T::OUT_WORDS, CHUNKS = OW / 4;
@@ -188,6 +211,7 @@ uint32_t mode_mask, uint32_t flags, uint32_t *invalid_flag) {
 			for (int k = 0; k < OW; k++)
 				px[k] = 0u;
 		}
+		apply_post_op<OW>(px, post_op);
 		const unsigned rare_mask = D::ENABLED ? __ballot_sync(0xFFFFFFFFu, rare) : 0u;
 		if (tile < n_tiles) {
 			uint8_t *tile_out = dst + (size_t)first * (OW * 4);
@@ -238,6 +262,7 @@ uint32_t mode_mask, uint32_t flags, uint32_t *invalid_flag) {
 					for (int k = 0; k < OW; k++)
 						qx[k] = 0u;
 				}
+				apply_post_op<OW>(qx, post_op);
 				uint8_t *out = dst + (size_t)j * (OW * 4);
 #pragma unroll
 				for (int c = 0; c < CHUNKS; c++)
@@ -258,7 +283,7 @@ uint32_t mode_mask, uint32_t flags, uint32_t *invalid_flag) {
 template <int F>
 __global__ void __launch_bounds__(CTA_THREADS)
 decode_linear_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, int width, int height,
-int wib, int hib, uint32_t mode_mask, uint32_t flags, uint32_t *invalid_flag) {
+int wib, int hib, uint32_t mode_mask, uint32_t flags, uint32_t post_op, uint32_t *invalid_flag) {
 	using T = FormatTraits<F>;
 	using D = DeferTraits<F>;
 	constexpr int BW = T::BLOCK_WORDS, OW = T::OUT_WORDS, ROW_BYTES = OW;
@@ -301,6 +326,7 @@ int wib, int hib, uint32_t mode_mask, uint32_t flags, uint32_t *invalid_flag) {
 						for (int j = 0; j < OW; j++)
 							px[j] = 0u;
 					}
+					apply_post_op<OW>(px, post_op);
 					store_linear_rows<OW>(dst, pitch, bx, by, height, px);
 				}
 			}
@@ -320,6 +346,7 @@ int wib, int hib, uint32_t mode_mask, uint32_t flags, uint32_t *invalid_flag) {
 					for (int jj = 0; jj < OW; jj++)
 						qp[jj] = 0u;
 				}
+				apply_post_op<OW>(qp, post_op);
 				store_linear_rows<OW>(dst, pitch, qx_, qy, height, qp);
 			}
 			__syncthreads();
@@ -335,7 +362,7 @@ int wib, int hib, uint32_t mode_mask, uint32_t flags, uint32_t *invalid_flag) {
 template <int F>
 __global__ void __launch_bounds__(CTA_THREADS)
 decode_linear_clipped_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, int width, int height,
-int wib, int hib, uint32_t mode_mask, uint32_t flags, uint32_t *invalid_flag) {
+int wib, int hib, uint32_t mode_mask, uint32_t flags, uint32_t post_op, uint32_t *invalid_flag) {
 	using T = FormatTraits<F>;
 	constexpr int BW = T::BLOCK_WORDS, OW = T::OUT_WORDS, PS = OW / 4;	// PS = bytes per pixel
 	__shared__ BptcTables tables;
@@ -355,6 +382,7 @@ int wib, int hib, uint32_t mode_mask, uint32_t flags, uint32_t *invalid_flag) {
 			for (int k = 0; k < OW; k++)
 				px[k] = 0u;
 		}
+		apply_post_op<OW>(px, post_op);
 		const int rows = min(4, height - by * 4), cols = min(4, width - bx * 4);
 #pragma unroll
 		for (int r = 0; r < 4; r++)
@@ -454,7 +482,7 @@ __device__ __forceinline__ uint32_t raw_slot(uint32_t id) { return id ^ ((id >> 
 template <int F, int LAYOUT>
 __global__ void __launch_bounds__(SORT_THREADS, 2)
 decode_sorted_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, uint32_t n_blocks, int width,
-int height, int wib, uint32_t mode_mask, uint32_t flags, uint32_t *invalid_flag) {
+int height, int wib, uint32_t mode_mask, uint32_t flags, uint32_t post_op, uint32_t *invalid_flag) {
 	using T = FormatTraits<F>;
 	using S = SortTraits<F>;
 	using SM = SortedSmem<F>;
@@ -546,6 +574,7 @@ int height, int wib, uint32_t mode_mask, uint32_t flags, uint32_t *invalid_flag)
 					for (int k = 0; k < OW; k++)
 						px[k] = 0u;
 				}
+				apply_post_op<OW>(px, post_op);
 #pragma unroll
 				for (int c = 0; c < CHUNKS; c++)
 					sm.out[stage_slot<TB, CHUNKS>(id, c)] = make_uint4(px[4 * c], px[4 * c + 1], px[4 * c + 2], px[4 * c + 3]);
@@ -640,10 +669,10 @@ static cudaError_t launch_format(const DecodeArgs &a, cudaStream_t stream) {
 			}
 			if (a.layout == LAYOUT_TILED)
 				decode_sorted_kernel<F, LAYOUT_TILED><<<grid, SORT_THREADS, smem, stream>>>(src, dst, (uint32_t)n_blocks,
-					a.width, a.height, a.wib, a.mode_mask, a.flags, a.invalid);
+					a.width, a.height, a.wib, a.mode_mask, a.flags, a.post_op, a.invalid);
 			else
 				decode_sorted_kernel<F, LAYOUT_LINEAR><<<grid, SORT_THREADS, smem, stream>>>(src, dst, (uint32_t)n_blocks,
-					a.width, a.height, a.wib, a.mode_mask, a.flags, a.invalid);
+					a.width, a.height, a.wib, a.mode_mask, a.flags, a.post_op, a.invalid);
 			count_launch();
 			return cudaGetLastError();
 		}
@@ -656,7 +685,7 @@ static cudaError_t launch_format(const DecodeArgs &a, cudaStream_t stream) {
 		const uint64_t cap = (uint64_t)sm_count() * 8 * 16;
 		const unsigned grid = (unsigned)(want < cap ? want : cap);
 		decode_tiled_kernel<F><<<grid, CTA_THREADS, 0, stream>>>(src, dst, (uint32_t)n_blocks,
-			a.mode_mask, a.flags, a.invalid);
+			a.mode_mask, a.flags, a.post_op, a.invalid);
 	}
 	else {
 		const bool fast = (a.width % 4 == 0) && aligned_out;
@@ -672,14 +701,14 @@ static cudaError_t launch_format(const DecodeArgs &a, cudaStream_t stream) {
 				gy = 65535u;
 			dim3 grid((unsigned)((a.wib + tx - 1) / tx), gy);
 			decode_linear_kernel<F><<<grid, block, 0, stream>>>(src, dst, a.width, a.height, a.wib, a.hib,
-				a.mode_mask, a.flags, a.invalid);
+				a.mode_mask, a.flags, a.post_op, a.invalid);
 		}
 		else {
 			const uint64_t want = (n_blocks + CTA_THREADS - 1) / CTA_THREADS;
 			const uint64_t cap = (uint64_t)sm_count() * 8 * 16;
 			const unsigned grid = (unsigned)(want < cap ? want : cap);
 			decode_linear_clipped_kernel<F><<<grid, CTA_THREADS, 0, stream>>>(src, dst, a.width, a.height,
-				a.wib, a.hib, a.mode_mask, a.flags, a.invalid);
+				a.wib, a.hib, a.mode_mask, a.flags, a.post_op, a.invalid);
 		}
 	}
 	count_launch();

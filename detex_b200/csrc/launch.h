@@ -14,6 +14,7 @@ struct DecodeArgs {
 	int wib, hib;		// blocks
 	int layout;
 	uint32_t mode_mask, flags;
+	uint32_t post_op;	// 0 none, 1 R<->B swap fused into the store (32- and 64-bit pixels)
 	uint32_t *invalid;	// device flag word or nullptr
 };
 
@@ -23,6 +24,9 @@ cudaError_t launch_decode(int format_index, const DecodeArgs &args, cudaStream_t
 // Pixel-format conversion on device (aux.cu); returns cudaErrorNotSupported for pairs
 // that are not implemented.
 bool convert_supported(uint32_t source_pixel_format, uint32_t target_pixel_format);
+// 0: the pair needs a separate conversion pass; 1: identical memory layout (X <-> A of the same
+// component order, a no-op); 2: R <-> B swap that the decode kernels fuse into their stores.
+int convert_fusable(uint32_t source_pixel_format, uint32_t target_pixel_format);
 cudaError_t launch_convert(const void *src, uint64_t nu_pixels, uint32_t source_pixel_format,
 	void *dst, uint32_t target_pixel_format, cudaStream_t stream);
 
