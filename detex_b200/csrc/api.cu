@@ -207,47 +207,63 @@ bool decode_texture_host(const detexTexture *t, uint8_t *pixel_buffer, uint32_t 
 		cuda_fail(who, e);
 		return false;
 	}
-	// Slabs of whole block rows, about 16 MiB of output each, at least one row.
-	const size_t out_row_bytes = layout == DETEXB200_LAYOUT_LINEAR ? (size_t)t->width * 4 * ps : (size_t)wib * 16 * ps;
-	int rows_per_slab = (int)((16u << 20) / (out_row_bytes ? out_row_bytes : 1));
-	if (rows_per_slab < 1)
-		rows_per_slab = 1;
+	// Slabs of about 16 MiB of output each: whole block rows for LINEAR (at least one row), any
+	// run of consecutive blocks for TILED (a multiple of 1024 so that slabs stay 16-byte aligned
+	// and tile-aligned for the sorted kernels).
 	int rc = DETEXB200_OK;
 	int k = 0;
-	for (int r0 = 0; r0 < hib && rc == DETEXB200_OK; r0 += rows_per_slab, k++) {
-		const int rows = (hib - r0) < rows_per_slab ? (hib - r0) : rows_per_slab;
-		cudaStream_t s = c.streams[k % N_STREAMS];
-		const size_t in_off = (size_t)r0 * wib * bb, in_len = (size_t)rows * wib * bb;
-		size_t out_off, out_len, tmp_off;
-		int slab_h;
-		if (layout == DETEXB200_LAYOUT_LINEAR) {
-			slab_h = t->height - r0 * 4;
+	if (layout == DETEXB200_LAYOUT_LINEAR) {
+		const size_t out_row_bytes = (size_t)t->width * 4 * ps;
+		int rows_per_slab = (int)((16u << 20) / (out_row_bytes ? out_row_bytes : 1));
+		if (rows_per_slab < 1)
+			rows_per_slab = 1;
+		for (int r0 = 0; r0 < hib && rc == DETEXB200_OK; r0 += rows_per_slab, k++) {
+			const int rows = (hib - r0) < rows_per_slab ? (hib - r0) : rows_per_slab;
+			cudaStream_t s = c.streams[k % N_STREAMS];
+			const size_t in_off = (size_t)r0 * wib * bb, in_len = (size_t)rows * wib * bb;
+			int slab_h = t->height - r0 * 4;
 			if (slab_h > rows * 4)
 				slab_h = rows * 4;
 			if (slab_h < 0)
 				slab_h = 0;
-			out_off = (size_t)r0 * 4 * t->width * ps;
-			out_len = (size_t)slab_h * t->width * ps;
-			tmp_off = (size_t)r0 * 4 * t->width * ps_native;
+			const size_t out_off = (size_t)r0 * 4 * t->width * ps, out_len = (size_t)slab_h * t->width * ps;
+			const size_t tmp_off = (size_t)r0 * 4 * t->width * ps_native;
+			if ((e = cudaMemcpyAsync((uint8_t *)c.d_in + in_off, t->data + in_off, in_len, cudaMemcpyHostToDevice, s)) != cudaSuccess) {
+				rc = cuda_fail("host to device copy", e);
+				break;
+			}
+			rc = enqueue_decode(tf, (uint8_t *)c.d_in + in_off, t->width, slab_h, wib, rows, (uint8_t *)c.d_out + out_off, pf,
+				layout, DETEX_MODE_MASK_ALL, 0, c.d_flag, tmp_bytes ? (uint8_t *)c.d_tmp + tmp_off : nullptr, s);
+			if (rc != DETEXB200_OK)
+				break;
+			if (out_len && (e = cudaMemcpyAsync(pixel_buffer + out_off, (uint8_t *)c.d_out + out_off, out_len,
+					cudaMemcpyDeviceToHost, s)) != cudaSuccess) {
+				rc = cuda_fail("device to host copy", e);
+				break;
+			}
 		}
-		else {
-			slab_h = rows * 4;
-			out_off = (size_t)r0 * wib * 16 * ps;
-			out_len = (size_t)rows * wib * 16 * ps;
-			tmp_off = (size_t)r0 * wib * 16 * ps_native;
-		}
-		if ((e = cudaMemcpyAsync((uint8_t *)c.d_in + in_off, t->data + in_off, in_len, cudaMemcpyHostToDevice, s)) != cudaSuccess) {
-			rc = cuda_fail("host to device copy", e);
-			break;
-		}
-		rc = enqueue_decode(tf, (uint8_t *)c.d_in + in_off, t->width, slab_h, wib, rows, (uint8_t *)c.d_out + out_off, pf,
-			layout, DETEX_MODE_MASK_ALL, 0, c.d_flag, tmp_bytes ? (uint8_t *)c.d_tmp + tmp_off : nullptr, s);
-		if (rc != DETEXB200_OK)
-			break;
-		if (out_len && (e = cudaMemcpyAsync(pixel_buffer + out_off, (uint8_t *)c.d_out + out_off, out_len,
-				cudaMemcpyDeviceToHost, s)) != cudaSuccess) {
-			rc = cuda_fail("device to host copy", e);
-			break;
+	}
+	else {
+		uint64_t per_slab = ((16u << 20) / (16u * ps)) & ~1023ull;
+		if (per_slab < 1024)
+			per_slab = 1024;
+		for (uint64_t b0 = 0; b0 < n_blocks && rc == DETEXB200_OK; b0 += per_slab, k++) {
+			const uint64_t count = (n_blocks - b0) < per_slab ? (n_blocks - b0) : per_slab;
+			cudaStream_t s = c.streams[k % N_STREAMS];
+			const size_t in_off = (size_t)b0 * bb, out_off = (size_t)b0 * 16 * ps, tmp_off = (size_t)b0 * 16 * ps_native;
+			if ((e = cudaMemcpyAsync((uint8_t *)c.d_in + in_off, t->data + in_off, (size_t)count * bb, cudaMemcpyHostToDevice, s)) != cudaSuccess) {
+				rc = cuda_fail("host to device copy", e);
+				break;
+			}
+			rc = enqueue_decode(tf, (uint8_t *)c.d_in + in_off, (int)count * 4, 4, (int)count, 1, (uint8_t *)c.d_out + out_off, pf,
+				layout, DETEX_MODE_MASK_ALL, 0, c.d_flag, tmp_bytes ? (uint8_t *)c.d_tmp + tmp_off : nullptr, s);
+			if (rc != DETEXB200_OK)
+				break;
+			if ((e = cudaMemcpyAsync(pixel_buffer + out_off, (uint8_t *)c.d_out + out_off, (size_t)count * 16 * ps,
+					cudaMemcpyDeviceToHost, s)) != cudaSuccess) {
+				rc = cuda_fail("device to host copy", e);
+				break;
+			}
 		}
 	}
 	for (int i = 0; i < N_STREAMS; i++)

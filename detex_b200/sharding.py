@@ -26,7 +26,7 @@ def linear_shard(height_in_blocks, rank, world):
 
 def linear_shard_view(width, height, width_in_blocks, height_in_blocks, block_bytes, pixel_bytes, rank, world):
     """Byte offsets and sizes of rank's slab: dict(row_lo, rows, height, in_offset, in_bytes,
-    out_offset, out_bytes) -- the same view arithmetic as the CPU harness (oracle/cpu_harness.c)
+    out_offset, out_bytes) -- the same view arithmetic as the row-sharded CPU baseline driver
     and the host shim's slab pipeline (detex_b200/csrc/api.cu)."""
     r0, r1 = linear_shard(height_in_blocks, rank, world)
     h = max(0, min(height - r0 * 4, (r1 - r0) * 4))

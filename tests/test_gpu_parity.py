@@ -312,6 +312,23 @@ def test_config_bc6h_8192(cpu):
     _full_size("BPTC_FLOAT", 8192, 8192, cpu, forced=14)
 
 
+def test_host_api_tiled_multi_slab(cpu):
+    """Flat block arrays through detexDecompressTextureTiled are cut into block-range slabs
+    (not rows): 1.5M EAC_RG11 blocks given as one 'row' of blocks -> several pipelined slabs."""
+    fmt = "EAC_RG11"
+    n = 1_500_000 + 37
+    b = H.synth_blocks(fmt, n, seed=4)
+    tf, bs, ps = H.FORMATS[fmt]
+    out = np.zeros(n * 16 * ps, dtype=np.uint8)
+    tex = D.DetexTexture(tf, b.ctypes.data, 4 * n, 4, n, 1)
+    ok = D.load().detexDecompressTextureTiled(C.byref(tex), out.ctypes.data, tf & 0xFFFF)
+    want, ok_w, _ = H.cpu_decode(cpu, fmt, b[: (n - 37) * bs], 4 * 1000, 4 * ((n - 37) // 1000), linear=False, threads=16)
+    assert ok == ok_w
+    assert np.array_equal(out[: want.size], want)
+    tail, _, _ = H.cpu_decode(cpu, fmt, b[(n - 37) * bs:], 4 * 37, 4, linear=False)
+    assert np.array_equal(out[want.size:], tail)
+
+
 def test_config_mixed_tiled_reduced(cpu):
     """configs[4] at 1/50 scale per format (2e6 blocks each), TILED layout, per-shard tree hashes
     computed on the device against the same construction on the host."""
