@@ -179,9 +179,10 @@ __device__ __forceinline__ bool decode_rgtc2(const uint4 blk, uint32_t, uint32_t
 // One signed channel.  Endpoints are int8 with -128 clamped to -127; (-127,-128)
 // is invalid; interpolation divides truncating toward zero (C '/' == the
 // reference's LUT * sign, detex.h:966-982); each value v in [-127,127] maps to
-// (v+127)*65535/254 - 32768 (Q5, decompress-rgtc.c:84-130).  out16[i] = 16-bit
-// result of pixel i.
-__device__ __forceinline__ bool rgtc_channel_s16(uint32_t w0, uint32_t w1, uint32_t (&out16)[16]) {
+// (v+127)*65535/254 - 32768 (Q5, decompress-rgtc.c:84-130).  The eight 16-bit results are
+// computed once, split into a low-byte and a high-byte table and looked up four pixels at a
+// time.  rows[y][0] = pixels x=0,1 of row y (16 bits each), rows[y][1] = pixels x=2,3.
+__device__ __forceinline__ bool rgtc_channel_s16(uint32_t w0, uint32_t w1, uint32_t (&rows)[4][2]) {
 	int l0 = (int)(int8_t)(w0 & 0xFFu), l1 = (int)(int8_t)((w0 >> 8) & 0xFFu);
 	const bool valid = !(l0 == -127 && l1 == -128);
 	l0 = max(l0, -127);
@@ -192,52 +193,62 @@ __device__ __forceinline__ bool rgtc_channel_s16(uint32_t w0, uint32_t w1, uint3
 	v[1] = l1;
 	const int step = l1 - l0;
 	int t = (seven ? 6 : 4) * l0 + l1;
+	// t / 7 resp. t / 5 truncating toward zero: |t| <= 889, so |t|/7 == (|t|*9363)>>16 and
+	// |t|/5 == (|t|*13108)>>16 (checked exhaustively over all endpoint pairs); sign restored.
+	const uint32_t m = seven ? 9363u : 13108u;
 #pragma unroll
 	for (int k = 2; k < 8; k++) {
-		v[k] = seven ? t / 7 : t / 5;
+		const int sgn = t >> 31;
+		const int q = (int)(((uint32_t)((t ^ sgn) - sgn) * m) >> 16);
+		v[k] = (q ^ sgn) - sgn;
 		t += step;
 	}
 	if (!seven) {
 		v[6] = -127;
 		v[7] = 127;
 	}
-	// Pre-map the eight ramp entries to biased bytes u = v + 127 in [0,254] and look
-	// pixels up with byte permutes, then expand each byte to 16 bits.
-	const uint32_t lo = (uint32_t)(v[0] + 127) | ((uint32_t)(v[1] + 127) << 8) |
-		((uint32_t)(v[2] + 127) << 16) | ((uint32_t)(v[3] + 127) << 24);
-	const uint32_t hi = (uint32_t)(v[4] + 127) | ((uint32_t)(v[5] + 127) << 8) |
-		((uint32_t)(v[6] + 127) << 16) | ((uint32_t)(v[7] + 127) << 24);
+	uint32_t e[8];
+#pragma unroll
+	for (int k = 0; k < 8; k++)
+		e[k] = (((uint32_t)(v[k] + 127) * 65535u) / 254u - 32768u) & 0xFFFFu;
+	const uint32_t e01 = e[0] | (e[1] << 16), e23 = e[2] | (e[3] << 16), e45 = e[4] | (e[5] << 16), e67 = e[6] | (e[7] << 16);
+	const uint32_t l_lo = prmt(e01, e23, 0x6420), l_hi = prmt(e45, e67, 0x6420);	// low bytes, byte k = entry k
+	const uint32_t h_lo = prmt(e01, e23, 0x7531), h_hi = prmt(e45, e67, 0x7531);	// high bytes
 	const uint32_t s_lo = __funnelshift_r(w0, w1, 16), s_hi = w1 >> 16;
 #pragma unroll
 	for (int r = 0; r < 4; r++) {
-		const uint32_t u4 = prmt(lo, hi, row_selector(s_lo, s_hi, r));
-#pragma unroll
-		for (int x = 0; x < 4; x++) {
-			const uint32_t u = (u4 >> (8 * x)) & 0xFFu;
-			out16[4 * r + x] = ((u * 65535u) / 254u - 32768u) & 0xFFFFu;
-		}
+		const uint32_t sel = row_selector(s_lo, s_hi, r);
+		const uint32_t l4 = prmt(l_lo, l_hi, sel), h4 = prmt(h_lo, h_hi, sel);	// byte x = pixel x
+		rows[r][0] = prmt(l4, h4, 0x5140);		// pixel 0 | pixel 1 << 16
+		rows[r][1] = prmt(l4, h4, 0x7362);		// pixel 2 | pixel 3 << 16
 	}
 	return valid;
 }
 
 // SIGNED_RGTC1 -> SIGNED_R16 (8 words).  decompress-rgtc.c:134-137.
 __device__ __forceinline__ bool decode_signed_rgtc1(const uint2 blk, uint32_t, uint32_t, uint32_t (&px)[8]) {
-	uint32_t h[16];
-	const bool ok = rgtc_channel_s16(blk.x, blk.y, h);
+	uint32_t rows[4][2];
+	const bool ok = rgtc_channel_s16(blk.x, blk.y, rows);
 #pragma unroll
-	for (int i = 0; i < 8; i++)
-		px[i] = h[2 * i] | (h[2 * i + 1] << 16);
+	for (int r = 0; r < 4; r++) {
+		px[2 * r] = rows[r][0];
+		px[2 * r + 1] = rows[r][1];
+	}
 	return ok;
 }
 
 // SIGNED_RGTC2 -> SIGNED_RG16 (16 words).  decompress-rgtc.c:141-147.
 __device__ __forceinline__ bool decode_signed_rgtc2(const uint4 blk, uint32_t, uint32_t, uint32_t (&px)[16]) {
-	uint32_t r[16], g[16];
+	uint32_t r[4][2], g[4][2];
 	const bool ok_r = rgtc_channel_s16(blk.x, blk.y, r);
 	const bool ok_g = rgtc_channel_s16(blk.z, blk.w, g);
 #pragma unroll
-	for (int i = 0; i < 16; i++)
-		px[i] = r[i] | (g[i] << 16);
+	for (int y = 0; y < 4; y++) {
+		px[4 * y + 0] = prmt(r[y][0], g[y][0], 0x5410);
+		px[4 * y + 1] = prmt(r[y][0], g[y][0], 0x7632);
+		px[4 * y + 2] = prmt(r[y][1], g[y][1], 0x5410);
+		px[4 * y + 3] = prmt(r[y][1], g[y][1], 0x7632);
+	}
 	return ok_r && ok_g;
 }
 
