@@ -46,6 +46,7 @@ constexpr int N_STREAMS = 4;
 
 struct Context {
 	bool ready = false, failed = false;
+	int device = -1;			// the context (streams, buffers) belongs to this device
 	cudaStream_t streams[N_STREAMS] = {};
 	void *d_in = nullptr, *d_out = nullptr, *d_tmp = nullptr;
 	size_t cap_in = 0, cap_out = 0, cap_tmp = 0;
@@ -54,8 +55,14 @@ struct Context {
 	void *h_small = nullptr;		// pinned scratch for single-block calls (512 bytes)
 
 	bool init() {
-		if (ready)
-			return true;
+		if (ready) {
+			int cur = -1;
+			if (cudaGetDevice(&cur) == cudaSuccess && cur == device)
+				return true;
+			set_error("detex_b200: calling thread switched CUDA device (%d -> %d); the host-pointer API keeps "
+				"one device per thread", device, cur);
+			return false;
+		}
 		if (failed)
 			return false;
 		int n = 0;
@@ -66,6 +73,7 @@ struct Context {
 			failed = true;
 			return false;
 		}
+		cudaGetDevice(&device);
 		for (int i = 0; i < N_STREAMS; i++)
 			if ((e = cudaStreamCreateWithFlags(&streams[i], cudaStreamNonBlocking)) != cudaSuccess) {
 				cuda_fail("cudaStreamCreate", e);

@@ -54,9 +54,6 @@ __device__ __forceinline__ void st_stream_u32(void *p, uint32_t a) {
 }
 
 // ---- bit helpers ---------------------------------------------------------------
-__device__ __forceinline__ uint32_t bfe(uint32_t v, int pos, int len) {
-	return (v >> pos) & ((1u << len) - 1u);
-}
 __device__ __forceinline__ int bfe_s(uint32_t v, int pos, int len) {	// sign-extending
 	return ((int)(v << (32 - pos - len))) >> (32 - len);
 }
@@ -65,9 +62,6 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
 }
 __device__ __forceinline__ uint32_t bswap32(uint32_t v) {
 	return __byte_perm(v, 0, 0x0123);
-}
-__device__ __forceinline__ int clamp255(int v) {	// exact replacement of the clamp LUT (Q17)
-	return min(max(v, 0), 255);
 }
 
 // n-bit field at compile-time position POS of a 128-bit little-endian stream held

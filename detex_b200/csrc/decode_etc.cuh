@@ -3,7 +3,7 @@
 // decompress-eac.c:21-231.  ETC/EAC blocks are big-endian byte strings; blocks are
 // held as little-endian words so byte k of the string is byte k&3 of word k>>2.
 // Pixels are numbered column-major in the stream (x = i>>2, y = i&3) and stored
-// row-major (Q12).  The clamp LUT of the reference is replaced by min/max (Q17).
+// row-major (Q12).  The clamp LUT of the reference is replaced by SIMD min/max (Q17).
 #pragma once
 #include "common.cuh"
 
@@ -36,18 +36,6 @@ __device__ __forceinline__ uint32_t etc2_mode(uint32_t w0) {
 	const bool ov_g = etc_overflow(etc_diff_sum((w0 >> 8) & 0xFFu));
 	const bool ov_b = etc_overflow(etc_diff_sum((w0 >> 16) & 0xFFu));
 	return ov_r ? (uint32_t)ETC_T : (ov_g ? (uint32_t)ETC_H : (ov_b ? (uint32_t)ETC_PLANAR : (uint32_t)ETC_DIFFERENTIAL));
-}
-
-// 2-bit selector of stream pixel i: LSB = bit i, MSB = bit 16+i of the big-endian
-// index word (decompress-etc.c:75-76; the pixel-15 MSB is honoured like the shipped
-// build does).
-__device__ __forceinline__ uint32_t etc_selector(uint32_t idx, int i) {
-	return ((idx >> i) & 1u) | (((idx >> (16 + i)) & 1u) << 1);
-}
-__host__ __device__ constexpr int etc_dest(int i) { return (i & 3) * 4 + (i >> 2); }
-
-__device__ __forceinline__ uint32_t pack_rgb(int r, int g, int b) {
-	return (uint32_t)r | ((uint32_t)g << 8) | ((uint32_t)b << 16);
 }
 
 // ---- palette engine shared by the individual, differential, T and H modes ----------------------

@@ -414,6 +414,9 @@ template <> struct SortTraits<F_BPTC> {
 	static constexpr int NUM_BINS = 9;		// modes 0-7 + invalid
 	// every BC7 mode is separate code: bins are padded to whole warps so that no warp mixes modes
 	static constexpr bool PAD_BINS = true;
+	// 64-byte tiles: pixels are staged in shared memory and copied out coalesced
+	static constexpr bool STAGE_OUTPUT = true;
+	static constexpr int TILE_BLOCKS = 1024;
 	static __device__ __forceinline__ int bin_of(const uint4 &b, uint32_t mode_mask, uint32_t flags) {
 		const int m = __ffs((int)(b.x & 0xFFu)) - 1;
 		const bool ok = m >= 0 && ((mode_mask >> m) & 1u) && !(m >= 4 && (flags & FLAG_OPAQUE_ONLY)) &&
@@ -424,10 +427,13 @@ template <> struct SortTraits<F_BPTC> {
 struct SortTraitsBc6h {
 	static constexpr bool ENABLED = true;
 	static constexpr int NUM_BINS = 15;		// detex modes 0-13 + invalid
-	// BC6H modes only differ in their ~50-instruction bit scatter, everything after it is shared
-	// code, so a warp straddling two bins costs little -- much less than padding 15 bins of a
-	// 512-block tile to whole warps (measured: 43 % idle lanes with distribution M).
-	static constexpr bool PAD_BINS = false;
+	static constexpr bool PAD_BINS = true;
+	// 128-byte tiles whose pixel rows are 32 bytes = one full sector: a lane's direct stores are
+	// already sector-complete in both layouts, so no staging buffer is needed and the shared memory
+	// goes into a 2048-block tile instead (15 bins padded to whole warps waste 43 % of the lanes
+	// on a 512-block tile with distribution M, 9 % on 2048 blocks).
+	static constexpr bool STAGE_OUTPUT = false;
+	static constexpr int TILE_BLOCKS = 2048;
 	static __device__ __forceinline__ int bin_of(const uint4 &b, uint32_t mode_mask, uint32_t) {
 		const int m = bc6h_mode(b.x);
 		return (m >= 0 && ((mode_mask >> m) & 1u)) ? m : 14;
@@ -436,8 +442,7 @@ struct SortTraitsBc6h {
 template <> struct SortTraits<F_BPTC_FLOAT> : SortTraitsBc6h {};
 template <> struct SortTraits<F_BPTC_SIGNED_FLOAT> : SortTraitsBc6h {};
 
-// Tile size: the staged output of one tile is 64 KiB (1024 BC7 blocks, 512 BC6H blocks).
-template <int F> constexpr int sort_tile() { return 65536 / (FormatTraits<F>::OUT_WORDS * 4); }
+template <int F> constexpr int sort_tile() { return SortTraits<F>::TILE_BLOCKS; }
 
 constexpr int SORT_THREADS = 512, SORT_WARPS = SORT_THREADS / 32;
 
@@ -459,7 +464,7 @@ template <int F>
 struct SortedSmem {
 	static constexpr int TB = sort_tile<F>(), NB = SortTraits<F>::NUM_BINS, CAP = TB + NB * 32;
 	static constexpr int CHUNKS = FormatTraits<F>::OUT_WORDS / 4;	// 16-byte chunks per decoded tile
-	uint4 out[TB * CHUNKS];		// staged pixels (stage_slot layout)
+	uint4 out[SortTraits<F>::STAGE_OUTPUT ? TB * CHUNKS : 1];	// staged pixels (stage_slot layout)
 	uint4 raw[2][TB];		// double-buffered compressed tile, filled by cp.async
 	uint16_t id[CAP];		// tile-local block index in each sorted slot
 	int count[2][16];		// per-mode histogram, double-buffered across tiles
@@ -585,11 +590,26 @@ int height, int wib, uint32_t mode_mask, uint32_t flags, uint32_t post_op, uint3
 						px[k] = 0u;
 				}
 				apply_post_op<OW>(px, post_op);
+				if constexpr (S::STAGE_OUTPUT) {
 #pragma unroll
-				for (int c = 0; c < CHUNKS; c++)
-					sm.out[stage_slot<TB, CHUNKS>(id, c)] = make_uint4(px[4 * c], px[4 * c + 1], px[4 * c + 2], px[4 * c + 3]);
+					for (int c = 0; c < CHUNKS; c++)
+						sm.out[stage_slot<TB, CHUNKS>(id, c)] = make_uint4(px[4 * c], px[4 * c + 1], px[4 * c + 2], px[4 * c + 3]);
+				}
+				else if (LAYOUT == LAYOUT_TILED) {
+					uint8_t *out = dst + (size_t)(tile0 + id) * (OW * 4);
+#pragma unroll
+					for (int c = 0; c < CHUNKS; c++)
+						st_stream_v4(out + 16 * c, px[4 * c], px[4 * c + 1], px[4 * c + 2], px[4 * c + 3]);
+				}
+				else {
+					const uint32_t i = tile0 + id;
+					const uint32_t by = i / (uint32_t)wib, bx = i - by * (uint32_t)wib;
+					store_linear_rows<OW>(dst, (size_t)width * (OW / 4), (int)bx, (int)by, height, px);
+				}
 			}
 		}
+		if constexpr (!S::STAGE_OUTPUT)
+			continue;		// direct stores: the barrier at the loop top is enough
 		__syncthreads();
 		// ---- store
 		if (LAYOUT == LAYOUT_TILED) {
@@ -634,16 +654,17 @@ static std::atomic<uint64_t> g_launches{0};
 uint64_t launch_count() { return g_launches.load(); }
 void count_launch() { g_launches.fetch_add(1); }
 
-static int g_sm_count = 0;
+static std::atomic<int> g_sm_count{0};
 static int sm_count() {
-	if (g_sm_count == 0) {
-		int dev = 0, n = 0;
+	int n = g_sm_count.load();
+	if (n == 0) {
+		int dev = 0;
 		if (cudaGetDevice(&dev) != cudaSuccess ||
 		    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
 			n = 148;
-		g_sm_count = n;
+		g_sm_count.store(n);
 	}
-	return g_sm_count;
+	return n;
 }
 
 // DETEXB200_UNSORTED=1 in the environment forces the plain one-block-per-lane kernels
@@ -671,11 +692,14 @@ static cudaError_t launch_format(const DecodeArgs &a, cudaStream_t stream) {
 			const uint64_t resident = (uint64_t)sm_count() * 2;		// persistent: two CTAs per SM
 			const unsigned grid = (unsigned)(tiles < resident ? tiles : resident);
 			const size_t smem = sizeof(SortedSmem<F>);
-			static bool configured = false;		// per template instantiation
-			if (!configured) {
+			// opt in to > 48 KiB of dynamic shared memory once per device (per template instantiation)
+			static std::atomic<bool> configured[64];
+			int dev = 0;
+			cudaGetDevice(&dev);
+			if (!configured[dev & 63].load()) {
 				cudaFuncSetAttribute(decode_sorted_kernel<F, LAYOUT_TILED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 				cudaFuncSetAttribute(decode_sorted_kernel<F, LAYOUT_LINEAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-				configured = true;
+				configured[dev & 63].store(true);
 			}
 			if (a.layout == LAYOUT_TILED)
 				decode_sorted_kernel<F, LAYOUT_TILED><<<grid, SORT_THREADS, smem, stream>>>(src, dst, (uint32_t)n_blocks,
