@@ -331,36 +331,40 @@ def run(out):
 
     # ---- end-to-end leg: reference-facing API, pinned host buffers, copies inside the timed region ----
     e2e_steps = args.e2e_steps or min(args.steps, 10)
-    e2e = None
     p0 = parts[0]
-    if len(parts) == 1:
-        host_blocks = torch.empty(p0["n"] * p0["bs"], dtype=torch.uint8).pin_memory()
-        host_blocks.copy_(p0["sets"][0][0])
-        n_out = (p0["w"] * p0["h"] if p0["layout"] == D.LAYOUT_LINEAR else p0["n"] * 16) * p0["ps"]
+    calls = []          # one reference-API call per part: (fn, texture, host pixels, pixel format)
+    h2d = d2h = 0
+    for p in parts:
+        host_blocks = torch.empty(p["n"] * p["bs"], dtype=torch.uint8).pin_memory()
+        host_blocks.copy_(p["sets"][0][0])
+        n_out = (p["w"] * p["h"] if p["layout"] == D.LAYOUT_LINEAR else p["n"] * 16) * p["ps"]
         host_pixels = torch.empty(n_out, dtype=torch.uint8).pin_memory()
-        tex = D.DetexTexture(p0["tf"], host_blocks.data_ptr(), p0["w"], p0["h"], p0["wib"], p0["hib"])
-        fn = lib.detexDecompressTextureLinear if p0["layout"] == D.LAYOUT_LINEAR else lib.detexDecompressTextureTiled
-        pf = p0["tf"] & 0xFFFF
-        for _ in range(3):
+        tex = D.DetexTexture(p["tf"], host_blocks.data_ptr(), p["w"], p["h"], p["wib"], p["hib"])
+        fn = lib.detexDecompressTextureLinear if p["layout"] == D.LAYOUT_LINEAR else lib.detexDecompressTextureTiled
+        calls.append((fn, tex, host_blocks, host_pixels, p["tf"] & 0xFFFF))
+        h2d += int(p["n"] * p["bs"])
+        d2h += int(n_out)
+
+    def e2e_step():
+        for fn, tex, _, host_pixels, pf in calls:
             fn(C.byref(tex), host_pixels.data_ptr(), pf)
-        if world > 1:
-            dist.barrier()
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            fn(C.byref(tex), host_pixels.data_ptr(), pf)
-        t_e2e = time.perf_counter() - t0
-        if world > 1:
-            t = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            t_e2e = float(t.item())
-        e2e = {"value": job_blocks * e2e_steps / t_e2e, "unit": "blocks/s", "steps": e2e_steps,
-               "ms_per_step": 1e3 * t_e2e / e2e_steps, "h2d_bytes_per_step": int(p0["n"] * p0["bs"]),
-               "d2h_bytes_per_step": int(n_out), "api": "detexDecompressTexture%s, pinned host buffers" %
-               ("Linear" if p0["layout"] == D.LAYOUT_LINEAR else "Tiled")}
-        # keep the e2e output for the parity spot-check below
-        e2e_pixels = host_pixels.numpy()
-    else:
-        e2e_pixels = None
+    for _ in range(3):
+        e2e_step()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    t_e2e = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_e2e = float(t.item())
+    e2e = {"value": job_blocks * e2e_steps / t_e2e, "unit": "blocks/s", "steps": e2e_steps,
+           "ms_per_step": 1e3 * t_e2e / e2e_steps, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+           "api": "detexDecompressTexture%s per part, pinned host buffers, wall clock around the synchronous calls" %
+           ("Linear" if p0["layout"] == D.LAYOUT_LINEAR else "Tiled")}
+    e2e_pixels = calls[0][3].numpy()      # kept for the parity spot-check below
 
     # ---- CPU baseline + parity of the timed configuration (rank 0, N = 1 only) ---------------------------
     cpu_baseline = None

@@ -46,6 +46,13 @@ __device__ __forceinline__ void st_stream_v4(void *p, uint32_t a, uint32_t b, ui
 	asm volatile("st.global.cs.v4.u32 [%0], {%1, %2, %3, %4};"
 		:: "l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
+// 256-bit streaming store (sm_100: STG.E.ENL2.256): one full 32-byte sector per lane.
+// The address must be 32-byte aligned.
+__device__ __forceinline__ void st_stream_v8(void *p, uint32_t a, uint32_t b, uint32_t c, uint32_t d,
+uint32_t e, uint32_t f, uint32_t g, uint32_t h) {
+	asm volatile("st.global.cs.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+		:: "l"(p), "r"(a), "r"(b), "r"(c), "r"(d), "r"(e), "r"(f), "r"(g), "r"(h) : "memory");
+}
 __device__ __forceinline__ void st_stream_v2(void *p, uint32_t a, uint32_t b) {
 	asm volatile("st.global.cs.v2.u32 [%0], {%1, %2};" :: "l"(p), "r"(a), "r"(b) : "memory");
 }

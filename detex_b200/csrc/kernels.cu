@@ -151,6 +151,8 @@ __device__ __forceinline__ void store_linear_rows(uint8_t *dst, size_t pitch, in
 	constexpr int ROW_WORDS = OW / 4, ROW_BYTES = OW;
 	uint8_t *out = dst + (size_t)by * 4 * pitch + (size_t)bx * ROW_BYTES;
 	const int rows = min(4, height - by * 4);		// clip the bottom edge (texture.c:117-120)
+	// 32-byte rows go out as one 256-bit store when image base and pitch keep them 32-byte aligned
+	const bool wide_ok = ROW_WORDS == 8 && ((((uintptr_t)dst) | pitch) & 31u) == 0;
 #pragma unroll
 	for (int r = 0; r < 4; r++) {
 		if (r < rows) {
@@ -161,6 +163,9 @@ __device__ __forceinline__ void store_linear_rows(uint8_t *dst, size_t pitch, in
 				st_stream_v2(p, px[2 * r], px[2 * r + 1]);
 			else if constexpr (ROW_WORDS == 4)
 				st_stream_v4(p, px[4 * r], px[4 * r + 1], px[4 * r + 2], px[4 * r + 3]);
+			else if (wide_ok)
+				st_stream_v8(p, px[8 * r], px[8 * r + 1], px[8 * r + 2], px[8 * r + 3],
+					px[8 * r + 4], px[8 * r + 5], px[8 * r + 6], px[8 * r + 7]);
 			else {
 				st_stream_v4(p, px[8 * r], px[8 * r + 1], px[8 * r + 2], px[8 * r + 3]);
 				st_stream_v4(p + 16, px[8 * r + 4], px[8 * r + 5], px[8 * r + 6], px[8 * r + 7]);
@@ -170,7 +175,9 @@ __device__ __forceinline__ void store_linear_rows(uint8_t *dst, size_t pitch, in
 }
 
 // ---- TILED --------------------------------------------------------------------------------
-template <int F>
+// DIRECT: every lane writes its own tile with 256-bit stores (tiles of >= 32 bytes on a 32-byte
+// aligned destination) instead of transposing the warp's tiles through shared memory.
+template <int F, bool DIRECT>
 __global__ void __launch_bounds__(CTA_THREADS)
 decode_tiled_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, uint32_t n_blocks,
 uint32_t mode_mask, uint32_t flags, uint32_t post_op, uint32_t *invalid_flag) {
@@ -178,7 +185,7 @@ uint32_t mode_mask, uint32_t flags, uint32_t post_op, uint32_t *invalid_flag) {
 	using D = DeferTraits<F>;
 	constexpr int BW = T::BLOCK_WORDS, OW = T::OUT_WORDS, CHUNKS = OW / 4;
 	__shared__ BptcTables tables;
-	__shared__ uint4 stage[CHUNKS > 1 ? CTA_WARPS * 32 * CHUNKS : 1];
+	__shared__ uint4 stage[CHUNKS > 1 && !DIRECT ? CTA_WARPS * 32 * CHUNKS : 1];
 	__shared__ uint32_t queue[D::ENABLED ? CTA_THREADS * DEFER_ITERS : 1];
 	__shared__ int queue_n;
 	if constexpr (T::USES_TABLES)
@@ -218,6 +225,14 @@ uint32_t mode_mask, uint32_t flags, uint32_t post_op, uint32_t *invalid_flag) {
 			if constexpr (CHUNKS == 1) {
 				if (active && !rare)
 					st_stream_v4(tile_out + lane * 16, px[0], px[1], px[2], px[3]);
+			}
+			else if constexpr (DIRECT) {
+				if (active && !rare) {
+#pragma unroll
+					for (int c = 0; c < CHUNKS; c += 2)
+						st_stream_v8(tile_out + lane * (OW * 4) + 16 * c, px[4 * c], px[4 * c + 1], px[4 * c + 2],
+							px[4 * c + 3], px[4 * c + 4], px[4 * c + 5], px[4 * c + 6], px[4 * c + 7]);
+				}
 			}
 			else {
 				// Transpose through shared memory: lane L parks chunk c of its tile at
@@ -597,9 +612,17 @@ int height, int wib, uint32_t mode_mask, uint32_t flags, uint32_t post_op, uint3
 				}
 				else if (LAYOUT == LAYOUT_TILED) {
 					uint8_t *out = dst + (size_t)(tile0 + id) * (OW * 4);
+					if ((((uintptr_t)dst) & 31u) == 0) {
 #pragma unroll
-					for (int c = 0; c < CHUNKS; c++)
-						st_stream_v4(out + 16 * c, px[4 * c], px[4 * c + 1], px[4 * c + 2], px[4 * c + 3]);
+						for (int c = 0; c < CHUNKS; c += 2)
+							st_stream_v8(out + 16 * c, px[4 * c], px[4 * c + 1], px[4 * c + 2], px[4 * c + 3],
+								px[4 * c + 4], px[4 * c + 5], px[4 * c + 6], px[4 * c + 7]);
+					}
+					else {
+#pragma unroll
+						for (int c = 0; c < CHUNKS; c++)
+							st_stream_v4(out + 16 * c, px[4 * c], px[4 * c + 1], px[4 * c + 2], px[4 * c + 3]);
+					}
 				}
 				else {
 					const uint32_t i = tile0 + id;
@@ -674,6 +697,13 @@ static bool force_unsorted() {
 	return v;
 }
 
+// DETEXB200_TILED_DIRECT=1: TILED output written by per-lane 256-bit stores (A/B against the
+// shared-memory transposition).
+static bool tiled_direct() {
+	static const bool v = [] { const char *e = getenv("DETEXB200_TILED_DIRECT"); return e && e[0] == '1'; }();
+	return v;
+}
+
 template <int F>
 static cudaError_t launch_format(const DecodeArgs &a, cudaStream_t stream) {
 	using T = FormatTraits<F>;
@@ -718,8 +748,13 @@ static cudaError_t launch_format(const DecodeArgs &a, cudaStream_t stream) {
 		const uint64_t want = (tiles + per_cta - 1) / per_cta;
 		const uint64_t cap = (uint64_t)sm_count() * 8 * 16;
 		const unsigned grid = (unsigned)(want < cap ? want : cap);
-		decode_tiled_kernel<F><<<grid, CTA_THREADS, 0, stream>>>(src, dst, (uint32_t)n_blocks,
-			a.mode_mask, a.flags, a.post_op, a.invalid);
+		constexpr bool CAN_DIRECT = T::OUT_WORDS >= 8;
+		if (CAN_DIRECT && (((uintptr_t)dst) & 31u) == 0 && tiled_direct())
+			decode_tiled_kernel<F, CAN_DIRECT><<<grid, CTA_THREADS, 0, stream>>>(src, dst, (uint32_t)n_blocks,
+				a.mode_mask, a.flags, a.post_op, a.invalid);
+		else
+			decode_tiled_kernel<F, false><<<grid, CTA_THREADS, 0, stream>>>(src, dst, (uint32_t)n_blocks,
+				a.mode_mask, a.flags, a.post_op, a.invalid);
 	}
 	else {
 		const bool fast = (a.width % 4 == 0) && aligned_out;
