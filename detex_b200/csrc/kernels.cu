@@ -505,7 +505,7 @@ __device__ __forceinline__ uint32_t raw_slot(uint32_t id) { return id ^ ((id >> 
 //           holds start[b]), ids scattered to their sorted slots, barrier
 //   decode  each warp takes groups of 32 same-mode blocks -> pixels parked in shared memory
 //   store   barrier, cooperative copy-out, 512 contiguous bytes per warp store instruction
-template <int F, int LAYOUT>
+template <int F, int LAYOUT, bool STAGE>
 __global__ void __launch_bounds__(SORT_THREADS, 2)
 decode_sorted_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, uint32_t n_blocks, int width,
 int height, int wib, uint32_t mode_mask, uint32_t flags, uint32_t post_op, uint32_t *invalid_flag) {
@@ -605,7 +605,7 @@ int height, int wib, uint32_t mode_mask, uint32_t flags, uint32_t post_op, uint3
 						px[k] = 0u;
 				}
 				apply_post_op<OW>(px, post_op);
-				if constexpr (S::STAGE_OUTPUT) {
+				if constexpr (STAGE) {
 #pragma unroll
 					for (int c = 0; c < CHUNKS; c++)
 						sm.out[stage_slot<TB, CHUNKS>(id, c)] = make_uint4(px[4 * c], px[4 * c + 1], px[4 * c + 2], px[4 * c + 3]);
@@ -631,12 +631,20 @@ int height, int wib, uint32_t mode_mask, uint32_t flags, uint32_t post_op, uint3
 				}
 			}
 		}
-		if constexpr (!S::STAGE_OUTPUT)
+		if constexpr (!STAGE)
 			continue;		// direct stores: the barrier at the loop top is enough
 		__syncthreads();
 		// ---- store
 		if (LAYOUT == LAYOUT_TILED) {
 			uint8_t *out = dst + (size_t)tile0 * (OW * 4);
+			if (CHUNKS % 2 == 0 && (((uintptr_t)dst) & 31u) == 0) {
+				for (uint32_t q = 2u * tid; q < n_here * CHUNKS; q += 2u * SORT_THREADS) {
+					const uint4 v0 = sm.out[stage_slot<TB, CHUNKS>(q / CHUNKS, q % CHUNKS)];
+					const uint4 v1 = sm.out[stage_slot<TB, CHUNKS>(q / CHUNKS, q % CHUNKS + 1)];
+					st_stream_v8(out + (size_t)q * 16, v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w);
+				}
+				continue;
+			}
 			for (uint32_t q = tid; q < n_here * CHUNKS; q += SORT_THREADS) {
 				const uint4 v = sm.out[stage_slot<TB, CHUNKS>(q / CHUNKS, q % CHUNKS)];
 				st_stream_v4(out + (size_t)q * 16, v.x, v.y, v.z, v.w);
@@ -646,6 +654,32 @@ int height, int wib, uint32_t mode_mask, uint32_t flags, uint32_t post_op, uint3
 			constexpr int ROW_BYTES = OW;		// bytes of one pixel row of one block
 			const size_t pitch = (size_t)width * (ROW_BYTES / 4);
 			const uint32_t by0 = tile0 / (uint32_t)wib, bx0 = tile0 - by0 * (uint32_t)wib;	// uniform
+			// 16-byte rows (CPR == 1): a thread takes the rows of two horizontally adjacent blocks and
+			// writes them as one 256-bit store each when everything is 32-byte aligned
+			const bool pair_ok = CPR == 1 && ((((uintptr_t)dst) | pitch) & 31u) == 0 && (wib & 1) == 0 && (TB & 1) == 0;
+			if (pair_ok) {
+#pragma unroll
+				for (int j = 0; j < TB / 2 / SORT_THREADS; j++) {
+					const uint32_t id = 2u * (j * SORT_THREADS + tid);
+					if (id < n_here) {		// n_here is even here: wib and TB are even, so is n_blocks
+						uint32_t bx = bx0 + id, by = by0;
+						while (bx >= (uint32_t)wib) {
+							bx -= (uint32_t)wib;
+							by++;
+						}
+						uint8_t *out = dst + (size_t)by * 4 * pitch + (size_t)bx * ROW_BYTES;
+						const int rows = min(4, height - (int)by * 4);
+#pragma unroll
+						for (int r = 0; r < 4; r++)
+							if (r < rows) {
+								const uint4 v0 = sm.out[stage_slot<TB, CHUNKS>(id, r)];
+								const uint4 v1 = sm.out[stage_slot<TB, CHUNKS>(id + 1, r)];
+								st_stream_v8(out + r * pitch, v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w);
+							}
+					}
+				}
+				continue;
+			}
 			// thread t owns row positions p = t, t+512, ... (p = id*CPR + half) for all 4 pixel rows
 #pragma unroll
 			for (int j = 0; j < TB * CPR / SORT_THREADS; j++) {
@@ -726,16 +760,21 @@ static cudaError_t launch_format(const DecodeArgs &a, cudaStream_t stream) {
 			static std::atomic<bool> configured[64];
 			int dev = 0;
 			cudaGetDevice(&dev);
+			constexpr bool ST = SortTraits<F>::STAGE_OUTPUT;
 			if (!configured[dev & 63].load()) {
-				cudaFuncSetAttribute(decode_sorted_kernel<F, LAYOUT_TILED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-				cudaFuncSetAttribute(decode_sorted_kernel<F, LAYOUT_LINEAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+				cudaFuncSetAttribute(decode_sorted_kernel<F, LAYOUT_TILED, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+				cudaFuncSetAttribute(decode_sorted_kernel<F, LAYOUT_TILED, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+				cudaFuncSetAttribute(decode_sorted_kernel<F, LAYOUT_LINEAR, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 				configured[dev & 63].store(true);
 			}
-			if (a.layout == LAYOUT_TILED)
-				decode_sorted_kernel<F, LAYOUT_TILED><<<grid, SORT_THREADS, smem, stream>>>(src, dst, (uint32_t)n_blocks,
+			if (a.layout == LAYOUT_TILED && tiled_direct() && (((uintptr_t)dst) & 31u) == 0)
+				decode_sorted_kernel<F, LAYOUT_TILED, false><<<grid, SORT_THREADS, smem, stream>>>(src, dst, (uint32_t)n_blocks,
+					a.width, a.height, a.wib, a.mode_mask, a.flags, a.post_op, a.invalid);
+			else if (a.layout == LAYOUT_TILED)
+				decode_sorted_kernel<F, LAYOUT_TILED, ST><<<grid, SORT_THREADS, smem, stream>>>(src, dst, (uint32_t)n_blocks,
 					a.width, a.height, a.wib, a.mode_mask, a.flags, a.post_op, a.invalid);
 			else
-				decode_sorted_kernel<F, LAYOUT_LINEAR><<<grid, SORT_THREADS, smem, stream>>>(src, dst, (uint32_t)n_blocks,
+				decode_sorted_kernel<F, LAYOUT_LINEAR, ST><<<grid, SORT_THREADS, smem, stream>>>(src, dst, (uint32_t)n_blocks,
 					a.width, a.height, a.wib, a.mode_mask, a.flags, a.post_op, a.invalid);
 			count_launch();
 			return cudaGetLastError();
