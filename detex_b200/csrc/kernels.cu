@@ -111,13 +111,15 @@ __device__ __forceinline__ void apply_post_op(uint32_t (&px)[OW], uint32_t post_
 constexpr int CTA_THREADS = 256;
 constexpr int CTA_WARPS = CTA_THREADS / 32;
 
-// Raise the texture-level "some block was invalid" flag: one read-mostly probe and at
-// most one plain store per CTA (every writer stores the same value).
+// Raise the texture-level "some block was invalid" flag: one read-mostly probe and at most one
+// plain store per warp that met an invalid block (every writer stores the same value).
 __device__ __forceinline__ void report_invalid(bool any_bad_in_thread, uint32_t *invalid_flag) {
-	const int any = __syncthreads_or(any_bad_in_thread ? 1 : 0);
-	if (any && threadIdx.x == 0 && threadIdx.y == 0 && invalid_flag != nullptr)
-		if (*(volatile uint32_t *)invalid_flag == 0u)
+	if (any_bad_in_thread && invalid_flag != nullptr) {
+		// one probe per warp that saw an invalid block; no CTA barrier on the common path
+		const unsigned peers = __activemask();
+		if ((threadIdx.x & 31) == __ffs((int)peers) - 1 && *(volatile uint32_t *)invalid_flag == 0u)
 			*(volatile uint32_t *)invalid_flag = 1u;
+	}
 }
 
 // ---- rare-mode deferral ------------------------------------------------------------------------
@@ -460,6 +462,9 @@ template <> struct SortTraits<F_BPTC_SIGNED_FLOAT> : SortTraitsBc6h {};
 template <int F> constexpr int sort_tile() { return SortTraits<F>::TILE_BLOCKS; }
 
 constexpr int SORT_THREADS = 512, SORT_WARPS = SORT_THREADS / 32;
+// measurement switches carried in the upper bits of the kernels' flags word (never set by the API)
+constexpr uint32_t FLAG_DEBUG_STATIC_GROUPS = 0x40000000u, FLAG_DEBUG_NARROW_STORES = 0x80000000u;
+constexpr uint32_t SLOT_EMPTY = 0xFFFFu;		// sorted slot that is bin padding
 
 // Physical 16-byte slot of chunk c of the block with tile-local index id in the staging buffer:
 // plane c, position id with its low three bits XOR-hashed by the next three bits of id and by
@@ -483,6 +488,7 @@ struct SortedSmem {
 	uint4 raw[2][TB];		// double-buffered compressed tile, filled by cp.async
 	uint16_t id[CAP];		// tile-local block index in each sorted slot
 	int count[2][16];		// per-mode histogram, double-buffered across tiles
+	int ticket[2];			// next unclaimed group of the decode phase, double-buffered likewise
 	BptcTables tables;
 };
 
@@ -522,6 +528,8 @@ int height, int wib, uint32_t mode_mask, uint32_t flags, uint32_t post_op, uint3
 	const uint32_t n_tiles = (n_blocks + TB - 1) / TB;
 	if (tid < 32)
 		(&sm.count[0][0])[tid] = 0;
+	if (tid < 2)
+		sm.ticket[tid] = SORT_WARPS * 32;
 	bptc_tables_load(sm.tables);
 
 	auto issue_tile_load = [&](uint32_t tile, int buf) {
@@ -544,6 +552,11 @@ int height, int wib, uint32_t mode_mask, uint32_t flags, uint32_t post_op, uint3
 			issue_tile_load(tile + gridDim.x, cur ^ 1);
 		if (tid < 16)
 			sm.count[cur ^ 1][tid] = 0;
+		if (tid == 16)
+			sm.ticket[cur ^ 1] = SORT_WARPS * 32;
+		// mark every sorted slot empty; the scatter below overwrites the occupied ones
+		for (int q = tid; q < SM::CAP / 2; q += SORT_THREADS)
+			reinterpret_cast<uint32_t *>(sm.id)[q] = SLOT_EMPTY | (SLOT_EMPTY << 16);
 		// ---- sort: classify, histogram
 		int bin[PER], off[PER];
 #pragma unroll
@@ -583,19 +596,26 @@ int height, int wib, uint32_t mode_mask, uint32_t flags, uint32_t post_op, uint3
 				sm.id[st + off[k]] = (uint16_t)(k * SORT_THREADS + tid);
 		}
 		__syncthreads();
-		// ---- decode: groups of 32 same-mode blocks
-		for (int g = warp * 32; g < total; g += SORT_WARPS * 32) {
-			const int pos = g + lane;
-			bool live = pos < total;
-			if constexpr (S::PAD_BINS) {
-				// bin of this group = highest bin whose start is <= g; its tail lanes are padding
-				const unsigned le = __ballot_sync(0xFFFFFFFFu, lane < NB && start <= g);
-				const int b = 31 - __clz((int)le);
-				const int b_start = __shfl_sync(0xFFFFFFFFu, start, b), b_count = __shfl_sync(0xFFFFFFFFu, my_count, b);
-				live = pos < b_start + b_count;
+		// ---- decode: groups of 32 same-mode blocks; padding slots hold the 0xFFFF sentinel.
+		// The next group's ids are fetched before the current group is decoded.
+		// Groups cost different amounts of work (mode, padding), so after its first group a warp
+		// draws the next one from a ticket counter; the draw is issued one group ahead.
+		const bool dynamic = !(flags & FLAG_DEBUG_STATIC_GROUPS);
+		int g = warp * 32, ticket = 0;
+		if (dynamic && lane == 0)
+			ticket = atomicAdd(&sm.ticket[cur], 32);
+		uint32_t id_next = g < total ? sm.id[g + lane] : SLOT_EMPTY;
+		for (int g_next; g < total; g = g_next) {
+			const uint32_t id = id_next;
+			g_next = g + SORT_WARPS * 32;
+			if (dynamic) {
+				g_next = __shfl_sync(0xFFFFFFFFu, ticket, 0);
+				if (lane == 0)
+					ticket = atomicAdd(&sm.ticket[cur], 32);
 			}
+			id_next = g_next < total ? sm.id[g_next + lane] : SLOT_EMPTY;
+			const bool live = id != SLOT_EMPTY;
 			if (live) {
-				const uint32_t id = sm.id[pos];
 				const uint4 w = sm.raw[cur][raw_slot(id)];
 				uint32_t px[OW];
 				if (!decode_block<F>(w, mode_mask, flags, &sm.tables, px)) {
@@ -637,7 +657,7 @@ int height, int wib, uint32_t mode_mask, uint32_t flags, uint32_t post_op, uint3
 		// ---- store
 		if (LAYOUT == LAYOUT_TILED) {
 			uint8_t *out = dst + (size_t)tile0 * (OW * 4);
-			if (CHUNKS % 2 == 0 && (((uintptr_t)dst) & 31u) == 0) {
+			if (CHUNKS % 2 == 0 && (((uintptr_t)dst) & 31u) == 0 && !(flags & FLAG_DEBUG_NARROW_STORES)) {
 				for (uint32_t q = 2u * tid; q < n_here * CHUNKS; q += 2u * SORT_THREADS) {
 					const uint4 v0 = sm.out[stage_slot<TB, CHUNKS>(q / CHUNKS, q % CHUNKS)];
 					const uint4 v1 = sm.out[stage_slot<TB, CHUNKS>(q / CHUNKS, q % CHUNKS + 1)];
@@ -656,7 +676,8 @@ int height, int wib, uint32_t mode_mask, uint32_t flags, uint32_t post_op, uint3
 			const uint32_t by0 = tile0 / (uint32_t)wib, bx0 = tile0 - by0 * (uint32_t)wib;	// uniform
 			// 16-byte rows (CPR == 1): a thread takes the rows of two horizontally adjacent blocks and
 			// writes them as one 256-bit store each when everything is 32-byte aligned
-			const bool pair_ok = CPR == 1 && ((((uintptr_t)dst) | pitch) & 31u) == 0 && (wib & 1) == 0 && (TB & 1) == 0;
+			const bool pair_ok = CPR == 1 && ((((uintptr_t)dst) | pitch) & 31u) == 0 && (wib & 1) == 0 && (TB & 1) == 0 &&
+				!(flags & FLAG_DEBUG_NARROW_STORES);
 			if (pair_ok) {
 #pragma unroll
 				for (int j = 0; j < TB / 2 / SORT_THREADS; j++) {
@@ -733,6 +754,19 @@ static bool force_unsorted() {
 
 // DETEXB200_TILED_DIRECT=1: TILED output written by per-lane 256-bit stores (A/B against the
 // shared-memory transposition).
+static uint32_t debug_flags() {
+	static const uint32_t v = [] {
+		uint32_t f = 0;
+		const char *e = getenv("DETEXB200_STATIC_GROUPS");
+		if (e && e[0] == '1')
+			f |= FLAG_DEBUG_STATIC_GROUPS;
+		e = getenv("DETEXB200_NARROW_STORES");
+		if (e && e[0] == '1')
+			f |= FLAG_DEBUG_NARROW_STORES;
+		return f;
+	}();
+	return v;
+}
 static bool tiled_direct() {
 	static const bool v = [] { const char *e = getenv("DETEXB200_TILED_DIRECT"); return e && e[0] == '1'; }();
 	return v;
@@ -769,13 +803,13 @@ static cudaError_t launch_format(const DecodeArgs &a, cudaStream_t stream) {
 			}
 			if (a.layout == LAYOUT_TILED && tiled_direct() && (((uintptr_t)dst) & 31u) == 0)
 				decode_sorted_kernel<F, LAYOUT_TILED, false><<<grid, SORT_THREADS, smem, stream>>>(src, dst, (uint32_t)n_blocks,
-					a.width, a.height, a.wib, a.mode_mask, a.flags, a.post_op, a.invalid);
+					a.width, a.height, a.wib, a.mode_mask, (a.flags & 0xFFFFu) | debug_flags(), a.post_op, a.invalid);
 			else if (a.layout == LAYOUT_TILED)
 				decode_sorted_kernel<F, LAYOUT_TILED, ST><<<grid, SORT_THREADS, smem, stream>>>(src, dst, (uint32_t)n_blocks,
-					a.width, a.height, a.wib, a.mode_mask, a.flags, a.post_op, a.invalid);
+					a.width, a.height, a.wib, a.mode_mask, (a.flags & 0xFFFFu) | debug_flags(), a.post_op, a.invalid);
 			else
 				decode_sorted_kernel<F, LAYOUT_LINEAR, ST><<<grid, SORT_THREADS, smem, stream>>>(src, dst, (uint32_t)n_blocks,
-					a.width, a.height, a.wib, a.mode_mask, a.flags, a.post_op, a.invalid);
+					a.width, a.height, a.wib, a.mode_mask, (a.flags & 0xFFFFu) | debug_flags(), a.post_op, a.invalid);
 			count_launch();
 			return cudaGetLastError();
 		}
