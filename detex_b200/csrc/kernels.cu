@@ -462,8 +462,6 @@ template <> struct SortTraits<F_BPTC_SIGNED_FLOAT> : SortTraitsBc6h {};
 template <int F> constexpr int sort_tile() { return SortTraits<F>::TILE_BLOCKS; }
 
 constexpr int SORT_THREADS = 512, SORT_WARPS = SORT_THREADS / 32;
-// measurement switches carried in the upper bits of the kernels' flags word (never set by the API)
-constexpr uint32_t FLAG_DEBUG_STATIC_GROUPS = 0x40000000u, FLAG_DEBUG_NARROW_STORES = 0x80000000u;
 constexpr uint32_t SLOT_EMPTY = 0xFFFFu;		// sorted slot that is bin padding
 
 // Physical 16-byte slot of chunk c of the block with tile-local index id in the staging buffer:
@@ -488,7 +486,6 @@ struct SortedSmem {
 	uint4 raw[2][TB];		// double-buffered compressed tile, filled by cp.async
 	uint16_t id[CAP];		// tile-local block index in each sorted slot
 	int count[2][16];		// per-mode histogram, double-buffered across tiles
-	int ticket[2];			// next unclaimed group of the decode phase, double-buffered likewise
 	BptcTables tables;
 };
 
@@ -528,8 +525,6 @@ int height, int wib, uint32_t mode_mask, uint32_t flags, uint32_t post_op, uint3
 	const uint32_t n_tiles = (n_blocks + TB - 1) / TB;
 	if (tid < 32)
 		(&sm.count[0][0])[tid] = 0;
-	if (tid < 2)
-		sm.ticket[tid] = SORT_WARPS * 32;
 	bptc_tables_load(sm.tables);
 
 	auto issue_tile_load = [&](uint32_t tile, int buf) {
@@ -552,8 +547,6 @@ int height, int wib, uint32_t mode_mask, uint32_t flags, uint32_t post_op, uint3
 			issue_tile_load(tile + gridDim.x, cur ^ 1);
 		if (tid < 16)
 			sm.count[cur ^ 1][tid] = 0;
-		if (tid == 16)
-			sm.ticket[cur ^ 1] = SORT_WARPS * 32;
 		// mark every sorted slot empty; the scatter below overwrites the occupied ones
 		for (int q = tid; q < SM::CAP / 2; q += SORT_THREADS)
 			reinterpret_cast<uint32_t *>(sm.id)[q] = SLOT_EMPTY | (SLOT_EMPTY << 16);
@@ -598,21 +591,11 @@ int height, int wib, uint32_t mode_mask, uint32_t flags, uint32_t post_op, uint3
 		__syncthreads();
 		// ---- decode: groups of 32 same-mode blocks; padding slots hold the 0xFFFF sentinel.
 		// The next group's ids are fetched before the current group is decoded.
-		// Groups cost different amounts of work (mode, padding), so after its first group a warp
-		// draws the next one from a ticket counter; the draw is issued one group ahead.
-		const bool dynamic = !(flags & FLAG_DEBUG_STATIC_GROUPS);
-		int g = warp * 32, ticket = 0;
-		if (dynamic && lane == 0)
-			ticket = atomicAdd(&sm.ticket[cur], 32);
+		int g = warp * 32;
 		uint32_t id_next = g < total ? sm.id[g + lane] : SLOT_EMPTY;
-		for (int g_next; g < total; g = g_next) {
+		for (; g < total; g += SORT_WARPS * 32) {
 			const uint32_t id = id_next;
-			g_next = g + SORT_WARPS * 32;
-			if (dynamic) {
-				g_next = __shfl_sync(0xFFFFFFFFu, ticket, 0);
-				if (lane == 0)
-					ticket = atomicAdd(&sm.ticket[cur], 32);
-			}
+			const int g_next = g + SORT_WARPS * 32;
 			id_next = g_next < total ? sm.id[g_next + lane] : SLOT_EMPTY;
 			const bool live = id != SLOT_EMPTY;
 			if (live) {
@@ -657,14 +640,6 @@ int height, int wib, uint32_t mode_mask, uint32_t flags, uint32_t post_op, uint3
 		// ---- store
 		if (LAYOUT == LAYOUT_TILED) {
 			uint8_t *out = dst + (size_t)tile0 * (OW * 4);
-			if (CHUNKS % 2 == 0 && (((uintptr_t)dst) & 31u) == 0 && !(flags & FLAG_DEBUG_NARROW_STORES)) {
-				for (uint32_t q = 2u * tid; q < n_here * CHUNKS; q += 2u * SORT_THREADS) {
-					const uint4 v0 = sm.out[stage_slot<TB, CHUNKS>(q / CHUNKS, q % CHUNKS)];
-					const uint4 v1 = sm.out[stage_slot<TB, CHUNKS>(q / CHUNKS, q % CHUNKS + 1)];
-					st_stream_v8(out + (size_t)q * 16, v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w);
-				}
-				continue;
-			}
 			for (uint32_t q = tid; q < n_here * CHUNKS; q += SORT_THREADS) {
 				const uint4 v = sm.out[stage_slot<TB, CHUNKS>(q / CHUNKS, q % CHUNKS)];
 				st_stream_v4(out + (size_t)q * 16, v.x, v.y, v.z, v.w);
@@ -674,33 +649,6 @@ int height, int wib, uint32_t mode_mask, uint32_t flags, uint32_t post_op, uint3
 			constexpr int ROW_BYTES = OW;		// bytes of one pixel row of one block
 			const size_t pitch = (size_t)width * (ROW_BYTES / 4);
 			const uint32_t by0 = tile0 / (uint32_t)wib, bx0 = tile0 - by0 * (uint32_t)wib;	// uniform
-			// 16-byte rows (CPR == 1): a thread takes the rows of two horizontally adjacent blocks and
-			// writes them as one 256-bit store each when everything is 32-byte aligned
-			const bool pair_ok = CPR == 1 && ((((uintptr_t)dst) | pitch) & 31u) == 0 && (wib & 1) == 0 && (TB & 1) == 0 &&
-				!(flags & FLAG_DEBUG_NARROW_STORES);
-			if (pair_ok) {
-#pragma unroll
-				for (int j = 0; j < TB / 2 / SORT_THREADS; j++) {
-					const uint32_t id = 2u * (j * SORT_THREADS + tid);
-					if (id < n_here) {		// n_here is even here: wib and TB are even, so is n_blocks
-						uint32_t bx = bx0 + id, by = by0;
-						while (bx >= (uint32_t)wib) {
-							bx -= (uint32_t)wib;
-							by++;
-						}
-						uint8_t *out = dst + (size_t)by * 4 * pitch + (size_t)bx * ROW_BYTES;
-						const int rows = min(4, height - (int)by * 4);
-#pragma unroll
-						for (int r = 0; r < 4; r++)
-							if (r < rows) {
-								const uint4 v0 = sm.out[stage_slot<TB, CHUNKS>(id, r)];
-								const uint4 v1 = sm.out[stage_slot<TB, CHUNKS>(id + 1, r)];
-								st_stream_v8(out + r * pitch, v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w);
-							}
-					}
-				}
-				continue;
-			}
 			// thread t owns row positions p = t, t+512, ... (p = id*CPR + half) for all 4 pixel rows
 #pragma unroll
 			for (int j = 0; j < TB * CPR / SORT_THREADS; j++) {
@@ -752,23 +700,10 @@ static bool force_unsorted() {
 	return v;
 }
 
-// DETEXB200_TILED_DIRECT=1: TILED output written by per-lane 256-bit stores (A/B against the
-// shared-memory transposition).
-static uint32_t debug_flags() {
-	static const uint32_t v = [] {
-		uint32_t f = 0;
-		const char *e = getenv("DETEXB200_STATIC_GROUPS");
-		if (e && e[0] == '1')
-			f |= FLAG_DEBUG_STATIC_GROUPS;
-		e = getenv("DETEXB200_NARROW_STORES");
-		if (e && e[0] == '1')
-			f |= FLAG_DEBUG_NARROW_STORES;
-		return f;
-	}();
-	return v;
-}
+// TILED output of tiles >= 32 bytes is written by per-lane 256-bit stores; DETEXB200_TILED_DIRECT=0
+// selects the older shared-memory transposition / staging instead (A/B measurements).
 static bool tiled_direct() {
-	static const bool v = [] { const char *e = getenv("DETEXB200_TILED_DIRECT"); return e && e[0] == '1'; }();
+	static const bool v = [] { const char *e = getenv("DETEXB200_TILED_DIRECT"); return !(e && e[0] == '0'); }();
 	return v;
 }
 
@@ -803,13 +738,13 @@ static cudaError_t launch_format(const DecodeArgs &a, cudaStream_t stream) {
 			}
 			if (a.layout == LAYOUT_TILED && tiled_direct() && (((uintptr_t)dst) & 31u) == 0)
 				decode_sorted_kernel<F, LAYOUT_TILED, false><<<grid, SORT_THREADS, smem, stream>>>(src, dst, (uint32_t)n_blocks,
-					a.width, a.height, a.wib, a.mode_mask, (a.flags & 0xFFFFu) | debug_flags(), a.post_op, a.invalid);
+					a.width, a.height, a.wib, a.mode_mask, a.flags, a.post_op, a.invalid);
 			else if (a.layout == LAYOUT_TILED)
 				decode_sorted_kernel<F, LAYOUT_TILED, ST><<<grid, SORT_THREADS, smem, stream>>>(src, dst, (uint32_t)n_blocks,
-					a.width, a.height, a.wib, a.mode_mask, (a.flags & 0xFFFFu) | debug_flags(), a.post_op, a.invalid);
+					a.width, a.height, a.wib, a.mode_mask, a.flags, a.post_op, a.invalid);
 			else
 				decode_sorted_kernel<F, LAYOUT_LINEAR, ST><<<grid, SORT_THREADS, smem, stream>>>(src, dst, (uint32_t)n_blocks,
-					a.width, a.height, a.wib, a.mode_mask, (a.flags & 0xFFFFu) | debug_flags(), a.post_op, a.invalid);
+					a.width, a.height, a.wib, a.mode_mask, a.flags, a.post_op, a.invalid);
 			count_launch();
 			return cudaGetLastError();
 		}
