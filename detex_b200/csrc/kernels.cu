@@ -147,6 +147,23 @@ template <> struct DeferTraits<F_ETC2_EAC> : DeferEtc2 {
 	static __device__ __forceinline__ bool is_rare(const uint4 &b) { return planar(b.z, true); }
 };
 
+// Measured tuning of the LINEAR kernel (profiles/README.md, "LINEAR kernel tuning"): block rows
+// per thread, and whether the warps of a CTA leave together.  Two rows per thread (both loads
+// issued up front) gain 5-8 % on every format that is not already at the HBM limit; BC1/BC1A sit
+// at the limit and run best with one row per thread and a closing CTA barrier.
+template <int F> struct LinearTune {
+	static constexpr int ITERS = DeferTraits<F>::ENABLED ? DEFER_ITERS : 2;
+	static constexpr bool EXIT_BARRIER = false;
+};
+struct LinearTuneAtLimit { static constexpr int ITERS = 1; static constexpr bool EXIT_BARRIER = true; };
+template <> struct LinearTune<F_BC1> : LinearTuneAtLimit {};
+template <> struct LinearTune<F_BC1A> : LinearTuneAtLimit {};
+template <> struct LinearTune<F_BC2> { static constexpr int ITERS = 1; static constexpr bool EXIT_BARRIER = false; };
+#ifndef DETEXB200_TILED_ITERS
+#define DETEXB200_TILED_ITERS 1
+#endif
+template <int F> struct TiledTune { static constexpr int ITERS = DeferTraits<F>::ENABLED ? 1 : DETEXB200_TILED_ITERS; };
+
 // pixel rows of one block into a LINEAR image (fast path: rows are whole vector stores)
 template <int OW>
 __device__ __forceinline__ void store_linear_rows(uint8_t *dst, size_t pitch, int bx, int by, int height, const uint32_t (&px)[OW]) {
@@ -201,70 +218,78 @@ uint32_t mode_mask, uint32_t flags, uint32_t post_op, uint32_t *invalid_flag) {
 	bool bad = false;
 	int it = 0;
 	// the loop bound is uniform over the CTA (needed for the barriers of the deferral pass)
-	for (uint32_t tile_base = blockIdx.x * CTA_WARPS; tile_base < n_tiles; tile_base += gridDim.x * CTA_WARPS, it++) {
-		const uint32_t tile = tile_base + warp;
-		const uint32_t first = tile * 32u, i = first + lane;
-		const bool active = tile < n_tiles && i < n_blocks;
-		uint32_t px[OW];
-		bool ok = true, rare = false;
-		if (active) {
-			const auto blk = BlockReg<BW>::load(src + (size_t)i * (BW * 4));
-			if constexpr (D::ENABLED)
-				rare = D::is_rare(blk);
-			if (!rare)
-				ok = decode_block<F, D::ENABLED ? ETC_PATHS_NO_PLANAR : ETC_PATHS_ALL>(blk, mode_mask, flags, &tables, px);
-		}
-		if (!ok) {
-			bad = true;
+	// a warp takes TI consecutive tiles per pass, all of their loads issued before the first decode
+	constexpr int TI = TiledTune<F>::ITERS;
+	const uint32_t n_groups = (n_tiles + TI - 1) / TI;
+	for (uint32_t tile_base = blockIdx.x * CTA_WARPS; tile_base < n_groups; tile_base += gridDim.x * CTA_WARPS, it++) {
 #pragma unroll
-			for (int k = 0; k < OW; k++)
-				px[k] = 0u;
-		}
-		apply_post_op<OW>(px, post_op);
-		const unsigned rare_mask = D::ENABLED ? __ballot_sync(0xFFFFFFFFu, rare) : 0u;
-		if (tile < n_tiles) {
-			uint8_t *tile_out = dst + (size_t)first * (OW * 4);
-			if constexpr (CHUNKS == 1) {
-				if (active && !rare)
-					st_stream_v4(tile_out + lane * 16, px[0], px[1], px[2], px[3]);
+		for (int k = 0; k < TI; k++) {
+			const uint32_t tile = (tile_base + warp) * TI + k;
+			const uint32_t first = tile * 32u, i = first + lane;
+			const bool active = tile < n_tiles && i < n_blocks;
+			uint32_t px[OW];
+			bool ok = true, rare = false;
+			if (active) {
+				const auto blk = BlockReg<BW>::load(src + (size_t)i * (BW * 4));
+				if constexpr (D::ENABLED)
+					rare = D::is_rare(blk);
+				if (!rare)
+					ok = decode_block<F, D::ENABLED ? ETC_PATHS_NO_PLANAR : ETC_PATHS_ALL>(blk, mode_mask, flags, &tables, px);
 			}
-			else if constexpr (DIRECT) {
-				if (active && !rare) {
+			if (!ok) {
+				bad = true;
 #pragma unroll
-					for (int c = 0; c < CHUNKS; c += 2)
-						st_stream_v8(tile_out + lane * (OW * 4) + 16 * c, px[4 * c], px[4 * c + 1], px[4 * c + 2],
-							px[4 * c + 3], px[4 * c + 4], px[4 * c + 5], px[4 * c + 6], px[4 * c + 7]);
+				for (int w = 0; w < OW; w++)
+					px[w] = 0u;
+			}
+			apply_post_op<OW>(px, post_op);
+			const unsigned rare_mask = D::ENABLED ? __ballot_sync(0xFFFFFFFFu, rare) : 0u;
+			if (tile < n_tiles) {
+				uint8_t *tile_out = dst + (size_t)first * (OW * 4);
+				if constexpr (CHUNKS == 1) {
+					if (active && !rare)
+						st_stream_v4(tile_out + lane * 16, px[0], px[1], px[2], px[3]);
+				}
+				else if constexpr (DIRECT) {
+					if (active && !rare) {
+#pragma unroll
+						for (int c = 0; c < CHUNKS; c += 2)
+							st_stream_v8(tile_out + lane * (OW * 4) + 16 * c, px[4 * c], px[4 * c + 1], px[4 * c + 2],
+								px[4 * c + 3], px[4 * c + 4], px[4 * c + 5], px[4 * c + 6], px[4 * c + 7]);
+					}
+				}
+				else {
+					// Transpose through shared memory: lane L parks chunk c of its tile at
+					// L*CHUNKS + (c ^ f(L)), f(L) = (L / (8/CHUNKS)) % CHUNKS, which makes both the
+					// 128-bit stores (fixed c, 8 consecutive lanes) and the 128-bit loads below
+					// (8 consecutive logical chunks) hit eight distinct 16-byte bank groups.
+					uint4 *buf = stage + warp * 32 * CHUNKS;
+					constexpr int GROUP = 8 / CHUNKS;
+					const int swz = (lane / GROUP) % CHUNKS;
+#pragma unroll
+					for (int c = 0; c < CHUNKS; c++)
+						buf[lane * CHUNKS + (c ^ swz)] = make_uint4(px[4 * c], px[4 * c + 1], px[4 * c + 2], px[4 * c + 3]);
+					__syncwarp();
+					const uint32_t valid_chunks = min(32u, n_blocks - first) * CHUNKS;
+#pragma unroll
+					for (int j = 0; j < CHUNKS; j++) {
+						const uint32_t q = j * 32 + lane;		// logical 16-byte chunk of the warp's output
+						const uint32_t b = q / CHUNKS, c = q % CHUNKS;
+						const uint4 v = buf[b * CHUNKS + (c ^ ((b / GROUP) % CHUNKS))];
+						if (q < valid_chunks && !((rare_mask >> b) & 1u))
+							st_stream_v4(tile_out + (size_t)q * 16, v.x, v.y, v.z, v.w);
+					}
+					__syncwarp();
 				}
 			}
-			else {
-				// Transpose through shared memory: lane L parks chunk c of its tile at
-				// L*CHUNKS + (c ^ f(L)), f(L) = (L / (8/CHUNKS)) % CHUNKS, which makes both the
-				// 128-bit stores (fixed c, 8 consecutive lanes) and the 128-bit loads below
-				// (8 consecutive logical chunks) hit eight distinct 16-byte bank groups.
-				uint4 *buf = stage + warp * 32 * CHUNKS;
-				constexpr int GROUP = 8 / CHUNKS;
-				const int swz = (lane / GROUP) % CHUNKS;
-#pragma unroll
-				for (int c = 0; c < CHUNKS; c++)
-					buf[lane * CHUNKS + (c ^ swz)] = make_uint4(px[4 * c], px[4 * c + 1], px[4 * c + 2], px[4 * c + 3]);
-				__syncwarp();
-				const uint32_t valid_chunks = min(32u, n_blocks - first) * CHUNKS;
-#pragma unroll
-				for (int j = 0; j < CHUNKS; j++) {
-					const uint32_t q = j * 32 + lane;		// logical 16-byte chunk of the warp's output
-					const uint32_t b = q / CHUNKS, c = q % CHUNKS;
-					const uint4 v = buf[b * CHUNKS + (c ^ ((b / GROUP) % CHUNKS))];
-					if (q < valid_chunks && !((rare_mask >> b) & 1u))
-						st_stream_v4(tile_out + (size_t)q * 16, v.x, v.y, v.z, v.w);
-				}
-				__syncwarp();
+			if constexpr (D::ENABLED) {
+				if (rare)
+					queue[atomicAdd(&queue_n, 1)] = i;
 			}
 		}
 		if constexpr (D::ENABLED) {
-			if (rare)
-				queue[atomicAdd(&queue_n, 1)] = i;
 			// drain the queue every DEFER_ITERS iterations and after the last one
-			const bool last = tile_base + gridDim.x * CTA_WARPS >= n_tiles;
+			const bool last = tile_base + gridDim.x * CTA_WARPS >= n_groups;
 			if ((it + 1) % DEFER_ITERS != 0 && !last)
 				continue;
 			__syncthreads();
@@ -322,10 +347,10 @@ int wib, int hib, uint32_t mode_mask, uint32_t flags, uint32_t post_op, uint32_t
 	const size_t pitch = (size_t)width * (ROW_BYTES / 4);		// bytes per image row
 	bool bad = false;
 	// CTA (bx tile, g) owns the ITERS strips of TY block rows starting at g*ITERS*TY; g grid-strides.
-	constexpr int ITERS = D::ENABLED ? DEFER_ITERS : 1;
+	constexpr int ITERS = LinearTune<F>::ITERS;
 	const int rows_per_group = ITERS * blockDim.y;
 	for (int g = blockIdx.y; g * rows_per_group < hib; g += gridDim.y) {
-#pragma unroll 1
+#pragma unroll(D::ENABLED ? 1 : ITERS)
 		for (int k = 0; k < ITERS; k++) {
 			const int by = g * rows_per_group + k * blockDim.y + threadIdx.y;
 			if (bx < wib && by < hib) {
@@ -372,6 +397,8 @@ int wib, int hib, uint32_t mode_mask, uint32_t flags, uint32_t post_op, uint32_t
 			__syncthreads();
 		}
 	}
+	if constexpr (LinearTune<F>::EXIT_BARRIER)
+		__syncthreads();
 	report_invalid(bad, invalid_flag);
 }
 
@@ -752,7 +779,7 @@ static cudaError_t launch_format(const DecodeArgs &a, cudaStream_t stream) {
 	if (a.layout == LAYOUT_TILED) {
 		const uint64_t tiles = (n_blocks + 31) / 32;
 		// enough CTAs to cover the work once, capped at a few waves of resident CTAs
-		const uint64_t per_cta = (uint64_t)CTA_WARPS * (DeferTraits<F>::ENABLED ? DEFER_ITERS : 1);
+		const uint64_t per_cta = (uint64_t)CTA_WARPS * (DeferTraits<F>::ENABLED ? DEFER_ITERS : TiledTune<F>::ITERS);
 		const uint64_t want = (tiles + per_cta - 1) / per_cta;
 		const uint64_t cap = (uint64_t)sm_count() * 8 * 16;
 		const unsigned grid = (unsigned)(want < cap ? want : cap);
@@ -772,7 +799,7 @@ static cudaError_t launch_format(const DecodeArgs &a, cudaStream_t stream) {
 				tx *= 2;
 			const int ty = CTA_THREADS / tx;
 			dim3 block(tx, ty);
-			const int rows_per_cta = ty * (DeferTraits<F>::ENABLED ? DEFER_ITERS : 1);
+			const int rows_per_cta = ty * LinearTune<F>::ITERS;
 			unsigned gy = (unsigned)((a.hib + rows_per_cta - 1) / rows_per_cta);
 			if (gy > 65535u)
 				gy = 65535u;

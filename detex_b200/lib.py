@@ -10,7 +10,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libdetex_b200.so")
+# DETEXB200_LIB selects another build of the same library (kernel A/B measurements)
+LIB_PATH = os.environ.get("DETEXB200_LIB") or os.path.join(HERE, "libdetex_b200.so")
 
 LAYOUT_TILED, LAYOUT_LINEAR = 0, 1
 
