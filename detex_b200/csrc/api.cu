@@ -355,15 +355,64 @@ void *d_pixels, uint32_t pf, int layout, uint32_t mode_mask, uint32_t flags, uin
 		set_error("detexConvertPixels: Unable to find conversion path (0x%04X -> 0x%04X on device)", native, pf);
 		return DETEXB200_EUNSUPPORTED;
 	}
-	if (pf != native && !convert_fusable(native, pf)) {
-		cudaError_t e = cudaMallocAsync(&tmp, (size_t)wib * hib * 16 * pixel_size(native) + 16, s);
-		if (e != cudaSuccess)
-			return cuda_fail("cudaMallocAsync", e);
+	if (pf == native || convert_fusable(native, pf))
+		return enqueue_decode(tf, d_blocks, width, height, wib, hib, d_pixels, pf, layout, mode_mask, flags, d_invalid, nullptr, s);
+	// Decode + conversion pass, slab by slab through ONE scratch buffer small enough to stay in the
+	// 126 MB L2: the native-format pixels of a slab are read back by the conversion kernel before
+	// they are evicted, so HBM sees the compressed input and the converted output only.
+	const int bb = block_bytes(tf), ps = pixel_size(pf), ps_native = pixel_size(native);
+	const size_t slab_budget = 24u << 20;
+	cudaError_t e = cudaMallocAsync(&tmp, slab_budget + (size_t)wib * 64 * ps_native + 1024 * 16 * ps_native, s);
+	if (e != cudaSuccess)
+		return cuda_fail("cudaMallocAsync", e);
+	int rc = DETEXB200_OK;
+	if (layout == DETEXB200_LAYOUT_LINEAR) {
+		const size_t row_bytes = (size_t)width * 4 * ps_native;
+		int rows_per_slab = (int)(slab_budget / (row_bytes ? row_bytes : 1));
+		if (rows_per_slab < 1)
+			rows_per_slab = 1;
+		for (int r0 = 0; r0 < hib && rc == DETEXB200_OK; r0 += rows_per_slab) {
+			const int rows = (hib - r0) < rows_per_slab ? (hib - r0) : rows_per_slab;
+			int slab_h = height - r0 * 4;
+			if (slab_h > rows * 4)
+				slab_h = rows * 4;
+			if (slab_h < 0)
+				slab_h = 0;
+			rc = enqueue_decode(tf, (const uint8_t *)d_blocks + (size_t)r0 * wib * bb, width, slab_h, wib, rows,
+				(uint8_t *)d_pixels + (size_t)r0 * 4 * width * ps, pf, layout, mode_mask, flags, d_invalid, tmp, s);
+		}
 	}
-	const int rc = enqueue_decode(tf, d_blocks, width, height, wib, hib, d_pixels, pf, layout, mode_mask, flags, d_invalid, tmp, s);
-	if (tmp)
-		cudaFreeAsync(tmp, s);
+	else {
+		const uint64_t n_blocks = (uint64_t)wib * hib;
+		uint64_t per_slab = (slab_budget / (16u * ps_native)) & ~1023ull;
+		if (per_slab < 1024)
+			per_slab = 1024;
+		for (uint64_t b0 = 0; b0 < n_blocks && rc == DETEXB200_OK; b0 += per_slab) {
+			const uint64_t count = (n_blocks - b0) < per_slab ? (n_blocks - b0) : per_slab;
+			rc = enqueue_decode(tf, (const uint8_t *)d_blocks + b0 * bb, (int)count * 4, 4, (int)count, 1,
+				(uint8_t *)d_pixels + b0 * 16 * ps, pf, layout, mode_mask, flags, d_invalid, tmp, s);
+		}
+	}
+	cudaFreeAsync(tmp, s);
 	return rc;
+}
+
+int detexb200ConversionPlan(uint32_t spf, uint32_t tpf, uint32_t formats_out[5]) {
+	int steps[4];
+	const int n = convert_plan(spf, tpf, steps);
+	if (n < 0)
+		return -1;
+	formats_out[0] = spf;
+	for (int i = 0; i < n; i++) {
+		uint32_t a, b;
+		conversion_table_entry(steps[i], &a, &b);
+		formats_out[i + 1] = b;
+	}
+	return n;
+}
+
+void detexSetHDRParameters(float gamma, float range_min, float range_max) {
+	set_hdr_parameters(gamma, range_min, range_max);
 }
 
 int detexb200ConvertPixelsDevice(const void *d_src, uint64_t n, uint32_t spf, void *d_dst, uint32_t tpf, void *stream) {
@@ -486,9 +535,21 @@ bool detexConvertPixels(uint8_t *src, uint32_t n, uint32_t spf, uint8_t *dst, ui
 
 // convert.c:1168-1171 (+ :1100-1113): only conversions that keep the pixel size.
 bool detexConvertPixelsInPlace(uint8_t *buf, uint32_t n, uint32_t spf, uint32_t tpf) {
-	if (pixel_size(spf) != pixel_size(tpf) || !convert_supported(spf, tpf)) {
-		set_error("Unable to find in-place conversion path");		// convert.c:1112
+	if (spf == tpf)
+		return true;
+	int steps[4];
+	const int n_steps = convert_plan(spf, tpf, steps);
+	if (n_steps < 0) {
+		set_error("detexConvertPixels: Unable to find conversion path");	// convert.c:1096
 		return false;
+	}
+	for (int i = 0; i < n_steps; i++) {		// every step of the chain has to keep the pixel size
+		uint32_t a, b;
+		conversion_table_entry(steps[i], &a, &b);
+		if (pixel_size(a) != pixel_size(b)) {
+			set_error("Unable to find in-place conversion path");		// convert.c:1112
+			return false;
+		}
 	}
 	return detexConvertPixels(buf, n, spf, buf, tpf);
 }

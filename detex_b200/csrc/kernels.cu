@@ -159,10 +159,11 @@ struct LinearTuneAtLimit { static constexpr int ITERS = 1; static constexpr bool
 template <> struct LinearTune<F_BC1> : LinearTuneAtLimit {};
 template <> struct LinearTune<F_BC1A> : LinearTuneAtLimit {};
 template <> struct LinearTune<F_BC2> { static constexpr int ITERS = 1; static constexpr bool EXIT_BARRIER = false; };
-#ifndef DETEXB200_TILED_ITERS
-#define DETEXB200_TILED_ITERS 1
-#endif
-template <int F> struct TiledTune { static constexpr int ITERS = DeferTraits<F>::ENABLED ? 1 : DETEXB200_TILED_ITERS; };
+// TILED kernel: tiles per warp pass.  Two gain 3-9 % on the formats that are not at the HBM limit.
+template <int F> struct TiledTune { static constexpr int ITERS = DeferTraits<F>::ENABLED ? 1 : 2; };
+template <> struct TiledTune<F_BC1> { static constexpr int ITERS = 1; };
+template <> struct TiledTune<F_BC1A> { static constexpr int ITERS = 1; };
+template <> struct TiledTune<F_BC2> { static constexpr int ITERS = 1; };
 
 // pixel rows of one block into a LINEAR image (fast path: rows are whole vector stores)
 template <int OW>
@@ -397,8 +398,13 @@ int wib, int hib, uint32_t mode_mask, uint32_t flags, uint32_t post_op, uint32_t
 			__syncthreads();
 		}
 	}
-	if constexpr (LinearTune<F>::EXIT_BARRIER)
+	if constexpr (LinearTune<F>::EXIT_BARRIER) {
+#ifdef DETEXB200_EXIT_BARRIER_OR
+		bad = __syncthreads_or(bad ? 1 : 0) != 0;
+#else
 		__syncthreads();
+#endif
+	}
 	report_invalid(bad, invalid_flag);
 }
 

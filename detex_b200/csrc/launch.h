@@ -21,8 +21,13 @@ struct DecodeArgs {
 // Enqueue the decode of one texture in its native pixel format.  format_index = texture_format >> 24.
 cudaError_t launch_decode(int format_index, const DecodeArgs &args, cudaStream_t stream);
 
-// Pixel-format conversion on device (aux.cu); returns cudaErrorNotSupported for pairs
-// that are not implemented.
+// Pixel-format conversion on device (convert.cu).  convert_plan restates the reference's search
+// (convert.c:887-1045): number of steps (0 = identical formats, -1 = no path) and the indices of
+// the table entries used; launch_convert returns cudaErrorNotSupported when there is no path.
+int convert_plan(uint32_t source_pixel_format, uint32_t target_pixel_format, int steps[4]);
+int conversion_table_size();
+void conversion_table_entry(int index, uint32_t *source_pixel_format, uint32_t *target_pixel_format);
+void set_hdr_parameters(float gamma, float range_min, float range_max);	// thread-local, hdr.c:26-38
 bool convert_supported(uint32_t source_pixel_format, uint32_t target_pixel_format);
 // 0: the pair needs a separate conversion pass; 1: identical memory layout (X <-> A of the same
 // component order, a no-op); 2: R <-> B swap that the decode kernels fuse into their stores.

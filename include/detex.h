@@ -186,6 +186,10 @@ DETEX_API bool detexConvertPixels(uint8_t *source_pixel_buffer, uint32_t nu_pixe
 DETEX_API bool detexConvertPixelsInPlace(uint8_t *source_pixel_buffer, uint32_t nu_pixels,
 	uint32_t source_pixel_format, uint32_t target_pixel_format);
 
+/* Range / gamma used by the *_HDR source formats, reference detex.h:792-800 / hdr.c:26-38
+ * (thread-local; defaults gamma 1, range 0..1). */
+DETEX_API void detexSetHDRParameters(float gamma, float range_min, float range_max);
+
 /* Thread-local message of the last failure, reference detex.h:806 / misc.c:75-93. */
 DETEX_API const char *detexGetErrorMessage(void);
 

@@ -74,6 +74,15 @@ DETEXB200_API int detexb200ConvertPixelsDevice(const void *d_src, uint64_t nu_pi
 	uint32_t source_pixel_format, void *d_dst, uint32_t target_pixel_format, void *stream);
 
 /*
+ * The chain of formats detexConvertPixels goes through for a (source, target) pair: the
+ * reference's search over its conversion table (convert.c:887-1045) restated.  Returns the
+ * number of steps (0 for identical formats, at most 4) and writes the steps + 1 formats of
+ * the chain, source first, to formats_out[5]; returns -1 when there is no path.  Host only.
+ */
+DETEXB200_API int detexb200ConversionPlan(uint32_t source_pixel_format, uint32_t target_pixel_format,
+	uint32_t formats_out[5]);
+
+/*
  * Fill a device buffer with the counter-based splitmix64 block generator of
  * SURVEY.md 8c/8d (word j = mix(seed + (first_word + j + 1) * 0x9E3779B97F4A7C15)),
  * so that every shard / GPU can synthesise its own index range in HBM.

@@ -87,7 +87,99 @@ def _bind_detex_api(lib):
         f.argtypes, f.restype = [C.POINTER(DetexTexture), C.c_void_p, C.c_uint32], C.c_bool
     lib.detexConvertPixels.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32]
     lib.detexConvertPixels.restype = C.c_bool
+    lib.detexConvertPixelsInPlace.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32]
+    lib.detexConvertPixelsInPlace.restype = C.c_bool
+    lib.detexGetErrorMessage.argtypes, lib.detexGetErrorMessage.restype = [], C.c_char_p
+    lib.detexSetHDRParameters.argtypes = [C.c_float, C.c_float, C.c_float]
+    lib.detexSetHDRParameters.restype = None
+    if hasattr(lib, "oracle_conversion_chain"):
+        lib.oracle_conversion_chain.argtypes = [C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32)]
+        lib.oracle_conversion_chain.restype = C.c_int
     return lib
+
+
+# ---- pixel-format conversion helpers (tests only) -------------------------------------------
+PIXEL_FORMATS = {
+    "RGBA8": 0x334, "BGRA8": 0x33C, "RGBX8": 0x320, "BGRX8": 0x328, "RGB8": 0x220,
+    "R8": 0x0, "SIGNED_R8": 0x1000, "RG8": 0x110, "SIGNED_RG8": 0x1110,
+    "R16": 0x101, "SIGNED_R16": 0x1101, "RG16": 0x311, "SIGNED_RG16": 0x1311,
+    "RGB16": 0x521, "RGBX16": 0x721, "RGBA16": 0x735,
+    "FLOAT_R16": 0x2101, "FLOAT_R16_HDR": 0x6101, "FLOAT_RG16": 0x2311, "FLOAT_RG16_HDR": 0x6311,
+    "FLOAT_RGBX16": 0x2721, "FLOAT_RGBX16_HDR": 0x6721, "FLOAT_RGBA16": 0x6735,
+    "FLOAT_RGB16": 0x2521, "FLOAT_RGB16_HDR": 0x6521, "FLOAT_BGRX16": 0x2729,
+    "FLOAT_R32": 0x2302, "FLOAT_R32_HDR": 0x6302, "FLOAT_RG32": 0x2712, "FLOAT_RG32_HDR": 0x6712,
+    "FLOAT_RGB32": 0x2B22, "FLOAT_RGB32_HDR": 0x6B22, "FLOAT_RGBX32": 0x2F22, "FLOAT_RGBX32_HDR": 0x6F22,
+    # in no table entry: conversions from / to these must fail
+    "BGR8": 0x228, "A8": 0x4, "FLOAT_RGBA32": 0x2F36,
+}
+# (source, target) table entries whose reference implementation dereferences an uninitialised
+# pointer (convert.c:704: `uint16_t *target_pixel16_buffer = (uint16_t *)target_pixel16_buffer;`):
+# never call the compiled reference on a chain that contains one of them.
+REFERENCE_UB_STEPS = {(0x2721, 0x2521), (0x6721, 0x6521)}
+
+
+def pixel_size(pf):
+    return 1 + ((pf & 0xF00) >> 8)
+
+
+def synth_pixels(pf, n, seed=1):
+    """n pixels of format pf: raw random bits for integer formats; for float formats a mix of
+    in-range, out-of-range, tiny, huge, zero and infinite values (no NaNs: the reference is built
+    with -ffinite-math-only and its NaN behaviour is unspecified)."""
+    rng = np.random.default_rng(seed)
+    nbytes = n * pixel_size(pf)
+    if not (pf & 0x2000):
+        return rng.integers(0, 256, nbytes, dtype=np.uint8)
+    if (pf & 3) == 2:
+        m = nbytes // 4
+        v = rng.uniform(-0.5, 1.5, m).astype(np.float32)
+        k = rng.integers(0, 16, m)
+        v = np.where(k == 0, rng.uniform(-70000, 70000, m), v).astype(np.float32)
+        v = np.where(k == 1, rng.uniform(-1e-4, 1e-4, m), v).astype(np.float32)
+        v = np.where(k == 2, rng.uniform(-1e-7, 1e-7, m), v).astype(np.float32)
+        v = np.where(k == 3, np.float32(0.0), v)
+        v = np.where(k == 4, np.float32(-0.0), v)
+        v = np.where(k == 5, np.float32(np.inf), v)
+        v = np.where(k == 6, np.float32(-np.inf), v)
+        v = np.where(k == 7, np.float32(1e-41), v).astype(np.float32)
+        v = np.where(k == 8, rng.integers(0, 65536, m).astype(np.float32) / np.float32(65535.0), v).astype(np.float32)
+        return v.view(np.uint8).copy()
+    h = rng.integers(0, 65536, nbytes // 2).astype(np.uint16)
+    nan = ((h & 0x7C00) == 0x7C00) & ((h & 0x3FF) != 0)
+    h = np.where(nan, h & 0xFC00, h).astype(np.uint16)        # NaN -> infinity of the same sign
+    return h.view(np.uint8).copy()
+
+
+_libm = None
+
+
+def reset_rounding_mode():
+    """The reference leaves the calling thread in FE_DOWNWARD after some conversions
+    (half-float.c:306,317; hdr.c:122,171); put it back to nearest before the next call."""
+    global _libm
+    if _libm is None:
+        _libm = C.CDLL("libm.so.6")
+    _libm.fesetround(0)
+
+
+def convert_pixels(lib, src, n, spf, tpf, primed=False):
+    """detexConvertPixels through lib; returns (ok, uint8 array of n target pixels).
+    primed=True runs the call with the thread in FE_DOWNWARD, the state the reference leaves
+    behind after any float -> uint16 conversion (half-float.c:306)."""
+    reset_rounding_mode()
+    if primed:
+        _libm.fesetround(0x400)
+    src = np.ascontiguousarray(src, dtype=np.uint8).copy()
+    out = np.zeros(n * pixel_size(tpf) + 64, dtype=np.uint8)
+    ok = lib.detexConvertPixels(src.ctypes.data, n, spf, out.ctypes.data, tpf)
+    reset_rounding_mode()
+    return bool(ok), out[: n * pixel_size(tpf)]
+
+
+def conversion_chain(oracle, spf, tpf):
+    f = (C.c_uint32 * 5)()
+    n = oracle.oracle_conversion_chain(spf, tpf, f)
+    return None if n < 0 else [int(f[i]) for i in range(n + 1)]
 
 
 _cache = {}
