@@ -136,10 +136,14 @@ uint32_t pf, int layout, uint32_t mode_mask, uint32_t flags, uint32_t *d_invalid
 	a.flags = flags;
 	a.invalid = d_invalid;
 	a.post_op = 0;
+	a.post_class = 0;
 	cudaError_t e;
-	const int fuse = pf == native ? 1 : convert_fusable(native, pf);
-	if (fuse) {		// native layout, or an R<->B swap done in the kernels' store epilogue
-		a.post_op = fuse == 2 ? 1u : 0u;
+	// Conversions the kernels do while storing: R<->B swap, sign flip, dropping the fourth component,
+	// 16 -> 8 bit.  Repacked tiles need a 32-byte aligned target (else: separate conversion pass).
+	const FusedConversion fuse = convert_fused(native, pf);
+	if (fuse.ok && (fuse.post_class == 0 || (((uintptr_t)d_pixels) & 31u) == 0)) {
+		a.post_op = fuse.post_op;
+		a.post_class = fuse.post_class;
 		a.pixels = d_pixels;
 		if ((e = launch_decode((int)(tf >> 24), a, stream)) != cudaSuccess)
 			return cuda_fail("decode kernel launch", e);
@@ -205,7 +209,8 @@ bool decode_texture_host(const detexTexture *t, uint8_t *pixel_buffer, uint32_t 
 	const int bb = block_bytes(tf), ps = pixel_size(pf), ps_native = pixel_size(native);
 	const size_t in_bytes = n_blocks * bb;
 	const size_t out_bytes = layout == DETEXB200_LAYOUT_LINEAR ? (size_t)t->width * t->height * ps : n_blocks * 16 * ps;
-	const size_t tmp_bytes = (pf == native || convert_fusable(native, pf)) ? 0 : n_blocks * 16 * ps_native;
+	const FusedConversion fuse = convert_fused(native, pf);
+	const size_t tmp_bytes = (fuse.ok && fuse.post_class == 0) ? 0 : n_blocks * 16 * ps_native;
 	if (!c.reserve(&c.d_in, &c.cap_in, in_bytes) || !c.reserve(&c.d_out, &c.cap_out, out_bytes + 16) ||
 	    (tmp_bytes && !c.reserve(&c.d_tmp, &c.cap_tmp, tmp_bytes)))
 		return false;
@@ -355,7 +360,8 @@ void *d_pixels, uint32_t pf, int layout, uint32_t mode_mask, uint32_t flags, uin
 		set_error("detexConvertPixels: Unable to find conversion path (0x%04X -> 0x%04X on device)", native, pf);
 		return DETEXB200_EUNSUPPORTED;
 	}
-	if (pf == native || convert_fusable(native, pf))
+	const FusedConversion fuse = convert_fused(native, pf);
+	if (fuse.ok && (fuse.post_class == 0 || (((uintptr_t)d_pixels) & 31u) == 0))
 		return enqueue_decode(tf, d_blocks, width, height, wib, hib, d_pixels, pf, layout, mode_mask, flags, d_invalid, nullptr, s);
 	// Decode + conversion pass, slab by slab through ONE scratch buffer small enough to stay in the
 	// 126 MB L2: the native-format pixels of a slab are read back by the conversion kernel before

@@ -163,22 +163,50 @@ bool convert_supported(uint32_t s, uint32_t d) {
 	return convert_plan(s, d, steps) >= 0;
 }
 
-// 1: the chain does not change any byte (X <-> A relabelling); 2: it is exactly one R <-> B swap of
-// 4-component pixels plus relabelling, which the decode kernels fuse into their stores; 0: other.
-int convert_fusable(uint32_t s, uint32_t d) {
+// Which conversions the decode kernels absorb into their store epilogue (kernels.cu, "post op" and
+// "post class"): relabelling steps anywhere, at most one R <-> B swap of four-component pixels, at
+// most one sign flip, and -- last -- at most one step that shrinks the pixel: dropping the fourth
+// component, or narrowing one / two 16-bit components to 8 bits.
+FusedConversion convert_fused(uint32_t s, uint32_t d) {
+	FusedConversion f = { false, 0u, 0 };
+	if (s == d) {
+		f.ok = true;
+		return f;
+	}
 	int steps[4];
 	const int n = convert_plan(s, d, steps);
-	if (n <= 0 || pixel_bytes(s) != pixel_bytes(d))
-		return 0;
-	int swaps = 0;
+	if (n <= 0)
+		return f;
+	bool shrunk = false;
 	for (int i = 0; i < n; i++) {
 		const TableEntry &e = conversion_table[steps[i]];
-		if (e.op == ST_SWAP_RB)
-			swaps++;
-		else if (e.op != ST_KEEP || pixel_bytes(e.source) != pixel_bytes(e.target))
-			return 0;
+		const int ps_in = pixel_bytes(e.source), ps_out = pixel_bytes(e.target), cs = component_bytes(e.source);
+		if (shrunk)
+			return f;				// nothing may follow the size change
+		if (e.op == ST_KEEP && ps_in == ps_out)
+			continue;
+		if (e.op == ST_SWAP_RB && ps_in / cs == 4 && !(f.post_op & 1u)) {
+			f.post_op |= 1u;
+			continue;
+		}
+		if (e.op == ST_FLIP_SIGN && !(f.post_op & 6u)) {
+			f.post_op |= cs == 2 ? 2u : 4u;
+			continue;
+		}
+		if (e.op == ST_KEEP && ps_in / cs == 4 && ps_out * 4 == ps_in * 3 && (cs == 1 || cs == 2)) {
+			f.post_class = 1;			// RGBX8 -> RGB8, FLOAT_RGBX16 -> FLOAT_RGB16
+			shrunk = true;
+			continue;
+		}
+		if (e.op == ST_NARROW && ps_in / cs <= 2) {
+			f.post_class = 2;			// R16 -> R8, RG16 -> RG8
+			shrunk = true;
+			continue;
+		}
+		return f;
 	}
-	return swaps == 0 ? 1 : (swaps == 1 ? 2 : 0);
+	f.ok = true;
+	return f;
 }
 
 // ---- HDR parameters (reference hdr.c:26-38: thread-local gamma and range) -----------------------
@@ -237,7 +265,14 @@ __device__ __forceinline__ uint32_t half_to_float_bits(uint32_t h) {
 
 // detexClamp0To1 (detex.h:941-948) as the shipped -Ofast build evaluates it with max / min
 // instructions: everything that is not greater than zero, -0.0 included, becomes +0.0.
-__device__ __forceinline__ float clamp01(float f) { return f > 0.0f ? (f > 1.0f ? 1.0f : f) : 0.0f; }
+// Decided on the bit pattern so that no min / max instruction selection can bring the sign of a
+// negative zero or a negative denormal back.
+__device__ __forceinline__ float clamp01(float f) {
+	const uint32_t b = __float_as_uint(f);
+	if ((b >> 31) != 0u || (b << 1) == 0u || (b << 1) > 0xFF000000u)	// negative, zero or NaN
+		return 0.0f;
+	return f > 1.0f ? 1.0f : f;
+}
 
 // lrintf(clamp(f) * 65535 + 0.5) with the rounding mode the reference selects, FE_DOWNWARD
 // (half-float.c:306-310, :317-321): product, sum and float -> int all round towards -infinity.

@@ -85,13 +85,23 @@ uint32_t mode_mask, uint32_t flags, const BptcTables *tab, uint32_t (&px)[Format
 	else return decode_eac_rg11<true>(blk, mode_mask, flags, px);
 }
 
-// Output-format conversion fused into the store epilogue: R <-> B swap of
-// 32-bit RGBA8/RGBX8 pixels (-> BGRA8/BGRX8, reference convert.c:37-52) or of 64-bit
-// FLOAT_RGBX16 pixels (-> FLOAT_BGRX16, convert.c:54-70).  post_op is uniform over the launch.
-constexpr uint32_t POST_NONE = 0, POST_SWAP_RB = 1;
+// Output-format conversion fused into the store epilogue.
+//   post_op (run-time, uniform over the launch) edits the decoded pixels in place:
+//     POST_SWAP_RB  R <-> B of 32-bit RGBA8/RGBX8 pixels (-> BGRA8/BGRX8, reference convert.c:37-52)
+//                   or of 64-bit FLOAT_RGBX16 pixels (-> FLOAT_BGRX16, convert.c:54-70);
+//     POST_FLIP16   signed <-> unsigned 16-bit components (+-32768, convert.c:139-186);
+//     POST_FLIP8    signed <-> unsigned 8-bit components (+-128, convert.c:89-136).
+//   The post class (compile-time, it changes the size of the stored tile) repacks them:
+//     PC_PACK3      drop the fourth component: RGBX8/RGBA8 -> RGB8 (convert.c:671-690),
+//                   FLOAT_RGBX16 -> FLOAT_RGB16 (convert.c:700-716);
+//     PC_NARROW     16-bit -> 8-bit components (v + 127) * 255 / 65535: R16 -> R8, RG16 -> RG8
+//                   (convert.c:263-290).
+constexpr uint32_t POST_NONE = 0, POST_SWAP_RB = 1, POST_FLIP16 = 2, POST_FLIP8 = 4;
+constexpr int PC_NATIVE = 0, PC_PACK3 = 1, PC_NARROW = 2;
+
 template <int OW>
 __device__ __forceinline__ void apply_post_op(uint32_t (&px)[OW], uint32_t post_op) {
-	if (post_op == POST_SWAP_RB) {
+	if (post_op & POST_SWAP_RB) {
 		if constexpr (OW == 16) {
 #pragma unroll
 			for (int k = 0; k < 16; k++)
@@ -105,6 +115,78 @@ __device__ __forceinline__ void apply_post_op(uint32_t (&px)[OW], uint32_t post_
 				px[2 * k + 1] = prmt(lo, hi, 0x7610);				// R|X<<16
 			}
 		}
+	}
+	if constexpr (OW <= 16) {		// one- and two-component formats (the API sets these bits only for them)
+		if (post_op & (POST_FLIP16 | POST_FLIP8)) {
+			const uint32_t top = (post_op & POST_FLIP16) ? 0x80008000u : 0x80808080u;
+#pragma unroll
+			for (int k = 0; k < OW; k++)
+				px[k] ^= top;
+		}
+	}
+}
+
+// words per decoded tile after the post class
+template <int OW, int PC> constexpr int post_words() { return PC == PC_PACK3 ? OW * 3 / 4 : (PC == PC_NARROW ? OW / 2 : OW); }
+// which (format, class) pairs exist: PACK3 for the four-component 8-bit formats and BC6H unsigned,
+// NARROW for the 16-bit one- and two-component formats
+template <int F, int PC> constexpr bool post_class_valid() {
+	constexpr int OW = FormatTraits<F>::OUT_WORDS;
+	if (PC == PC_NATIVE)
+		return true;
+	if (PC == PC_PACK3)
+		return (OW == 16 && F != F_EAC_RG11 && F != F_EAC_SIGNED_RG11 && F != F_SIGNED_RGTC2) || F == F_BPTC_FLOAT;
+	return F == F_EAC_R11 || F == F_EAC_SIGNED_R11 || F == F_EAC_RG11 || F == F_EAC_SIGNED_RG11 ||
+		F == F_SIGNED_RGTC1 || F == F_SIGNED_RGTC2;
+}
+
+__device__ __forceinline__ uint32_t narrow16(uint32_t v) { return ((v + 127u) * 255u) / 65535u; }
+// two 16-bit components of one word -> two bytes
+__device__ __forceinline__ uint32_t narrow_pair(uint32_t w) { return narrow16(w & 0xFFFFu) | (narrow16(w >> 16) << 8); }
+
+template <int PC, int OW>
+__device__ __forceinline__ void repack(const uint32_t (&px)[OW], uint32_t (&q)[post_words<OW, PC>()]) {
+	if constexpr (PC == PC_PACK3 && OW == 16) {
+#pragma unroll
+		for (int r = 0; r < 4; r++) {			// R0G0B0R1 | G1B1R2G2 | B2R3G3B3
+			q[3 * r] = prmt(px[4 * r], px[4 * r + 1], 0x4210);
+			q[3 * r + 1] = prmt(px[4 * r + 1], px[4 * r + 2], 0x5421);
+			q[3 * r + 2] = prmt(px[4 * r + 2], px[4 * r + 3], 0x6542);
+		}
+	}
+	else if constexpr (PC == PC_PACK3 && OW == 32) {
+#pragma unroll
+		for (int h = 0; h < 8; h++) {			// pixel pairs: R0G0 | B0R1 | G1B1
+			const uint32_t lo0 = px[4 * h], hi0 = px[4 * h + 1], lo1 = px[4 * h + 2], hi1 = px[4 * h + 3];
+			q[3 * h] = lo0;
+			q[3 * h + 1] = prmt(hi0, lo1, 0x5410);
+			q[3 * h + 2] = prmt(lo1, hi1, 0x5432);
+		}
+	}
+	else if constexpr (PC == PC_NARROW && OW == 8) {	// R16: two pixels per word -> four per word
+#pragma unroll
+		for (int r = 0; r < 4; r++)
+			q[r] = narrow_pair(px[2 * r]) | (narrow_pair(px[2 * r + 1]) << 16);
+	}
+	else {							// RG16: one pixel per word -> two per word
+		static_assert(PC == PC_NARROW && OW == 16, "unsupported post class");
+#pragma unroll
+		for (int k = 0; k < 8; k++)
+			q[k] = narrow_pair(px[2 * k]) | (narrow_pair(px[2 * k + 1]) << 16);
+	}
+}
+
+// post_op, then hand the words that go to memory to store(words): the decoded array itself for
+// the native class, a repacked one otherwise.
+template <int PC, int OW, typename Store>
+__device__ __forceinline__ void emit(uint32_t (&px)[OW], uint32_t post_op, Store &&store) {
+	apply_post_op<OW>(px, post_op);
+	if constexpr (PC == PC_NATIVE)
+		store(px);
+	else {
+		uint32_t q[post_words<OW, PC>()];
+		repack<PC, OW>(px, q);
+		store(q);
 	}
 }
 
@@ -181,8 +263,18 @@ __device__ __forceinline__ void store_linear_rows(uint8_t *dst, size_t pitch, in
 				st_stream_u32(p, px[r]);
 			else if constexpr (ROW_WORDS == 2)
 				st_stream_v2(p, px[2 * r], px[2 * r + 1]);
+			else if constexpr (ROW_WORDS == 3) {		// 12-byte RGB8 rows
+				st_stream_u32(p, px[3 * r]);
+				st_stream_u32(p + 4, px[3 * r + 1]);
+				st_stream_u32(p + 8, px[3 * r + 2]);
+			}
 			else if constexpr (ROW_WORDS == 4)
 				st_stream_v4(p, px[4 * r], px[4 * r + 1], px[4 * r + 2], px[4 * r + 3]);
+			else if constexpr (ROW_WORDS == 6) {		// 24-byte FLOAT_RGB16 rows
+				st_stream_v2(p, px[6 * r], px[6 * r + 1]);
+				st_stream_v2(p + 8, px[6 * r + 2], px[6 * r + 3]);
+				st_stream_v2(p + 16, px[6 * r + 4], px[6 * r + 5]);
+			}
 			else if (wide_ok)
 				st_stream_v8(p, px[8 * r], px[8 * r + 1], px[8 * r + 2], px[8 * r + 3],
 					px[8 * r + 4], px[8 * r + 5], px[8 * r + 6], px[8 * r + 7]);
@@ -197,13 +289,14 @@ __device__ __forceinline__ void store_linear_rows(uint8_t *dst, size_t pitch, in
 // ---- TILED --------------------------------------------------------------------------------
 // DIRECT: every lane writes its own tile with 256-bit stores (tiles of >= 32 bytes on a 32-byte
 // aligned destination) instead of transposing the warp's tiles through shared memory.
-template <int F, bool DIRECT>
+template <int F, bool DIRECT, int PC>
 __global__ void __launch_bounds__(CTA_THREADS)
 decode_tiled_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, uint32_t n_blocks,
 uint32_t mode_mask, uint32_t flags, uint32_t post_op, uint32_t *invalid_flag) {
 	using T = FormatTraits<F>;
 	using D = DeferTraits<F>;
-	constexpr int BW = T::BLOCK_WORDS, OW = T::OUT_WORDS, CHUNKS = OW / 4;
+	constexpr int BW = T::BLOCK_WORDS, OW = T::OUT_WORDS, OWO = post_words<OW, PC>(), CHUNKS = OWO / 4;
+	static_assert(PC == PC_NATIVE || DIRECT, "repacked tiles are stored directly");
 	__shared__ BptcTables tables;
 	__shared__ uint4 stage[CHUNKS > 1 && !DIRECT ? CTA_WARPS * 32 * CHUNKS : 1];
 	__shared__ uint32_t queue[D::ENABLED ? CTA_THREADS * DEFER_ITERS : 1];
@@ -243,20 +336,29 @@ uint32_t mode_mask, uint32_t flags, uint32_t post_op, uint32_t *invalid_flag) {
 				for (int w = 0; w < OW; w++)
 					px[w] = 0u;
 			}
-			apply_post_op<OW>(px, post_op);
 			const unsigned rare_mask = D::ENABLED ? __ballot_sync(0xFFFFFFFFu, rare) : 0u;
-			if (tile < n_tiles) {
-				uint8_t *tile_out = dst + (size_t)first * (OW * 4);
+			emit<PC>(px, post_op, [&](auto &w) {
+				if (tile >= n_tiles)
+					return;
+				uint8_t *tile_out = dst + (size_t)first * (OWO * 4);
 				if constexpr (CHUNKS == 1) {
 					if (active && !rare)
-						st_stream_v4(tile_out + lane * 16, px[0], px[1], px[2], px[3]);
+						st_stream_v4(tile_out + lane * 16, w[0], w[1], w[2], w[3]);
 				}
 				else if constexpr (DIRECT) {
 					if (active && !rare) {
+						uint8_t *mine = tile_out + lane * (OWO * 4);
+						if constexpr (CHUNKS % 2 == 0) {
 #pragma unroll
-						for (int c = 0; c < CHUNKS; c += 2)
-							st_stream_v8(tile_out + lane * (OW * 4) + 16 * c, px[4 * c], px[4 * c + 1], px[4 * c + 2],
-								px[4 * c + 3], px[4 * c + 4], px[4 * c + 5], px[4 * c + 6], px[4 * c + 7]);
+							for (int c = 0; c < CHUNKS; c += 2)
+								st_stream_v8(mine + 16 * c, w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3],
+									w[4 * c + 4], w[4 * c + 5], w[4 * c + 6], w[4 * c + 7]);
+						}
+						else {
+#pragma unroll
+							for (int c = 0; c < CHUNKS; c++)
+								st_stream_v4(mine + 16 * c, w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
+						}
 					}
 				}
 				else {
@@ -269,7 +371,7 @@ uint32_t mode_mask, uint32_t flags, uint32_t post_op, uint32_t *invalid_flag) {
 					const int swz = (lane / GROUP) % CHUNKS;
 #pragma unroll
 					for (int c = 0; c < CHUNKS; c++)
-						buf[lane * CHUNKS + (c ^ swz)] = make_uint4(px[4 * c], px[4 * c + 1], px[4 * c + 2], px[4 * c + 3]);
+						buf[lane * CHUNKS + (c ^ swz)] = make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
 					__syncwarp();
 					const uint32_t valid_chunks = min(32u, n_blocks - first) * CHUNKS;
 #pragma unroll
@@ -282,7 +384,7 @@ uint32_t mode_mask, uint32_t flags, uint32_t post_op, uint32_t *invalid_flag) {
 					}
 					__syncwarp();
 				}
-			}
+			});
 			if constexpr (D::ENABLED) {
 				if (rare)
 					queue[atomicAdd(&queue_n, 1)] = i;
@@ -305,11 +407,12 @@ uint32_t mode_mask, uint32_t flags, uint32_t post_op, uint32_t *invalid_flag) {
 					for (int k = 0; k < OW; k++)
 						qx[k] = 0u;
 				}
-				apply_post_op<OW>(qx, post_op);
-				uint8_t *out = dst + (size_t)j * (OW * 4);
+				emit<PC>(qx, post_op, [&](auto &w) {
+					uint8_t *out = dst + (size_t)j * (OWO * 4);
 #pragma unroll
-				for (int c = 0; c < CHUNKS; c++)
-					st_stream_v4(out + 16 * c, qx[4 * c], qx[4 * c + 1], qx[4 * c + 2], qx[4 * c + 3]);
+					for (int c = 0; c < CHUNKS; c++)
+						st_stream_v4(out + 16 * c, w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
+				});
 			}
 			__syncthreads();
 			if (threadIdx.x == 0)
@@ -323,13 +426,13 @@ uint32_t mode_mask, uint32_t flags, uint32_t post_op, uint32_t *invalid_flag) {
 // ---- LINEAR, fast path: width % 4 == 0 and 16-byte aligned output ---------------------------
 // blockDim = (TX, TY): thread (x, y) decodes block (blockIdx.x*TX + x, by) with by
 // grid-strided over block rows.
-template <int F>
+template <int F, int PC>
 __global__ void __launch_bounds__(CTA_THREADS)
 decode_linear_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, int width, int height,
 int wib, int hib, uint32_t mode_mask, uint32_t flags, uint32_t post_op, uint32_t *invalid_flag) {
 	using T = FormatTraits<F>;
 	using D = DeferTraits<F>;
-	constexpr int BW = T::BLOCK_WORDS, OW = T::OUT_WORDS, ROW_BYTES = OW;
+	constexpr int BW = T::BLOCK_WORDS, OW = T::OUT_WORDS, ROW_BYTES = post_words<OW, PC>();
 	__shared__ BptcTables tables;
 	__shared__ uint32_t queue[D::ENABLED ? CTA_THREADS * DEFER_ITERS : 1];
 	__shared__ int queue_n;
@@ -369,8 +472,7 @@ int wib, int hib, uint32_t mode_mask, uint32_t flags, uint32_t post_op, uint32_t
 						for (int j = 0; j < OW; j++)
 							px[j] = 0u;
 					}
-					apply_post_op<OW>(px, post_op);
-					store_linear_rows<OW>(dst, pitch, bx, by, height, px);
+					emit<PC>(px, post_op, [&](auto &w) { store_linear_rows(dst, pitch, bx, by, height, w); });
 				}
 			}
 		}
@@ -389,8 +491,7 @@ int wib, int hib, uint32_t mode_mask, uint32_t flags, uint32_t post_op, uint32_t
 					for (int jj = 0; jj < OW; jj++)
 						qp[jj] = 0u;
 				}
-				apply_post_op<OW>(qp, post_op);
-				store_linear_rows<OW>(dst, pitch, qx_, qy, height, qp);
+				emit<PC>(qp, post_op, [&](auto &w) { store_linear_rows(dst, pitch, qx_, qy, height, w); });
 			}
 			__syncthreads();
 			if (tid == 0)
@@ -398,23 +499,18 @@ int wib, int hib, uint32_t mode_mask, uint32_t flags, uint32_t post_op, uint32_t
 			__syncthreads();
 		}
 	}
-	if constexpr (LinearTune<F>::EXIT_BARRIER) {
-#ifdef DETEXB200_EXIT_BARRIER_OR
-		bad = __syncthreads_or(bad ? 1 : 0) != 0;
-#else
-		__syncthreads();
-#endif
-	}
+	if constexpr (LinearTune<F>::EXIT_BARRIER)
+		bad = __syncthreads_or(bad ? 1 : 0) != 0;	// (measured: the reducing barrier, not a plain one)
 	report_invalid(bad, invalid_flag);
 }
 
 // ---- LINEAR, general path: any width / alignment, byte-granular clipped stores -------------
-template <int F>
+template <int F, int PC>
 __global__ void __launch_bounds__(CTA_THREADS)
 decode_linear_clipped_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, int width, int height,
 int wib, int hib, uint32_t mode_mask, uint32_t flags, uint32_t post_op, uint32_t *invalid_flag) {
 	using T = FormatTraits<F>;
-	constexpr int BW = T::BLOCK_WORDS, OW = T::OUT_WORDS, PS = OW / 4;	// PS = bytes per pixel
+	constexpr int BW = T::BLOCK_WORDS, OW = T::OUT_WORDS, PS = post_words<OW, PC>() / 4;	// PS = bytes per stored pixel
 	__shared__ BptcTables tables;
 	if constexpr (T::USES_TABLES) {
 		bptc_tables_load(tables);
@@ -432,20 +528,21 @@ int wib, int hib, uint32_t mode_mask, uint32_t flags, uint32_t post_op, uint32_t
 			for (int k = 0; k < OW; k++)
 				px[k] = 0u;
 		}
-		apply_post_op<OW>(px, post_op);
 		const int rows = min(4, height - by * 4), cols = min(4, width - bx * 4);
+		emit<PC>(px, post_op, [&](auto &w) {
 #pragma unroll
-		for (int r = 0; r < 4; r++)
+			for (int r = 0; r < 4; r++)
 #pragma unroll
-			for (int x = 0; x < 4; x++)
-				if (r < rows && x < cols) {
-					uint8_t *p = dst + ((size_t)(by * 4 + r) * width + (size_t)(bx * 4 + x)) * PS;
+				for (int x = 0; x < 4; x++)
+					if (r < rows && x < cols) {
+						uint8_t *p = dst + ((size_t)(by * 4 + r) * width + (size_t)(bx * 4 + x)) * PS;
 #pragma unroll
-					for (int b = 0; b < PS; b++) {
-						const int byte_index = (r * 4 + x) * PS + b;
-						p[b] = (uint8_t)(px[byte_index >> 2] >> (8 * (byte_index & 3)));
+						for (int b = 0; b < PS; b++) {
+							const int byte_index = (r * 4 + x) * PS + b;
+							p[b] = (uint8_t)(w[byte_index >> 2] >> (8 * (byte_index & 3)));
+						}
 					}
-				}
+		});
 	}
 	report_invalid(bad, invalid_flag);
 }
@@ -541,7 +638,7 @@ __device__ __forceinline__ uint32_t raw_slot(uint32_t id) { return id ^ ((id >> 
 //           holds start[b]), ids scattered to their sorted slots, barrier
 //   decode  each warp takes groups of 32 same-mode blocks -> pixels parked in shared memory
 //   store   barrier, cooperative copy-out, 512 contiguous bytes per warp store instruction
-template <int F, int LAYOUT, bool STAGE>
+template <int F, int LAYOUT, bool STAGE, int PC>
 __global__ void __launch_bounds__(SORT_THREADS, 2)
 decode_sorted_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, uint32_t n_blocks, int width,
 int height, int wib, uint32_t mode_mask, uint32_t flags, uint32_t post_op, uint32_t *invalid_flag) {
@@ -640,30 +737,36 @@ int height, int wib, uint32_t mode_mask, uint32_t flags, uint32_t post_op, uint3
 					for (int k = 0; k < OW; k++)
 						px[k] = 0u;
 				}
-				apply_post_op<OW>(px, post_op);
 				if constexpr (STAGE) {
+					// staged in the native layout; a post class is applied by the copy-out below
+					apply_post_op<OW>(px, post_op);
 #pragma unroll
 					for (int c = 0; c < CHUNKS; c++)
 						sm.out[stage_slot<TB, CHUNKS>(id, c)] = make_uint4(px[4 * c], px[4 * c + 1], px[4 * c + 2], px[4 * c + 3]);
 				}
-				else if (LAYOUT == LAYOUT_TILED) {
-					uint8_t *out = dst + (size_t)(tile0 + id) * (OW * 4);
-					if ((((uintptr_t)dst) & 31u) == 0) {
-#pragma unroll
-						for (int c = 0; c < CHUNKS; c += 2)
-							st_stream_v8(out + 16 * c, px[4 * c], px[4 * c + 1], px[4 * c + 2], px[4 * c + 3],
-								px[4 * c + 4], px[4 * c + 5], px[4 * c + 6], px[4 * c + 7]);
-					}
-					else {
-#pragma unroll
-						for (int c = 0; c < CHUNKS; c++)
-							st_stream_v4(out + 16 * c, px[4 * c], px[4 * c + 1], px[4 * c + 2], px[4 * c + 3]);
-					}
-				}
 				else {
-					const uint32_t i = tile0 + id;
-					const uint32_t by = i / (uint32_t)wib, bx = i - by * (uint32_t)wib;
-					store_linear_rows<OW>(dst, (size_t)width * (OW / 4), (int)bx, (int)by, height, px);
+					emit<PC>(px, post_op, [&](auto &w) {
+						constexpr int OWO = post_words<OW, PC>(), CH = OWO / 4;
+						if (LAYOUT == LAYOUT_TILED) {
+							uint8_t *out = dst + (size_t)(tile0 + id) * (OWO * 4);
+							if (CH % 2 == 0 && (((uintptr_t)dst) & 31u) == 0) {
+#pragma unroll
+								for (int c = 0; c + 1 < CH; c += 2)
+									st_stream_v8(out + 16 * c, w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3],
+										w[4 * c + 4], w[4 * c + 5], w[4 * c + 6], w[4 * c + 7]);
+							}
+							else {
+#pragma unroll
+								for (int c = 0; c < CH; c++)
+									st_stream_v4(out + 16 * c, w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
+							}
+						}
+						else {
+							const uint32_t i = tile0 + id;
+							const uint32_t by = i / (uint32_t)wib, bx = i - by * (uint32_t)wib;
+							store_linear_rows(dst, (size_t)width * (OWO / 4), (int)bx, (int)by, height, w);
+						}
+					});
 				}
 			}
 		}
@@ -671,6 +774,8 @@ int height, int wib, uint32_t mode_mask, uint32_t flags, uint32_t post_op, uint3
 			continue;		// direct stores: the barrier at the loop top is enough
 		__syncthreads();
 		// ---- store
+		static_assert(!STAGE || PC == PC_NATIVE || (PC == PC_PACK3 && LAYOUT == LAYOUT_LINEAR && OW == 16),
+			"staged copy-out repacks RGB8 rows only");
 		if (LAYOUT == LAYOUT_TILED) {
 			uint8_t *out = dst + (size_t)tile0 * (OW * 4);
 			for (uint32_t q = tid; q < n_here * CHUNKS; q += SORT_THREADS) {
@@ -679,7 +784,7 @@ int height, int wib, uint32_t mode_mask, uint32_t flags, uint32_t post_op, uint3
 			}
 		}
 		else {
-			constexpr int ROW_BYTES = OW;		// bytes of one pixel row of one block
+			constexpr int ROW_BYTES = post_words<OW, PC>();	// bytes of one stored pixel row of one block
 			const size_t pitch = (size_t)width * (ROW_BYTES / 4);
 			const uint32_t by0 = tile0 / (uint32_t)wib, bx0 = tile0 - by0 * (uint32_t)wib;	// uniform
 			// thread t owns row positions p = t, t+512, ... (p = id*CPR + half) for all 4 pixel rows
@@ -698,7 +803,13 @@ int height, int wib, uint32_t mode_mask, uint32_t flags, uint32_t post_op, uint3
 					for (int r = 0; r < 4; r++)
 						if (r < rows) {
 							const uint4 v = sm.out[stage_slot<TB, CHUNKS>(id, r * CPR + half)];
-							st_stream_v4(out + r * pitch, v.x, v.y, v.z, v.w);
+							if constexpr (PC == PC_PACK3) {		// four RGBX8 pixels -> 12 bytes
+								st_stream_u32(out + r * pitch, prmt(v.x, v.y, 0x4210));
+								st_stream_u32(out + r * pitch + 4, prmt(v.y, v.z, 0x5421));
+								st_stream_u32(out + r * pitch + 8, prmt(v.z, v.w, 0x6542));
+							}
+							else
+								st_stream_v4(out + r * pitch, v.x, v.y, v.z, v.w);
 						}
 				}
 			}
@@ -740,7 +851,24 @@ static bool tiled_direct() {
 	return v;
 }
 
-template <int F>
+// One instantiation of the sorted kernel: opt in to > 48 KiB of dynamic shared memory once per
+// device, then launch.
+template <int F, int LAYOUT, bool STAGE, int PC>
+static void launch_sorted(unsigned grid, const uint8_t *src, uint8_t *dst, uint32_t n_blocks, const DecodeArgs &a,
+cudaStream_t stream) {
+	const size_t smem = sizeof(SortedSmem<F>);
+	static std::atomic<bool> configured[64];
+	int dev = 0;
+	cudaGetDevice(&dev);
+	if (!configured[dev & 63].load()) {
+		cudaFuncSetAttribute(decode_sorted_kernel<F, LAYOUT, STAGE, PC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		configured[dev & 63].store(true);
+	}
+	decode_sorted_kernel<F, LAYOUT, STAGE, PC><<<grid, SORT_THREADS, smem, stream>>>(src, dst, n_blocks,
+		a.width, a.height, a.wib, a.mode_mask, a.flags, a.post_op, a.invalid);
+}
+
+template <int F, int PC>
 static cudaError_t launch_format(const DecodeArgs &a, cudaStream_t stream) {
 	using T = FormatTraits<F>;
 	const uint64_t n_blocks = (uint64_t)a.wib * (uint64_t)a.hib;
@@ -749,6 +877,9 @@ static cudaError_t launch_format(const DecodeArgs &a, cudaStream_t stream) {
 	const uint8_t *src = (const uint8_t *)a.blocks;
 	uint8_t *dst = (uint8_t *)a.pixels;
 	const bool aligned_out = (((uintptr_t)dst & 15u) == 0);
+	const bool aligned32 = (((uintptr_t)dst & 31u) == 0);
+	if (PC != PC_NATIVE && !aligned32)
+		return cudaErrorMisalignedAddress;	// the caller falls back to decode + conversion pass
 	if constexpr (SortTraits<F>::ENABLED) {
 		// multi-mode formats: mode-sorted kernel whenever there is enough work to sort
 		const bool linear_ok = a.layout == LAYOUT_TILED || (a.width % 4 == 0);
@@ -757,27 +888,13 @@ static cudaError_t launch_format(const DecodeArgs &a, cudaStream_t stream) {
 			const uint64_t tiles = (n_blocks + TB - 1) / TB;
 			const uint64_t resident = (uint64_t)sm_count() * 2;		// persistent: two CTAs per SM
 			const unsigned grid = (unsigned)(tiles < resident ? tiles : resident);
-			const size_t smem = sizeof(SortedSmem<F>);
-			// opt in to > 48 KiB of dynamic shared memory once per device (per template instantiation)
-			static std::atomic<bool> configured[64];
-			int dev = 0;
-			cudaGetDevice(&dev);
 			constexpr bool ST = SortTraits<F>::STAGE_OUTPUT;
-			if (!configured[dev & 63].load()) {
-				cudaFuncSetAttribute(decode_sorted_kernel<F, LAYOUT_TILED, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-				cudaFuncSetAttribute(decode_sorted_kernel<F, LAYOUT_TILED, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-				cudaFuncSetAttribute(decode_sorted_kernel<F, LAYOUT_LINEAR, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-				configured[dev & 63].store(true);
-			}
-			if (a.layout == LAYOUT_TILED && tiled_direct() && (((uintptr_t)dst) & 31u) == 0)
-				decode_sorted_kernel<F, LAYOUT_TILED, false><<<grid, SORT_THREADS, smem, stream>>>(src, dst, (uint32_t)n_blocks,
-					a.width, a.height, a.wib, a.mode_mask, a.flags, a.post_op, a.invalid);
+			if (a.layout == LAYOUT_TILED && (PC != PC_NATIVE || (tiled_direct() && aligned32)))
+				launch_sorted<F, LAYOUT_TILED, false, PC>(grid, src, dst, (uint32_t)n_blocks, a, stream);
 			else if (a.layout == LAYOUT_TILED)
-				decode_sorted_kernel<F, LAYOUT_TILED, ST><<<grid, SORT_THREADS, smem, stream>>>(src, dst, (uint32_t)n_blocks,
-					a.width, a.height, a.wib, a.mode_mask, a.flags, a.post_op, a.invalid);
+				launch_sorted<F, LAYOUT_TILED, ST, PC_NATIVE>(grid, src, dst, (uint32_t)n_blocks, a, stream);
 			else
-				decode_sorted_kernel<F, LAYOUT_LINEAR, ST><<<grid, SORT_THREADS, smem, stream>>>(src, dst, (uint32_t)n_blocks,
-					a.width, a.height, a.wib, a.mode_mask, a.flags, a.post_op, a.invalid);
+				launch_sorted<F, LAYOUT_LINEAR, ST, PC>(grid, src, dst, (uint32_t)n_blocks, a, stream);
 			count_launch();
 			return cudaGetLastError();
 		}
@@ -789,13 +906,20 @@ static cudaError_t launch_format(const DecodeArgs &a, cudaStream_t stream) {
 		const uint64_t want = (tiles + per_cta - 1) / per_cta;
 		const uint64_t cap = (uint64_t)sm_count() * 8 * 16;
 		const unsigned grid = (unsigned)(want < cap ? want : cap);
-		constexpr bool CAN_DIRECT = T::OUT_WORDS >= 8;
-		if (CAN_DIRECT && (((uintptr_t)dst) & 31u) == 0 && tiled_direct())
-			decode_tiled_kernel<F, CAN_DIRECT><<<grid, CTA_THREADS, 0, stream>>>(src, dst, (uint32_t)n_blocks,
-				a.mode_mask, a.flags, a.post_op, a.invalid);
-		else
-			decode_tiled_kernel<F, false><<<grid, CTA_THREADS, 0, stream>>>(src, dst, (uint32_t)n_blocks,
-				a.mode_mask, a.flags, a.post_op, a.invalid);
+		constexpr bool CAN_DIRECT = post_words<T::OUT_WORDS, PC>() >= 8;
+		bool launched = false;
+		if constexpr (PC != PC_NATIVE || CAN_DIRECT) {
+			if (PC != PC_NATIVE || (aligned32 && tiled_direct())) {
+				decode_tiled_kernel<F, true, PC><<<grid, CTA_THREADS, 0, stream>>>(src, dst, (uint32_t)n_blocks,
+					a.mode_mask, a.flags, a.post_op, a.invalid);
+				launched = true;
+			}
+		}
+		if constexpr (PC == PC_NATIVE) {
+			if (!launched)
+				decode_tiled_kernel<F, false, PC_NATIVE><<<grid, CTA_THREADS, 0, stream>>>(src, dst, (uint32_t)n_blocks,
+					a.mode_mask, a.flags, a.post_op, a.invalid);
+		}
 	}
 	else {
 		const bool fast = (a.width % 4 == 0) && aligned_out;
@@ -810,25 +934,40 @@ static cudaError_t launch_format(const DecodeArgs &a, cudaStream_t stream) {
 			if (gy > 65535u)
 				gy = 65535u;
 			dim3 grid((unsigned)((a.wib + tx - 1) / tx), gy);
-			decode_linear_kernel<F><<<grid, block, 0, stream>>>(src, dst, a.width, a.height, a.wib, a.hib,
+			decode_linear_kernel<F, PC><<<grid, block, 0, stream>>>(src, dst, a.width, a.height, a.wib, a.hib,
 				a.mode_mask, a.flags, a.post_op, a.invalid);
 		}
 		else {
 			const uint64_t want = (n_blocks + CTA_THREADS - 1) / CTA_THREADS;
 			const uint64_t cap = (uint64_t)sm_count() * 8 * 16;
 			const unsigned grid = (unsigned)(want < cap ? want : cap);
-			decode_linear_clipped_kernel<F><<<grid, CTA_THREADS, 0, stream>>>(src, dst, a.width, a.height,
+			decode_linear_clipped_kernel<F, PC><<<grid, CTA_THREADS, 0, stream>>>(src, dst, a.width, a.height,
 				a.wib, a.hib, a.mode_mask, a.flags, a.post_op, a.invalid);
 		}
 	}
 	count_launch();
-	(void)sizeof(T);
 	return cudaGetLastError();
+}
+
+// post class -> instantiation, for the (format, class) pairs that exist
+template <int F>
+static cudaError_t launch_classes(const DecodeArgs &a, cudaStream_t stream) {
+	if (a.post_class == PC_NATIVE)
+		return launch_format<F, PC_NATIVE>(a, stream);
+	if constexpr (post_class_valid<F, PC_PACK3>()) {
+		if (a.post_class == PC_PACK3)
+			return launch_format<F, PC_PACK3>(a, stream);
+	}
+	if constexpr (post_class_valid<F, PC_NARROW>()) {
+		if (a.post_class == PC_NARROW)
+			return launch_format<F, PC_NARROW>(a, stream);
+	}
+	return cudaErrorInvalidValue;
 }
 
 cudaError_t launch_decode(int format_index, const DecodeArgs &a, cudaStream_t stream) {
 	switch (format_index) {
-#define DETEX_CASE(F) case F: return launch_format<F>(a, stream);
+#define DETEX_CASE(F) case F: return launch_classes<F>(a, stream);
 	DETEX_CASE(F_BC1) DETEX_CASE(F_BC1A) DETEX_CASE(F_BC2) DETEX_CASE(F_BC3)
 	DETEX_CASE(F_RGTC1) DETEX_CASE(F_SIGNED_RGTC1) DETEX_CASE(F_RGTC2) DETEX_CASE(F_SIGNED_RGTC2)
 	DETEX_CASE(F_BPTC_FLOAT) DETEX_CASE(F_BPTC_SIGNED_FLOAT) DETEX_CASE(F_BPTC)

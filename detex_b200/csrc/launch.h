@@ -14,7 +14,8 @@ struct DecodeArgs {
 	int wib, hib;		// blocks
 	int layout;
 	uint32_t mode_mask, flags;
-	uint32_t post_op;	// 0 none, 1 R<->B swap fused into the store (32- and 64-bit pixels)
+	uint32_t post_op;	// bit 0: R<->B swap, bit 1: signed<->unsigned 16-bit components, fused into the store
+	int post_class;		// 0 native tile size, 1 drop the fourth component, 2 16-bit -> 8-bit components
 	uint32_t *invalid;	// device flag word or nullptr
 };
 
@@ -29,9 +30,9 @@ int conversion_table_size();
 void conversion_table_entry(int index, uint32_t *source_pixel_format, uint32_t *target_pixel_format);
 void set_hdr_parameters(float gamma, float range_min, float range_max);	// thread-local, hdr.c:26-38
 bool convert_supported(uint32_t source_pixel_format, uint32_t target_pixel_format);
-// 0: the pair needs a separate conversion pass; 1: identical memory layout (X <-> A of the same
-// component order, a no-op); 2: R <-> B swap that the decode kernels fuse into their stores.
-int convert_fusable(uint32_t source_pixel_format, uint32_t target_pixel_format);
+// A conversion the decode kernels can do while storing: post_op / post_class as in DecodeArgs.
+struct FusedConversion { bool ok; uint32_t post_op; int post_class; };
+FusedConversion convert_fused(uint32_t source_pixel_format, uint32_t target_pixel_format);
 cudaError_t launch_convert(const void *src, uint64_t nu_pixels, uint32_t source_pixel_format,
 	void *dst, uint32_t target_pixel_format, cudaStream_t stream);
 

@@ -149,16 +149,26 @@ def test_hdr_parameters(oracle):
         oracle.detexSetHDRParameters(1.0, 0.0, 1.0)
 
 
-@pytest.mark.parametrize("fmt,target", [("BC1", "RGB8"), ("BC3", "R8"), ("ETC2_EAC", "RG8"), ("EAC_R11", "R8"),
-                                        ("EAC_RG11", "RG8"), ("EAC_SIGNED_RG11", "RG8"), ("SIGNED_RGTC1", "R8"),
-                                        ("RGTC2", "RGBX8"), ("RGTC1", "R16"), ("BPTC", "RGBA16"),
-                                        ("BPTC_FLOAT", "FLOAT_RGB16"), ("BPTC_FLOAT", "RGBX16"),
-                                        ("BPTC_FLOAT", "FLOAT_RGBX32"), ("EAC_R11", "FLOAT_R16")])
-def test_device_decode_with_size_changing_conversion(fmt, target, oracle):
-    """detexb200DecodeDevice through the L2-resident slab loop; 2048 x 1536 gives several slabs."""
+# fused into the decode kernels' store epilogue (post op / post class) ...
+FUSED = [("BC1", "RGB8"), ("BC1A", "RGB8"), ("BC2", "RGB8"), ("BC3", "RGB8"), ("ETC1", "RGB8"), ("ETC2", "RGB8"),
+         ("ETC2_PUNCHTHROUGH", "RGB8"), ("ETC2_EAC", "RGB8"), ("BPTC", "RGB8"), ("BPTC_FLOAT", "FLOAT_RGB16"),
+         ("EAC_R11", "R8"), ("EAC_RG11", "RG8"), ("EAC_SIGNED_R11", "R8"), ("EAC_SIGNED_RG11", "RG8"),
+         ("SIGNED_RGTC1", "R8"), ("SIGNED_RGTC2", "RG8"), ("RGTC1", "SIGNED_R8"), ("RGTC2", "SIGNED_RG8"),
+         ("EAC_SIGNED_R11", "R16"), ("EAC_R11", "SIGNED_R16"), ("SIGNED_RGTC2", "RG16"), ("EAC_RG11", "SIGNED_RG16")]
+# ... and through the decode + conversion pass over L2-resident slabs
+TWO_PASS = [("BC3", "R8"), ("ETC2_EAC", "RG8"), ("RGTC2", "RGBX8"), ("RGTC1", "R16"), ("BPTC", "RGBA16"),
+            ("BPTC_FLOAT", "RGBX16"), ("BPTC_FLOAT", "FLOAT_RGBX32"), ("EAC_R11", "FLOAT_R16")]
+
+
+@pytest.mark.parametrize("fmt,target", FUSED + TWO_PASS)
+def test_device_decode_with_conversion(fmt, target, oracle):
+    """detexb200DecodeDevice with a target format other than the native one; 2048 x 1536 gives
+    several slabs on the two-pass path and several tiles per CTA on the fused one; the last case
+    has a target that is only 16-byte aligned (fused classes fall back to two passes)."""
     pf = H.PIXEL_FORMATS[target]
     tf, bs, ps = H.FORMATS[fmt]
-    for (w, h, layout) in ((2048, 1536, D.LAYOUT_LINEAR), (2048, 1536, D.LAYOUT_TILED), (250, 61, D.LAYOUT_LINEAR)):
+    for (w, h, layout, shift) in ((2048, 1536, D.LAYOUT_LINEAR, 0), (2048, 1536, D.LAYOUT_TILED, 0),
+                                  (250, 61, D.LAYOUT_LINEAR, 0), (256, 64, D.LAYOUT_TILED, 16), (256, 64, D.LAYOUT_LINEAR, 16)):
         wib, hib = (w + 3) // 4, (h + 3) // 4
         b = H.synth_blocks(fmt, wib * hib, seed=21)
         if fmt.startswith("BPTC"):
@@ -166,11 +176,13 @@ def test_device_decode_with_size_changing_conversion(fmt, target, oracle):
         d_blocks = torch.from_numpy(b.copy()).cuda()
         linear = layout == D.LAYOUT_LINEAR
         n_px = w * h if linear else wib * hib * 16
-        d_out = torch.zeros(n_px * H.pixel_size(pf), dtype=torch.uint8, device="cuda")
+        d_out = torch.full((n_px * H.pixel_size(pf) + 64,), 0x5A, dtype=torch.uint8, device="cuda")
         flag = torch.zeros(1, dtype=torch.int32, device="cuda")
-        D.decode_device(fmt, d_blocks.data_ptr(), w, h, d_out.data_ptr(), pixel_format=pf, layout=layout,
+        D.decode_device(fmt, d_blocks.data_ptr(), w, h, d_out.data_ptr() + shift, pixel_format=pf, layout=layout,
                         d_invalid=flag.data_ptr())
         torch.cuda.synchronize()
         want, ok_w, _ = H.cpu_decode(oracle, fmt, b, w, h, linear=linear, pixel_format=pf, threads=32)
-        assert np.array_equal(d_out.cpu().numpy(), want), (fmt, target, w, h, layout)
+        got = d_out.cpu().numpy()
+        assert np.array_equal(got[shift:shift + want.size], want), (fmt, target, w, h, layout, shift)
+        assert (got[:shift] == 0x5A).all() and (got[shift + want.size:] == 0x5A).all()
         assert bool(flag.item() == 0) == ok_w
