@@ -325,7 +325,7 @@ __device__ __forceinline__ void apply_step(uint32_t op, uint32_t sf, uint32_t tf
 	case ST_NARROW:						// convert.c:263-331
 #pragma unroll
 		for (int j = 0; j < 4; j++)
-			c[j] = ((c[j] + 127u) * 255u) / 65535u;
+			c[j] = ((c[j] + 127u) * 255u) / 65535u;		// 16-bit inputs only; kernels.cu has the cheap form
 		if (n_out == 4 && !(tf & 0x4u))
 			c[3] = 0xFFu;				// RGBX16 -> RGBX8 writes alpha 0xFF (:312-316)
 		break;

@@ -140,7 +140,9 @@ template <int F, int PC> constexpr bool post_class_valid() {
 		F == F_SIGNED_RGTC1 || F == F_SIGNED_RGTC2;
 }
 
-__device__ __forceinline__ uint32_t narrow16(uint32_t v) { return ((v + 127u) * 255u) / 65535u; }
+// (v + 127) * 255 / 65535 == (v + 127) / 257 == ((v + 127) * 65281) >> 24 for every 16-bit v
+// (65281 * 257 = 2^24 + 1; checked exhaustively, the product stays below 2^32)
+__device__ __forceinline__ uint32_t narrow16(uint32_t v) { return ((v + 127u) * 65281u) >> 24; }
 // two 16-bit components of one word -> two bytes
 __device__ __forceinline__ uint32_t narrow_pair(uint32_t w) { return narrow16(w & 0xFFFFu) | (narrow16(w >> 16) << 8); }
 
@@ -270,10 +272,15 @@ __device__ __forceinline__ void store_linear_rows(uint8_t *dst, size_t pitch, in
 			}
 			else if constexpr (ROW_WORDS == 4)
 				st_stream_v4(p, px[4 * r], px[4 * r + 1], px[4 * r + 2], px[4 * r + 3]);
-			else if constexpr (ROW_WORDS == 6) {		// 24-byte FLOAT_RGB16 rows
-				st_stream_v2(p, px[6 * r], px[6 * r + 1]);
-				st_stream_v2(p + 8, px[6 * r + 2], px[6 * r + 3]);
-				st_stream_v2(p + 16, px[6 * r + 4], px[6 * r + 5]);
+			else if constexpr (ROW_WORDS == 6) {		// 24-byte FLOAT_RGB16 rows: 16 + 8 or 8 + 16 bytes
+				if ((((uintptr_t)p) & 15u) == 0) {
+					st_stream_v4(p, px[6 * r], px[6 * r + 1], px[6 * r + 2], px[6 * r + 3]);
+					st_stream_v2(p + 16, px[6 * r + 4], px[6 * r + 5]);
+				}
+				else {
+					st_stream_v2(p, px[6 * r], px[6 * r + 1]);
+					st_stream_v4(p + 8, px[6 * r + 2], px[6 * r + 3], px[6 * r + 4], px[6 * r + 5]);
+				}
 			}
 			else if (wide_ok)
 				st_stream_v8(p, px[8 * r], px[8 * r + 1], px[8 * r + 2], px[8 * r + 3],

@@ -73,7 +73,7 @@ def test_every_connected_pair_matches_oracle_at_size(oracle):
             got = _device_convert(src, n, a, b)
             assert np.array_equal(got, want), (hex(a), hex(b))
             done += 1
-    assert done > 450
+    assert done > 400
 
 
 @pytest.mark.parametrize("n", [0, 1, 3, 1023, 1024, 1025, 4097])
