@@ -123,7 +123,8 @@ bool is_compressed_format(uint32_t tf) {
 
 // Enqueue decode (+ optional conversion through d_tmp) of a block range on a stream.
 int enqueue_decode(uint32_t tf, const void *d_blocks, int width, int height, int wib, int hib, void *d_pixels,
-uint32_t pf, int layout, uint32_t mode_mask, uint32_t flags, uint32_t *d_invalid, void *d_tmp, cudaStream_t stream) {
+uint32_t pf, int layout, uint32_t mode_mask, uint32_t flags, uint32_t *d_invalid, void *d_tmp, uint32_t *d_map,
+cudaStream_t stream) {
 	const uint32_t native = tf & 0xFFFF;
 	DecodeArgs a;
 	a.blocks = d_blocks;
@@ -137,6 +138,7 @@ uint32_t pf, int layout, uint32_t mode_mask, uint32_t flags, uint32_t *d_invalid
 	a.invalid = d_invalid;
 	a.post_op = 0;
 	a.post_class = 0;
+	a.invalid_map = nullptr;
 	cudaError_t e;
 	// Conversions the kernels do while storing: R<->B swap, sign flip, dropping the fourth component,
 	// 16 -> 8 bit.  Repacked tiles need a 32-byte aligned target (else: separate conversion pass).
@@ -153,12 +155,21 @@ uint32_t pf, int layout, uint32_t mode_mask, uint32_t flags, uint32_t *d_invalid
 		set_error("detexConvertPixels: Unable to find conversion path (0x%04X -> 0x%04X on device)", native, pf);
 		return DETEXB200_EUNSUPPORTED;
 	}
+	// Separate conversion pass.  The conversion of a zero pixel need not be zero (sign flips, forced
+	// alpha), but an invalid block leaves zeros in the TARGET format (texture.c:90-93): the decode
+	// kernels record invalid blocks in a bitmap and their tiles are cleared after the conversion.
+	const uint64_t n_blocks = (uint64_t)wib * hib;
 	a.pixels = d_tmp;
+	a.invalid_map = d_map;
+	if (d_map && (e = cudaMemsetAsync(d_map, 0, (size_t)((n_blocks + 31) / 32) * 4, stream)) != cudaSuccess)
+		return cuda_fail("cudaMemsetAsync", e);
 	if ((e = launch_decode((int)(tf >> 24), a, stream)) != cudaSuccess)
 		return cuda_fail("decode kernel launch", e);
-	const uint64_t n_px = layout == DETEXB200_LAYOUT_LINEAR ? (uint64_t)width * height : (uint64_t)wib * hib * 16;
+	const uint64_t n_px = layout == DETEXB200_LAYOUT_LINEAR ? (uint64_t)width * height : n_blocks * 16;
 	if ((e = launch_convert(d_tmp, n_px, native, d_pixels, pf, stream)) != cudaSuccess)
 		return cuda_fail("convert kernel launch", e);
+	if (d_map && (e = launch_zero_invalid(d_map, d_pixels, width, height, wib, hib, layout, pixel_size(pf), stream)) != cudaSuccess)
+		return cuda_fail("zero_invalid kernel launch", e);
 	return DETEXB200_OK;
 }
 
@@ -210,10 +221,14 @@ bool decode_texture_host(const detexTexture *t, uint8_t *pixel_buffer, uint32_t 
 	const size_t in_bytes = n_blocks * bb;
 	const size_t out_bytes = layout == DETEXB200_LAYOUT_LINEAR ? (size_t)t->width * t->height * ps : n_blocks * 16 * ps;
 	const FusedConversion fuse = convert_fused(native, pf);
-	const size_t tmp_bytes = (fuse.ok && fuse.post_class == 0) ? 0 : n_blocks * 16 * ps_native;
+	const size_t tmp_bytes = (fuse.ok && fuse.post_class == 0) ? 0 : ((n_blocks * 16 * ps_native + 255) & ~(size_t)255);
+	// behind the scratch pixels: the invalid-block bitmaps of the slabs (slab k of blocks [b, b + n)
+	// uses the words from b / 32 + k on; consecutive slabs never overlap)
+	const size_t map_bytes = tmp_bytes ? (n_blocks / 32 + n_blocks / 1024 + 4096) * 4 : 0;
 	if (!c.reserve(&c.d_in, &c.cap_in, in_bytes) || !c.reserve(&c.d_out, &c.cap_out, out_bytes + 16) ||
-	    (tmp_bytes && !c.reserve(&c.d_tmp, &c.cap_tmp, tmp_bytes)))
+	    (tmp_bytes && !c.reserve(&c.d_tmp, &c.cap_tmp, tmp_bytes + map_bytes)))
 		return false;
+	uint32_t *const map_base = tmp_bytes ? (uint32_t *)((uint8_t *)c.d_tmp + tmp_bytes) : nullptr;
 	cudaError_t e;
 	if ((e = cudaMemsetAsync(c.d_flag, 0, 4, c.streams[0])) != cudaSuccess ||
 	    (e = cudaStreamSynchronize(c.streams[0])) != cudaSuccess) {
@@ -246,7 +261,8 @@ bool decode_texture_host(const detexTexture *t, uint8_t *pixel_buffer, uint32_t 
 				break;
 			}
 			rc = enqueue_decode(tf, (uint8_t *)c.d_in + in_off, t->width, slab_h, wib, rows, (uint8_t *)c.d_out + out_off, pf,
-				layout, DETEX_MODE_MASK_ALL, 0, c.d_flag, tmp_bytes ? (uint8_t *)c.d_tmp + tmp_off : nullptr, s);
+				layout, DETEX_MODE_MASK_ALL, 0, c.d_flag, tmp_bytes ? (uint8_t *)c.d_tmp + tmp_off : nullptr,
+				map_base ? map_base + ((size_t)r0 * wib) / 32 + k : nullptr, s);
 			if (rc != DETEXB200_OK)
 				break;
 			if (out_len && (e = cudaMemcpyAsync(pixel_buffer + out_off, (uint8_t *)c.d_out + out_off, out_len,
@@ -269,7 +285,8 @@ bool decode_texture_host(const detexTexture *t, uint8_t *pixel_buffer, uint32_t 
 				break;
 			}
 			rc = enqueue_decode(tf, (uint8_t *)c.d_in + in_off, (int)count * 4, 4, (int)count, 1, (uint8_t *)c.d_out + out_off, pf,
-				layout, DETEX_MODE_MASK_ALL, 0, c.d_flag, tmp_bytes ? (uint8_t *)c.d_tmp + tmp_off : nullptr, s);
+				layout, DETEX_MODE_MASK_ALL, 0, c.d_flag, tmp_bytes ? (uint8_t *)c.d_tmp + tmp_off : nullptr,
+				map_base ? map_base + b0 / 32 + k : nullptr, s);
 			if (rc != DETEXB200_OK)
 				break;
 			if ((e = cudaMemcpyAsync(pixel_buffer + out_off, (uint8_t *)c.d_out + out_off, (size_t)count * 16 * ps,
@@ -310,7 +327,7 @@ uint8_t *pixel_buffer, uint32_t pf, bool set_message) {
 		return false;
 	}
 	const int bb = block_bytes(tf), out_bytes = 16 * pixel_size(pf);
-	if (!c.reserve(&c.d_in, &c.cap_in, 64) || !c.reserve(&c.d_out, &c.cap_out, 512) || !c.reserve(&c.d_tmp, &c.cap_tmp, 512))
+	if (!c.reserve(&c.d_in, &c.cap_in, 64) || !c.reserve(&c.d_out, &c.cap_out, 512) || !c.reserve(&c.d_tmp, &c.cap_tmp, 1024))
 		return false;
 	cudaStream_t s = c.streams[0];
 	uint8_t *hs = (uint8_t *)c.h_small;
@@ -321,7 +338,8 @@ uint8_t *pixel_buffer, uint32_t pf, bool set_message) {
 		cuda_fail("detexDecompressBlock", e);
 		return false;
 	}
-	if (enqueue_decode(tf, c.d_in, 4, 4, 1, 1, c.d_out, pf, DETEXB200_LAYOUT_TILED, mode_mask, flags, c.d_flag, c.d_tmp, s) != DETEXB200_OK)
+	if (enqueue_decode(tf, c.d_in, 4, 4, 1, 1, c.d_out, pf, DETEXB200_LAYOUT_TILED, mode_mask, flags, c.d_flag, c.d_tmp,
+			(uint32_t *)((uint8_t *)c.d_tmp + 512), s) != DETEXB200_OK)
 		return false;
 	if ((e = cudaMemcpyAsync(hs + 64, c.d_out, out_bytes, cudaMemcpyDeviceToHost, s)) != cudaSuccess ||
 	    (e = cudaMemcpyAsync(c.h_flag, c.d_flag, 4, cudaMemcpyDeviceToHost, s)) != cudaSuccess ||
@@ -362,15 +380,18 @@ void *d_pixels, uint32_t pf, int layout, uint32_t mode_mask, uint32_t flags, uin
 	}
 	const FusedConversion fuse = convert_fused(native, pf);
 	if (fuse.ok && (fuse.post_class == 0 || (((uintptr_t)d_pixels) & 31u) == 0))
-		return enqueue_decode(tf, d_blocks, width, height, wib, hib, d_pixels, pf, layout, mode_mask, flags, d_invalid, nullptr, s);
+		return enqueue_decode(tf, d_blocks, width, height, wib, hib, d_pixels, pf, layout, mode_mask, flags, d_invalid, nullptr, nullptr, s);
 	// Decode + conversion pass, slab by slab through ONE scratch buffer small enough to stay in the
 	// 126 MB L2: the native-format pixels of a slab are read back by the conversion kernel before
 	// they are evicted, so HBM sees the compressed input and the converted output only.
 	const int bb = block_bytes(tf), ps = pixel_size(pf), ps_native = pixel_size(native);
 	const size_t slab_budget = 24u << 20;
-	cudaError_t e = cudaMallocAsync(&tmp, slab_budget + (size_t)wib * 64 * ps_native + 1024 * 16 * ps_native, s);
+	const size_t pixel_region = (slab_budget + (size_t)wib * 64 * ps_native + 1024 * 16 * ps_native + 255) & ~(size_t)255;
+	const size_t map_region = (pixel_region / (16 * ps_native) / 32 + 64) * 4;	// one bit per block of a slab
+	cudaError_t e = cudaMallocAsync(&tmp, pixel_region + map_region, s);
 	if (e != cudaSuccess)
 		return cuda_fail("cudaMallocAsync", e);
+	uint32_t *const map = (uint32_t *)((uint8_t *)tmp + pixel_region);
 	int rc = DETEXB200_OK;
 	if (layout == DETEXB200_LAYOUT_LINEAR) {
 		const size_t row_bytes = (size_t)width * 4 * ps_native;
@@ -385,7 +406,7 @@ void *d_pixels, uint32_t pf, int layout, uint32_t mode_mask, uint32_t flags, uin
 			if (slab_h < 0)
 				slab_h = 0;
 			rc = enqueue_decode(tf, (const uint8_t *)d_blocks + (size_t)r0 * wib * bb, width, slab_h, wib, rows,
-				(uint8_t *)d_pixels + (size_t)r0 * 4 * width * ps, pf, layout, mode_mask, flags, d_invalid, tmp, s);
+				(uint8_t *)d_pixels + (size_t)r0 * 4 * width * ps, pf, layout, mode_mask, flags, d_invalid, tmp, map, s);
 		}
 	}
 	else {
@@ -396,7 +417,7 @@ void *d_pixels, uint32_t pf, int layout, uint32_t mode_mask, uint32_t flags, uin
 		for (uint64_t b0 = 0; b0 < n_blocks && rc == DETEXB200_OK; b0 += per_slab) {
 			const uint64_t count = (n_blocks - b0) < per_slab ? (n_blocks - b0) : per_slab;
 			rc = enqueue_decode(tf, (const uint8_t *)d_blocks + b0 * bb, (int)count * 4, 4, (int)count, 1,
-				(uint8_t *)d_pixels + b0 * 16 * ps, pf, layout, mode_mask, flags, d_invalid, tmp, s);
+				(uint8_t *)d_pixels + b0 * 16 * ps, pf, layout, mode_mask, flags, d_invalid, tmp, map, s);
 		}
 	}
 	cudaFreeAsync(tmp, s);

@@ -470,6 +470,42 @@ convert_kernel(const uint8_t *src, uint8_t *dst, uint64_t n_pixels, ConvertProgr
 	}
 }
 
+// One thread per block: clear the 4x4 pixels (clipped to the image for LINEAR) of marked blocks.
+__global__ void __launch_bounds__(256)
+zero_invalid_kernel(const uint32_t *__restrict__ invalid_map, uint8_t *pixels, int width, int height, int wib,
+uint32_t n_blocks, int layout, int ps) {
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_blocks; i += gridDim.x * blockDim.x) {
+		if (!((invalid_map[i >> 5] >> (i & 31u)) & 1u))
+			continue;
+		if (layout == LAYOUT_TILED) {
+			uint8_t *p = pixels + (size_t)i * 16 * ps;
+			for (int b = 0; b < 16 * ps; b++)
+				p[b] = 0;
+		}
+		else {
+			const int by = (int)(i / (uint32_t)wib), bx = (int)(i % (uint32_t)wib);
+			const int rows = min(4, height - by * 4), cols = min(4, width - bx * 4);
+			for (int r = 0; r < rows; r++) {
+				uint8_t *p = pixels + ((size_t)(by * 4 + r) * width + (size_t)bx * 4) * ps;
+				for (int b = 0; b < cols * ps; b++)
+					p[b] = 0;
+			}
+		}
+	}
+}
+
+cudaError_t launch_zero_invalid(const uint32_t *invalid_map, void *pixels, int width, int height, int wib, int hib,
+int layout, int ps, cudaStream_t stream) {
+	const uint64_t n = (uint64_t)wib * (uint64_t)hib;
+	if (n == 0)
+		return cudaSuccess;
+	const uint64_t want = (n + 255) / 256;
+	zero_invalid_kernel<<<(unsigned)(want < 148ull * 32 ? want : 148ull * 32), 256, 0, stream>>>(invalid_map,
+		(uint8_t *)pixels, width, height, wib, (uint32_t)n, layout, ps);
+	count_launch();
+	return cudaGetLastError();
+}
+
 cudaError_t launch_convert(const void *src, uint64_t n, uint32_t s, void *dst, uint32_t d, cudaStream_t stream) {
 	if (n == 0)
 		return cudaSuccess;

@@ -192,6 +192,20 @@ __device__ __forceinline__ void emit(uint32_t (&px)[OW], uint32_t post_op, Store
 	}
 }
 
+// Pixels of an invalid block are zero IN THE TARGET FORMAT (texture.c:90-93,125-128).  Swap,
+// drop-X and narrowing keep zero at zero; a sign flip does not, so the fill value is the flip's
+// pre-image of zero.
+__device__ __forceinline__ uint32_t invalid_fill(uint32_t post_op) {
+	return (post_op & POST_FLIP16) ? 0x80008000u : ((post_op & POST_FLIP8) ? 0x80808080u : 0u);
+}
+// Optional per-block record of invalid blocks (one bit per block), for the decode + conversion
+// pass path: the conversion of a zero pixel is not always zero, so the tiles of invalid blocks are
+// cleared again after the conversion (zero_invalid_kernel).
+__device__ __forceinline__ void mark_invalid(uint32_t *invalid_map, uint32_t block) {
+	if (invalid_map != nullptr)
+		atomicOr(&invalid_map[block >> 5], 1u << (block & 31u));
+}
+
 constexpr int CTA_THREADS = 256;
 constexpr int CTA_WARPS = CTA_THREADS / 32;
 
@@ -299,7 +313,7 @@ __device__ __forceinline__ void store_linear_rows(uint8_t *dst, size_t pitch, in
 template <int F, bool DIRECT, int PC>
 __global__ void __launch_bounds__(CTA_THREADS)
 decode_tiled_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, uint32_t n_blocks,
-uint32_t mode_mask, uint32_t flags, uint32_t post_op, uint32_t *invalid_flag) {
+uint32_t mode_mask, uint32_t flags, uint32_t post_op, uint32_t *invalid_flag, uint32_t *invalid_map) {
 	using T = FormatTraits<F>;
 	using D = DeferTraits<F>;
 	constexpr int BW = T::BLOCK_WORDS, OW = T::OUT_WORDS, OWO = post_words<OW, PC>(), CHUNKS = OWO / 4;
@@ -339,9 +353,10 @@ uint32_t mode_mask, uint32_t flags, uint32_t post_op, uint32_t *invalid_flag) {
 			}
 			if (!ok) {
 				bad = true;
+				mark_invalid(invalid_map, i);
 #pragma unroll
 				for (int w = 0; w < OW; w++)
-					px[w] = 0u;
+					px[w] = invalid_fill(post_op);
 			}
 			const unsigned rare_mask = D::ENABLED ? __ballot_sync(0xFFFFFFFFu, rare) : 0u;
 			emit<PC>(px, post_op, [&](auto &w) {
@@ -410,9 +425,10 @@ uint32_t mode_mask, uint32_t flags, uint32_t post_op, uint32_t *invalid_flag) {
 				uint32_t qx[OW];
 				if (!decode_block<F, ETC_PATHS_PLANAR_ONLY>(blk, mode_mask, flags, &tables, qx)) {
 					bad = true;
+					mark_invalid(invalid_map, j);
 #pragma unroll
 					for (int k = 0; k < OW; k++)
-						qx[k] = 0u;
+						qx[k] = invalid_fill(post_op);
 				}
 				emit<PC>(qx, post_op, [&](auto &w) {
 					uint8_t *out = dst + (size_t)j * (OWO * 4);
@@ -436,7 +452,7 @@ uint32_t mode_mask, uint32_t flags, uint32_t post_op, uint32_t *invalid_flag) {
 template <int F, int PC>
 __global__ void __launch_bounds__(CTA_THREADS)
 decode_linear_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, int width, int height,
-int wib, int hib, uint32_t mode_mask, uint32_t flags, uint32_t post_op, uint32_t *invalid_flag) {
+int wib, int hib, uint32_t mode_mask, uint32_t flags, uint32_t post_op, uint32_t *invalid_flag, uint32_t *invalid_map) {
 	using T = FormatTraits<F>;
 	using D = DeferTraits<F>;
 	constexpr int BW = T::BLOCK_WORDS, OW = T::OUT_WORDS, ROW_BYTES = post_words<OW, PC>();
@@ -475,9 +491,10 @@ int wib, int hib, uint32_t mode_mask, uint32_t flags, uint32_t post_op, uint32_t
 					uint32_t px[OW];
 					if (!decode_block<F, D::ENABLED ? ETC_PATHS_NO_PLANAR : ETC_PATHS_ALL>(blk, mode_mask, flags, &tables, px)) {
 						bad = true;
+						mark_invalid(invalid_map, (uint32_t)by * (uint32_t)wib + (uint32_t)bx);
 #pragma unroll
 						for (int j = 0; j < OW; j++)
-							px[j] = 0u;
+							px[j] = invalid_fill(post_op);
 					}
 					emit<PC>(px, post_op, [&](auto &w) { store_linear_rows(dst, pitch, bx, by, height, w); });
 				}
@@ -494,9 +511,10 @@ int wib, int hib, uint32_t mode_mask, uint32_t flags, uint32_t post_op, uint32_t
 				uint32_t qp[OW];
 				if (!decode_block<F, ETC_PATHS_PLANAR_ONLY>(blk, mode_mask, flags, &tables, qp)) {
 					bad = true;
+					mark_invalid(invalid_map, j);
 #pragma unroll
 					for (int jj = 0; jj < OW; jj++)
-						qp[jj] = 0u;
+						qp[jj] = invalid_fill(post_op);
 				}
 				emit<PC>(qp, post_op, [&](auto &w) { store_linear_rows(dst, pitch, qx_, qy, height, w); });
 			}
@@ -515,7 +533,7 @@ int wib, int hib, uint32_t mode_mask, uint32_t flags, uint32_t post_op, uint32_t
 template <int F, int PC>
 __global__ void __launch_bounds__(CTA_THREADS)
 decode_linear_clipped_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, int width, int height,
-int wib, int hib, uint32_t mode_mask, uint32_t flags, uint32_t post_op, uint32_t *invalid_flag) {
+int wib, int hib, uint32_t mode_mask, uint32_t flags, uint32_t post_op, uint32_t *invalid_flag, uint32_t *invalid_map) {
 	using T = FormatTraits<F>;
 	constexpr int BW = T::BLOCK_WORDS, OW = T::OUT_WORDS, PS = post_words<OW, PC>() / 4;	// PS = bytes per stored pixel
 	__shared__ BptcTables tables;
@@ -531,9 +549,10 @@ int wib, int hib, uint32_t mode_mask, uint32_t flags, uint32_t post_op, uint32_t
 		uint32_t px[OW];
 		if (!decode_block<F>(blk, mode_mask, flags, &tables, px)) {
 			bad = true;
+			mark_invalid(invalid_map, i);
 #pragma unroll
 			for (int k = 0; k < OW; k++)
-				px[k] = 0u;
+				px[k] = invalid_fill(post_op);
 		}
 		const int rows = min(4, height - by * 4), cols = min(4, width - bx * 4);
 		emit<PC>(px, post_op, [&](auto &w) {
@@ -648,7 +667,7 @@ __device__ __forceinline__ uint32_t raw_slot(uint32_t id) { return id ^ ((id >> 
 template <int F, int LAYOUT, bool STAGE, int PC>
 __global__ void __launch_bounds__(SORT_THREADS, 2)
 decode_sorted_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, uint32_t n_blocks, int width,
-int height, int wib, uint32_t mode_mask, uint32_t flags, uint32_t post_op, uint32_t *invalid_flag) {
+int height, int wib, uint32_t mode_mask, uint32_t flags, uint32_t post_op, uint32_t *invalid_flag, uint32_t *invalid_map) {
 	using T = FormatTraits<F>;
 	using S = SortTraits<F>;
 	using SM = SortedSmem<F>;
@@ -740,9 +759,10 @@ int height, int wib, uint32_t mode_mask, uint32_t flags, uint32_t post_op, uint3
 				uint32_t px[OW];
 				if (!decode_block<F>(w, mode_mask, flags, &sm.tables, px)) {
 					bad = true;
+					mark_invalid(invalid_map, tile0 + id);
 #pragma unroll
 					for (int k = 0; k < OW; k++)
-						px[k] = 0u;
+						px[k] = invalid_fill(post_op);
 				}
 				if constexpr (STAGE) {
 					// staged in the native layout; a post class is applied by the copy-out below
@@ -872,7 +892,7 @@ cudaStream_t stream) {
 		configured[dev & 63].store(true);
 	}
 	decode_sorted_kernel<F, LAYOUT, STAGE, PC><<<grid, SORT_THREADS, smem, stream>>>(src, dst, n_blocks,
-		a.width, a.height, a.wib, a.mode_mask, a.flags, a.post_op, a.invalid);
+		a.width, a.height, a.wib, a.mode_mask, a.flags, a.post_op, a.invalid, a.invalid_map);
 }
 
 template <int F, int PC>
@@ -918,14 +938,14 @@ static cudaError_t launch_format(const DecodeArgs &a, cudaStream_t stream) {
 		if constexpr (PC != PC_NATIVE || CAN_DIRECT) {
 			if (PC != PC_NATIVE || (aligned32 && tiled_direct())) {
 				decode_tiled_kernel<F, true, PC><<<grid, CTA_THREADS, 0, stream>>>(src, dst, (uint32_t)n_blocks,
-					a.mode_mask, a.flags, a.post_op, a.invalid);
+					a.mode_mask, a.flags, a.post_op, a.invalid, a.invalid_map);
 				launched = true;
 			}
 		}
 		if constexpr (PC == PC_NATIVE) {
 			if (!launched)
 				decode_tiled_kernel<F, false, PC_NATIVE><<<grid, CTA_THREADS, 0, stream>>>(src, dst, (uint32_t)n_blocks,
-					a.mode_mask, a.flags, a.post_op, a.invalid);
+					a.mode_mask, a.flags, a.post_op, a.invalid, a.invalid_map);
 		}
 	}
 	else {
@@ -942,14 +962,14 @@ static cudaError_t launch_format(const DecodeArgs &a, cudaStream_t stream) {
 				gy = 65535u;
 			dim3 grid((unsigned)((a.wib + tx - 1) / tx), gy);
 			decode_linear_kernel<F, PC><<<grid, block, 0, stream>>>(src, dst, a.width, a.height, a.wib, a.hib,
-				a.mode_mask, a.flags, a.post_op, a.invalid);
+				a.mode_mask, a.flags, a.post_op, a.invalid, a.invalid_map);
 		}
 		else {
 			const uint64_t want = (n_blocks + CTA_THREADS - 1) / CTA_THREADS;
 			const uint64_t cap = (uint64_t)sm_count() * 8 * 16;
 			const unsigned grid = (unsigned)(want < cap ? want : cap);
 			decode_linear_clipped_kernel<F, PC><<<grid, CTA_THREADS, 0, stream>>>(src, dst, a.width, a.height,
-				a.wib, a.hib, a.mode_mask, a.flags, a.post_op, a.invalid);
+				a.wib, a.hib, a.mode_mask, a.flags, a.post_op, a.invalid, a.invalid_map);
 		}
 	}
 	count_launch();

@@ -17,6 +17,7 @@ struct DecodeArgs {
 	uint32_t post_op;	// bit 0: R<->B swap, bit 1: signed<->unsigned 16-bit components, fused into the store
 	int post_class;		// 0 native tile size, 1 drop the fourth component, 2 16-bit -> 8-bit components
 	uint32_t *invalid;	// device flag word or nullptr
+	uint32_t *invalid_map;	// device bitmap, one bit per block, set for invalid blocks; or nullptr
 };
 
 // Enqueue the decode of one texture in its native pixel format.  format_index = texture_format >> 24.
@@ -33,6 +34,9 @@ bool convert_supported(uint32_t source_pixel_format, uint32_t target_pixel_forma
 // A conversion the decode kernels can do while storing: post_op / post_class as in DecodeArgs.
 struct FusedConversion { bool ok; uint32_t post_op; int post_class; };
 FusedConversion convert_fused(uint32_t source_pixel_format, uint32_t target_pixel_format);
+// Clear the target pixels of the blocks marked in invalid_map (after a separate conversion pass).
+cudaError_t launch_zero_invalid(const uint32_t *invalid_map, void *pixels, int width, int height, int wib, int hib,
+	int layout, int pixel_bytes, cudaStream_t stream);
 cudaError_t launch_convert(const void *src, uint64_t nu_pixels, uint32_t source_pixel_format,
 	void *dst, uint32_t target_pixel_format, cudaStream_t stream);
 

@@ -123,6 +123,18 @@ def test_host_api_convert_and_in_place_rules(oracle):
     assert not ok and "Unable to find conversion path" in D.detexGetErrorMessage()
 
 
+def test_host_texture_api_with_conversions_and_invalid_blocks(oracle):
+    for fmt, target in (("EAC_SIGNED_R11", "R8"), ("ETC1", "RGBX16"), ("EAC_SIGNED_R11", "FLOAT_R16"), ("ETC1", "RGB8")):
+        pf = H.PIXEL_FORMATS[target]
+        for (w, h) in ((512, 256), (61, 35)):
+            b = H.synth_blocks(fmt, ((w + 3) // 4) * ((h + 3) // 4), seed=17)
+            for linear in (True, False):
+                want, ok_w, _ = H.cpu_decode(oracle, fmt, b, w, h, linear=linear, pixel_format=pf)
+                fn = D.detexDecompressTextureLinear if linear else D.detexDecompressTextureTiled
+                got, ok = fn(fmt, b, w, h, pixel_format=pf)
+                assert not ok_w and ok == ok_w and np.array_equal(got, want), (fmt, target, w, h, linear)
+
+
 def test_hdr_parameters(oracle):
     lib = D.lib.load()
     lib.detexSetHDRParameters.argtypes = [C.c_float, C.c_float, C.c_float]
@@ -156,8 +168,11 @@ FUSED = [("BC1", "RGB8"), ("BC1A", "RGB8"), ("BC2", "RGB8"), ("BC3", "RGB8"), ("
          ("SIGNED_RGTC1", "R8"), ("SIGNED_RGTC2", "RG8"), ("RGTC1", "SIGNED_R8"), ("RGTC2", "SIGNED_RG8"),
          ("EAC_SIGNED_R11", "R16"), ("EAC_R11", "SIGNED_R16"), ("SIGNED_RGTC2", "RG16"), ("EAC_RG11", "SIGNED_RG16")]
 # ... and through the decode + conversion pass over L2-resident slabs
+# (ETC1 -> RGBX16 and EAC_SIGNED_R11 -> FLOAT_R16: uniform random blocks contain invalid ones, and the
+# conversion of a zero pixel is not zero there -- the target must still be zero, texture.c:90-93)
 TWO_PASS = [("BC3", "R8"), ("ETC2_EAC", "RG8"), ("RGTC2", "RGBX8"), ("RGTC1", "R16"), ("BPTC", "RGBA16"),
-            ("BPTC_FLOAT", "RGBX16"), ("BPTC_FLOAT", "FLOAT_RGBX32"), ("EAC_R11", "FLOAT_R16")]
+            ("BPTC_FLOAT", "RGBX16"), ("BPTC_FLOAT", "FLOAT_RGBX32"), ("EAC_R11", "FLOAT_R16"),
+            ("ETC1", "RGBX16"), ("EAC_SIGNED_R11", "FLOAT_R16"), ("EAC_SIGNED_RG11", "RGBX8")]
 
 
 @pytest.mark.parametrize("fmt,target", FUSED + TWO_PASS)
