@@ -132,7 +132,8 @@ def test_host_texture_api_with_conversions_and_invalid_blocks(oracle):
                 want, ok_w, _ = H.cpu_decode(oracle, fmt, b, w, h, linear=linear, pixel_format=pf)
                 fn = D.detexDecompressTextureLinear if linear else D.detexDecompressTextureTiled
                 got, ok = fn(fmt, b, w, h, pixel_format=pf)
-                assert not ok_w and ok == ok_w and np.array_equal(got, want), (fmt, target, w, h, linear)
+                assert ok == ok_w and np.array_equal(got, want), (fmt, target, w, h, linear)
+                assert not ok_w or w < 512        # the large size does contain invalid blocks
 
 
 def test_hdr_parameters(oracle):
