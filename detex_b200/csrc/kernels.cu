@@ -253,6 +253,18 @@ template <int F> struct LinearTune {
 	static constexpr int ITERS = DeferTraits<F>::ENABLED ? DEFER_ITERS : 2;
 	static constexpr bool EXIT_BARRIER = false;
 };
+// Resident CTAs per SM the plain kernels are compiled for.  The light decoders are latency-bound on
+// HBM and want all 64 warps of an SM (8 CTAs -> at most 32 registers); the heavy ones keep their
+// registers.  (BC1 LINEAR lost 4 % when its kernel grew from 30 to 37 registers and 8 -> 6 CTAs.)
+#ifndef DETEXB200_LIGHT_MIN_CTAS
+#define DETEXB200_LIGHT_MIN_CTAS 8
+#endif
+template <int F> constexpr int min_ctas() {
+	// 0: no constraint.  BC3, SIGNED_RGTC1 and EAC_SIGNED_R11 measured 2-4 % faster unconstrained.
+	return (F == F_BPTC || F == F_BPTC_FLOAT || F == F_BPTC_SIGNED_FLOAT || F == F_ETC2 ||
+		F == F_ETC2_PUNCHTHROUGH || F == F_ETC2_EAC || F == F_BC3 || F == F_SIGNED_RGTC1 ||
+		F == F_EAC_SIGNED_R11) ? 0 : DETEXB200_LIGHT_MIN_CTAS;
+}
 struct LinearTuneAtLimit { static constexpr int ITERS = 1; static constexpr bool EXIT_BARRIER = true; };
 template <> struct LinearTune<F_BC1> : LinearTuneAtLimit {};
 template <> struct LinearTune<F_BC1A> : LinearTuneAtLimit {};
@@ -311,7 +323,7 @@ __device__ __forceinline__ void store_linear_rows(uint8_t *dst, size_t pitch, in
 // DIRECT: every lane writes its own tile with 256-bit stores (tiles of >= 32 bytes on a 32-byte
 // aligned destination) instead of transposing the warp's tiles through shared memory.
 template <int F, bool DIRECT, int PC>
-__global__ void __launch_bounds__(CTA_THREADS)
+__global__ void __launch_bounds__(CTA_THREADS, min_ctas<F>())
 decode_tiled_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, uint32_t n_blocks,
 uint32_t mode_mask, uint32_t flags, uint32_t post_op, uint32_t *invalid_flag, uint32_t *invalid_map) {
 	using T = FormatTraits<F>;
@@ -450,7 +462,7 @@ uint32_t mode_mask, uint32_t flags, uint32_t post_op, uint32_t *invalid_flag, ui
 // blockDim = (TX, TY): thread (x, y) decodes block (blockIdx.x*TX + x, by) with by
 // grid-strided over block rows.
 template <int F, int PC>
-__global__ void __launch_bounds__(CTA_THREADS)
+__global__ void __launch_bounds__(CTA_THREADS, min_ctas<F>())
 decode_linear_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, int width, int height,
 int wib, int hib, uint32_t mode_mask, uint32_t flags, uint32_t post_op, uint32_t *invalid_flag, uint32_t *invalid_map) {
 	using T = FormatTraits<F>;
