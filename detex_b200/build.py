@@ -6,7 +6,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libdetex_b200.so")
-SOURCES = ["kernels.cu", "convert.cu", "aux.cu", "api.cu"]
+SOURCES = ["kernels.cu", "convert.cu", "aux.cu", "ingest.cu", "api.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "--expt-relaxed-constexpr", "-diag-suppress", "177", "-Xcompiler", "-fPIC,-fvisibility=hidden", "-shared",

@@ -33,6 +33,12 @@ void set_error(const char *fmt, ...) {
 	g_error = buf;
 }
 
+}  // namespace
+namespace detexb200 {
+void set_error_text(const char *text) { g_error = text; }
+}
+namespace {
+
 int cuda_fail(const char *what, cudaError_t e) {
 	set_error("%s: CUDA error %d (%s)", what, (int)e, cudaGetErrorString(e));
 	return DETEXB200_ECUDA;

@@ -45,6 +45,9 @@ cudaError_t launch_generate(void *blocks, uint64_t n_blocks, int block_bytes, ui
 	uint64_t first_block, int force_modes, cudaStream_t stream);
 cudaError_t device_hash(const void *buf, uint64_t n_bytes, uint64_t *hash_out, cudaStream_t stream);
 
+// Thread-local error text behind detexGetErrorMessage (api.cu).
+void set_error_text(const char *text);
+
 uint64_t launch_count();
 void count_launch();
 

@@ -204,3 +204,25 @@ def hash_device(d_buf, n_bytes, stream=0):
 
 def launch_count():
     return int(load().detexb200LaunchCount())
+
+
+# ---- KTX / DDS ingest straight to device memory (include/detex_b200.h) ----------------------------
+class DeviceImage(C.Structure):
+    _fields_ = [("d_pixels", C.c_void_p), ("pixel_bytes", C.c_size_t), ("width", C.c_int), ("height", C.c_int),
+                ("width_in_blocks", C.c_int), ("height_in_blocks", C.c_int)]
+
+
+def load_texture_file_to_device(filename, max_mipmaps=32, pixel_format=0, layout=LAYOUT_LINEAR, stream=0):
+    """detexb200LoadTextureFileToDevice -> (levels, texture_format, all_valid, free).  levels is a list
+    of DeviceImage (device pointers into one allocation); call free() when done."""
+    lib = load()
+    lib.detexb200LoadTextureFileToDevice.argtypes = [C.c_char_p, C.c_int, C.c_uint32, C.c_int, C.POINTER(DeviceImage),
+                                                    C.POINTER(C.c_int), C.POINTER(C.c_uint32), C.POINTER(C.c_int), C.c_void_p]
+    lib.detexb200LoadTextureFileToDevice.restype = C.c_int
+    lib.detexb200FreeDeviceImages.argtypes = [C.POINTER(DeviceImage), C.c_int]
+    lib.detexb200FreeDeviceImages.restype = None
+    levels = (DeviceImage * max_mipmaps)()
+    n, tf, valid = C.c_int(0), C.c_uint32(0), C.c_int(0)
+    _check(lib.detexb200LoadTextureFileToDevice(filename.encode(), max_mipmaps, pixel_format, layout, levels,
+                                                C.byref(n), C.byref(tf), C.byref(valid), stream))
+    return [levels[i] for i in range(n.value)], tf.value, bool(valid.value), lambda: lib.detexb200FreeDeviceImages(levels, n.value)

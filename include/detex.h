@@ -186,6 +186,19 @@ DETEX_API bool detexConvertPixels(uint8_t *source_pixel_buffer, uint32_t nu_pixe
 DETEX_API bool detexConvertPixelsInPlace(uint8_t *source_pixel_buffer, uint32_t nu_pixels,
 	uint32_t source_pixel_format, uint32_t target_pixel_format);
 
+/* ---- KTX / DDS loaders, reference detex.h:826-867 (ktx.c:36-176, dds.c:32-143, misc.c:98-121) --
+ * textures_out receives a malloc'd array of malloc'd textures (each with malloc'd data);
+ * release everything with free(), as with the reference. */
+DETEX_API bool detexLoadKTXFileWithMipmaps(const char *filename, int max_mipmaps,
+	detexTexture ***textures_out, int *nu_levels_out);
+DETEX_API bool detexLoadKTXFile(const char *filename, detexTexture **texture_out);
+DETEX_API bool detexLoadDDSFileWithMipmaps(const char *filename, int max_mipmaps,
+	detexTexture ***textures_out, int *nu_levels_out);
+DETEX_API bool detexLoadDDSFile(const char *filename, detexTexture **texture_out);
+DETEX_API bool detexLoadTextureFileWithMipmaps(const char *filename, int max_mipmaps,
+	detexTexture ***textures_out, int *nu_levels_out);
+DETEX_API bool detexLoadTextureFile(const char *filename, detexTexture **texture_out);
+
 /* Range / gamma used by the *_HDR source formats, reference detex.h:792-800 / hdr.c:26-38
  * (thread-local; defaults gamma 1, range 0..1). */
 DETEX_API void detexSetHDRParameters(float gamma, float range_min, float range_max);

@@ -99,6 +99,26 @@ DETEXB200_API int detexb200GenerateBlocksDevice(void *d_blocks, uint64_t n_block
 DETEXB200_API int detexb200HashDevice(const void *d_buf, uint64_t n_bytes, uint64_t *h_hash_out,
 	void *stream);
 
+/*
+ * KTX / DDS file -> decoded mip chain in device memory.  The header is parsed
+ * on the host like detexLoadTextureFileWithMipmaps does (ktx.c:36-176, dds.c:32-143), the
+ * payload of every level goes through one pinned buffer and one asynchronous copy, and every
+ * level is decoded (compressed formats) or converted (uncompressed formats) on `stream` into ONE
+ * device allocation.  pixel_format 0 = the file's native pixel format.  levels_out must have
+ * room for max_mipmaps entries; levels_out[0].d_pixels is the base of the allocation, release
+ * it with detexb200FreeDeviceImages.  Synchronous: the pixels are complete on return.
+ * *all_valid_out is 0 when some block was invalid (its pixels are zero, as in texture.c:90-93).
+ */
+typedef struct {
+	void *d_pixels;
+	size_t pixel_bytes;
+	int width, height, width_in_blocks, height_in_blocks;
+} detexb200DeviceImage;
+DETEXB200_API int detexb200LoadTextureFileToDevice(const char *filename, int max_mipmaps,
+	uint32_t pixel_format, int layout, detexb200DeviceImage *levels_out, int *nu_levels_out,
+	uint32_t *texture_format_out, int *all_valid_out, void *stream);
+DETEXB200_API void detexb200FreeDeviceImages(detexb200DeviceImage *levels, int nu_levels);
+
 /* Library / device information. */
 DETEXB200_API int detexb200DeviceCount(void);
 DETEXB200_API const char *detexb200Version(void);
