@@ -403,6 +403,71 @@ __device__ __forceinline__ void apply_step(uint32_t op, uint32_t sf, uint32_t tf
 
 constexpr int CONVERT_THREADS = 256, CONVERT_TILE = 1024;		// pixels per CTA pass
 
+// Components of one staged pixel <-> registers.  Pixels of 4, 8, 12 or 16 bytes are whole words
+// (the tile is 16-byte aligned and the pixel size a multiple of 4): one to four 32-bit shared
+// accesses instead of one per component; the other sizes go component by component.
+__device__ __forceinline__ void load_pixel(const uint8_t *in, uint32_t ps, uint32_t cs, int n, uint32_t (&c)[4]) {
+	if ((ps & 3u) == 0u) {
+		const uint32_t *w = reinterpret_cast<const uint32_t *>(in);
+		if (cs == 4u) {
+#pragma unroll
+			for (int j = 0; j < 4; j++)
+				if (j < n)
+					c[j] = w[j];
+		}
+		else if (cs == 2u) {
+			const uint32_t a = w[0];
+			c[0] = a & 0xFFFFu;
+			c[1] = a >> 16;
+			if (ps == 8u) {
+				const uint32_t b = w[1];
+				c[2] = b & 0xFFFFu;
+				c[3] = b >> 16;
+			}
+		}
+		else {
+			const uint32_t a = w[0];
+			c[0] = a & 0xFFu;
+			c[1] = (a >> 8) & 0xFFu;
+			c[2] = (a >> 16) & 0xFFu;
+			c[3] = a >> 24;
+		}
+		return;
+	}
+#pragma unroll
+	for (int j = 0; j < 4; j++)
+		if (j < n)
+			c[j] = cs == 1u ? in[j] : reinterpret_cast<const uint16_t *>(in)[j];
+}
+
+__device__ __forceinline__ void store_pixel(uint8_t *out, uint32_t ps, uint32_t cs, int n, const uint32_t (&c)[4]) {
+	if ((ps & 3u) == 0u) {
+		uint32_t *w = reinterpret_cast<uint32_t *>(out);
+		if (cs == 4u) {
+#pragma unroll
+			for (int j = 0; j < 4; j++)
+				if (j < n)
+					w[j] = c[j];
+		}
+		else if (cs == 2u) {
+			w[0] = (c[0] & 0xFFFFu) | (c[1] << 16);
+			if (ps == 8u)
+				w[1] = (c[2] & 0xFFFFu) | (c[3] << 16);
+		}
+		else
+			w[0] = (c[0] & 0xFFu) | ((c[1] & 0xFFu) << 8) | ((c[2] & 0xFFu) << 16) | (c[3] << 24);
+		return;
+	}
+#pragma unroll
+	for (int j = 0; j < 4; j++)
+		if (j < n) {
+			if (cs == 1u)
+				out[j] = (uint8_t)c[j];
+			else
+				reinterpret_cast<uint16_t *>(out)[j] = (uint16_t)c[j];
+		}
+}
+
 // Coalesced copy of n bytes between global and shared memory: 16-byte vectors when both sides
 // allow it, bytes otherwise (odd pixel sizes at a tile tail, unaligned caller buffers).
 template <bool TO_SHARED>
@@ -444,25 +509,10 @@ convert_kernel(const uint8_t *src, uint8_t *dst, uint64_t n_pixels, ConvertProgr
 		__syncthreads();
 		for (uint32_t px = threadIdx.x; px < here; px += CONVERT_THREADS) {
 			uint32_t c[4] = { 0u, 0u, 0u, 0u };
-			const uint8_t *in = tile_in + px * ps_in;
-#pragma unroll
-			for (int j = 0; j < 4; j++)
-				if (j < n_in)
-					c[j] = cs_in == 1u ? in[j] : (cs_in == 2u ? reinterpret_cast<const uint16_t *>(in)[j] :
-						reinterpret_cast<const uint32_t *>(in)[j]);
+			load_pixel(tile_in + px * ps_in, ps_in, cs_in, n_in, c);
 			for (int s = 0; s < prog.n_steps; s++)
 				apply_step(prog.op[s], prog.format[s], prog.format[s + 1], c, prog);
-			uint8_t *out = tile_out + px * ps_out;
-#pragma unroll
-			for (int j = 0; j < 4; j++)
-				if (j < n_out) {
-					if (cs_out == 1u)
-						out[j] = (uint8_t)c[j];
-					else if (cs_out == 2u)
-						reinterpret_cast<uint16_t *>(out)[j] = (uint16_t)c[j];
-					else
-						reinterpret_cast<uint32_t *>(out)[j] = c[j];
-				}
+			store_pixel(tile_out + px * ps_out, ps_out, cs_out, n_out, c);
 		}
 		__syncthreads();
 		tile_copy<false>(tile_out, dst + first * ps_out, here * ps_out);

@@ -78,7 +78,7 @@ def test_uncompressed_file_is_converted_on_device(tmp_path):
     pay = [rng.integers(0, 256, a * b * 4, dtype=np.uint8).tobytes() for (a, b, _, _) in dims]
     path = str(tmp_path / "rgba.ktx")
     CF.write_ktx(path, 0x1908, 0x1908, 0x1401, w, h, 4, 1, pay)
-    for pf in (0, H.PIXEL_FORMATS["BGRA8"], H.PIXEL_FORMATS["RGB8"], H.PIXEL_FORMATS["FLOAT_RGBA16"]):
+    for pf in (0, H.PIXEL_FORMATS["BGRA8"], H.PIXEL_FORMATS["RGB8"], H.PIXEL_FORMATS["RGBA16"], H.PIXEL_FORMATS["FLOAT_RGBX16"]):
         imgs, tf, all_valid, free = D.load_texture_file_to_device(path, 8, pf)
         try:
             assert tf == 0x334 and len(imgs) == levels and all_valid
