@@ -25,8 +25,9 @@ int force_modes) {
 	for (uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; u < n_units; u += (uint64_t)gridDim.x * blockDim.x) {
 		const uint64_t g = first_unit + u;
 		uint64_t w0 = splitmix64_word(seed, 2 * g), w1 = splitmix64_word(seed, 2 * g + 1);
-		if (force_modes == 8) {			// BC7: unary mode prefix, block g gets mode g % 8
-			const uint32_t m = (uint32_t)(g % 8ull);
+		if (force_modes == 8 || (force_modes >= 100 && force_modes < 108)) {
+			// BC7: unary mode prefix, block g gets mode g % 8 (100 + m: every block mode m, profiling aid)
+			const uint32_t m = force_modes == 8 ? (uint32_t)(g % 8ull) : (uint32_t)(force_modes - 100);
 			const uint64_t b0 = ((w0 & 0xFFull) & ((0xFFull << (m + 1)) & 0xFFull)) | (1ull << m);
 			w0 = (w0 & ~0xFFull) | b0;
 		}

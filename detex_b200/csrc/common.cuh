@@ -12,7 +12,13 @@
 //     zero-fills the tile (Q16, reference texture.c:90-93,125-128).
 #pragma once
 #include <cstdint>
+#ifdef DETEXB200_HOST_EMU
+// tests/emu/host_emu.h: the decoders' register arithmetic compiled for the CPU so that tests can
+// compare it with the oracle without a GPU (test infrastructure only; never part of the library)
+#include "host_emu.h"
+#else
 #include <cuda_runtime.h>
+#endif
 
 namespace detexb200 {
 
@@ -27,6 +33,7 @@ enum FormatIndex : int {
 // Decompression flags (reference detex.h:398-411).
 constexpr uint32_t FLAG_ENCODE = 1, FLAG_OPAQUE_ONLY = 2, FLAG_NON_OPAQUE_ONLY = 4;
 
+#ifndef DETEXB200_HOST_EMU
 // ---- streaming global memory access --------------------------------------------
 // Inputs are read exactly once: non-coherent path, do not allocate in L1.
 __device__ __forceinline__ uint2 ld_stream_v2(const void *p) {
@@ -59,6 +66,8 @@ __device__ __forceinline__ void st_stream_v2(void *p, uint32_t a, uint32_t b) {
 __device__ __forceinline__ void st_stream_u32(void *p, uint32_t a) {
 	asm volatile("st.global.cs.u32 [%0], %1;" :: "l"(p), "r"(a) : "memory");
 }
+
+#endif  // DETEXB200_HOST_EMU
 
 // ---- bit helpers ---------------------------------------------------------------
 __device__ __forceinline__ int bfe_s(uint32_t v, int pos, int len) {	// sign-extending

@@ -66,9 +66,13 @@ __device__ __forceinline__ typename IndexWord<BITS>::type index_window(const uin
 }
 // a*b + c, pinned to the integer multiply-add (FMA pipe) instead of a compiler-chosen select
 __device__ __forceinline__ uint32_t mad_u32(uint32_t a, uint32_t b, uint32_t c) {
+#ifdef DETEXB200_HOST_EMU
+	return a * b + c;
+#else
 	uint32_t d;
 	asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
 	return d;
+#endif
 }
 
 // Interpolation weights aWeight2/3/4 (bptc-tables.c:192-201) in closed form:
@@ -113,37 +117,65 @@ __device__ __forceinline__ uint32_t widen8(uint32_t v) {
 		return ((v << (8 - N)) | (v >> (2 * N - 8))) & 0xFFu;
 }
 
-template <int M>
-__device__ __forceinline__ void bc7_decode_mode(const uint4 &w, const BptcTables &tab, uint32_t (&px)[16]) {
-	constexpr Bc7ModeInfo I = bc7_mode_info(M);
-	constexpr int NS = I.ns, NE = 2 * I.ns, CB = I.cb, AB = I.ab, IB = I.ib, IB2 = I.ib2;
-	constexpr int P_PART = M + 1;
-	constexpr int P_ROT = P_PART + I.pb;
-	constexpr int P_ISB = P_ROT + I.rb;
-	constexpr int P_COL = P_ISB + I.isb;
-	constexpr int P_ALPHA = P_COL + 3 * NE * CB;
-	constexpr int P_PBIT = P_ALPHA + NE * AB;
-	constexpr int P_IDX = P_PBIT + (I.epb ? NE : (I.spb ? NS : 0));
-	constexpr int P_IDX2 = P_IDX + 16 * IB - NS;
+// Compile-time field positions of mode M (layout comment decompress-bptc.c:23-42).
+template <int M> struct Bc7Layout {
+	static constexpr Bc7ModeInfo I = bc7_mode_info(M);
+	static constexpr int NS = I.ns, NE = 2 * I.ns, CB = I.cb, AB = I.ab, IB = I.ib, IB2 = I.ib2;
+	static constexpr int P_PART = M + 1;
+	static constexpr int P_ROT = P_PART + I.pb;
+	static constexpr int P_ISB = P_ROT + I.rb;
+	static constexpr int P_COL = P_ISB + I.isb;
+	static constexpr int P_ALPHA = P_COL + 3 * NE * CB;
+	static constexpr int P_PBIT = P_ALPHA + NE * AB;
+	static constexpr int P_IDX = P_PBIT + (I.epb ? NE : (I.spb ? NS : 0));
+	static constexpr int P_IDX2 = P_IDX + 16 * IB - NS;
 	static_assert(IB2 == 0 || NS == 1, "dual index sets only occur in single-subset modes");
 	static_assert(P_IDX2 + (IB2 ? 16 * IB2 - 1 : 0) == 128, "mode layout must fill the block");
+};
 
-	const uint32_t partition = field128<P_PART, I.pb>(w);
-	const uint32_t rotation = field128<P_ROT, I.rb>(w);
-	const uint32_t isb = field128<P_ISB, I.isb>(w);
-
-	// ---- endpoints: component-major fields (decompress-bptc.c:82-87) -> packed lanes.
-	// Fields are packed two to a register first (R | B<<16, G | A<<16) so that the p-bit append
-	// and the widening to 8 bits (left-align + MSB replication, :160-175) run once per register.
-	constexpr int CP = CB + ((I.epb || I.spb) ? 1 : 0);	// colour precision incl. p-bit
-	uint32_t e_rb[NE], e_ga[NE];
+// Endpoints of mode M: component-major fields (decompress-bptc.c:82-87) -> packed lanes
+// e_rb[e] = R | B << 16, e_ga[e] = G | A << 16, widened to 8 bits.  Fields are packed two to a
+// register first so that the p-bit append and the widening to 8 bits (left-align + MSB
+// replication, :160-175) run once per register.
+template <int M>
+__device__ __forceinline__ void bc7_endpoints(const uint4 &w, uint32_t (&e_rb)[2 * bc7_mode_info(M).ns],
+uint32_t (&e_ga)[2 * bc7_mode_info(M).ns]) {
+	using L = Bc7Layout<M>;
+	constexpr int NE = L::NE;
+	if constexpr (M == 0) {
+		// Mode 0: six 4-bit fields per channel, contiguous, then six p-bits.  All six endpoints of a
+		// channel are widened together, one byte each: even endpoints (= endpoint 0 of subsets
+		// 0,1,2) in bytes 0-2 of one register, odd endpoints in another; byte 3 stays zero and
+		// serves as the zero byte of the PRMT that forms the 16-bit lanes.
+		const uint32_t xr = field128<L::P_COL, 24>(w), xg = field128<L::P_COL + 24, 24>(w), xb = field128<L::P_COL + 48, 24>(w);
+		const uint32_t p = field128<L::P_PBIT, 6>(w);
+		// p-bits 0,2,4 -> bit 0 of bytes 0,1,2: copies at +0,+6,+12 touch nine distinct bit positions
+		const uint32_t pe = ((p & 0x15u) * 0x1041u) & 0x010101u, po = (((p >> 1) & 0x15u) * 0x1041u) & 0x010101u;
+		auto widen = [](uint32_t nib, uint32_t pb) {		// 4 bits + p-bit -> 5 -> 8 (:160-175), three bytes at once
+			const uint32_t v5 = nib * 2u + pb;
+			return (v5 * 8u) | ((v5 >> 2) & 0x070707u);
+		};
+		const uint32_t re = widen(xr & 0x0F0F0Fu, pe), ro = widen((xr >> 4) & 0x0F0F0Fu, po);
+		const uint32_t ge = widen(xg & 0x0F0F0Fu, pe), go = widen((xg >> 4) & 0x0F0F0Fu, po);
+		const uint32_t be = widen(xb & 0x0F0F0Fu, pe), bo = widen((xb >> 4) & 0x0F0F0Fu, po);
+#pragma unroll
+		for (int s = 0; s < 3; s++) {
+			e_rb[2 * s] = prmt(re, be, 0x3430u + 0x0101u * s);	// {re.s, 0, be.s, 0}
+			e_rb[2 * s + 1] = prmt(ro, bo, 0x3430u + 0x0101u * s);
+			e_ga[2 * s] = prmt(ge, 0xFFu, 0x3430u + s);		// {ge.s, 0, 255, 0}: alpha 255 (:176-179)
+			e_ga[2 * s + 1] = prmt(go, 0xFFu, 0x3430u + s);
+		}
+		return;
+	}
 	static_for<0, NE>([&](auto e_) {
 		constexpr int e = decltype(e_)::value;
-		constexpr Bc7ModeInfo J = bc7_mode_info(M);	// (constexpr locals of the enclosing scope are not usable here)
+		constexpr Bc7ModeInfo J = bc7_mode_info(M);
+		constexpr int CB = J.cb, AB = J.ab, NEJ = 2 * J.ns;
+		constexpr int P_COL = Bc7Layout<M>::P_COL, P_ALPHA = Bc7Layout<M>::P_ALPHA, P_PBIT = Bc7Layout<M>::P_PBIT;
 		constexpr int CPJ = J.cb + ((J.epb || J.spb) ? 1 : 0), APJ = J.ab + (J.epb ? 1 : 0);
-		const uint32_t r = field128<P_COL + (0 * NE + e) * CB, CB>(w);
-		const uint32_t g = field128<P_COL + (1 * NE + e) * CB, CB>(w);
-		const uint32_t b = field128<P_COL + (2 * NE + e) * CB, CB>(w);
+		const uint32_t r = field128<P_COL + (0 * NEJ + e) * CB, CB>(w);
+		const uint32_t g = field128<P_COL + (1 * NEJ + e) * CB, CB>(w);
+		const uint32_t b = field128<P_COL + (2 * NEJ + e) * CB, CB>(w);
 		const uint32_t a = field128<P_ALPHA + e * AB, AB>(w);
 		uint32_t rb = r | (b << 16), ga = g | (a << 16);
 		if constexpr (J.epb != 0) {
@@ -176,6 +208,21 @@ __device__ __forceinline__ void bc7_decode_mode(const uint4 &w, const BptcTables
 		e_rb[e] = rb;
 		e_ga[e] = ga;
 	});
+}
+
+template <int M>
+__device__ __forceinline__ void bc7_decode_mode(const uint4 &w, const BptcTables &tab, uint32_t (&px)[16]) {
+	using L = Bc7Layout<M>;
+	constexpr Bc7ModeInfo I = bc7_mode_info(M);
+	constexpr int NS = L::NS, NE = L::NE, IB = L::IB, IB2 = L::IB2;
+	constexpr int P_PART = L::P_PART, P_ROT = L::P_ROT, P_ISB = L::P_ISB, P_IDX = L::P_IDX, P_IDX2 = L::P_IDX2;
+
+	const uint32_t partition = field128<P_PART, I.pb>(w);
+	const uint32_t rotation = field128<P_ROT, I.rb>(w);
+	const uint32_t isb = field128<P_ISB, I.isb>(w);
+
+	uint32_t e_rb[NE], e_ga[NE];
+	bc7_endpoints<M>(w, e_rb, e_ga);
 	// Per subset: A = 4*(64*E0 + 32) per lane, K = 4*(E1 - E0) (packed integer difference).
 	uint32_t a_rb[NS], k_rb[NS], a_ga[NS], k_ga[NS];
 #pragma unroll

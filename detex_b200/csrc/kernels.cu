@@ -24,6 +24,7 @@
 #include "decode_s3tc.cuh"
 #include "decode_etc.cuh"
 #include "decode_bptc.cuh"
+#include "decode_bptc_palette.cuh"
 #include "decode_bptc_float.cuh"
 #include "launch.h"
 
@@ -857,6 +858,351 @@ int height, int wib, uint32_t mode_mask, uint32_t flags, uint32_t post_op, uint3
 	report_invalid(bad, invalid_flag);
 }
 
+// ---- BC7: mode-sorted, palette-staged, barrier-free dataflow kernel ---------------------------
+// One persistent CTA of 1024 threads per SM works through tiles of 1024 consecutive blocks.  As in
+// decode_sorted_kernel the blocks of a tile are counting-sorted by mode so that a warp decodes 32
+// blocks of ONE mode, but
+//   * what a lane parks in shared memory is not the 16 pixels of its block: it is the block's
+//     PALETTE (<= 16 colours, each computed with a compile-time subset and weight,
+//     decode_bptc_palette.cuh) plus 16 selector bytes; the look-ups happen in the copy-out, whose
+//     lanes map to blocks in image order so that their stores are contiguous;
+//   * there is no CTA-wide barrier after start-up.  The cost of a decode group differs 6x between
+//     modes, so any scheme that makes all warps meet once per tile leaves most of them waiting for
+//     the mode-0 groups (measured: 24 % of all warp time).  Instead
+//       - four BOOKKEEPER warps run ahead through the tiles: cp.async load (one tile ahead),
+//         classify, histogram, bin starts, scatter of the sorted ids -- synchronising among
+//         themselves with a 128-thread named barrier -- and publish `book_done`;
+//       - every other warp (and the bookkeepers once they run out of tiles) draws WORK ITEMS from one
+//         monotonic ticket: per tile FLOW_DEC decode slots (group r of tile j; slots beyond the
+//         tile's group count are empty) followed by FLOW_OUT copy-out chunks of tile j-1;
+//       - dependencies are monotonic counters in shared memory (decode slots finished per stage
+//         buffer, copy-out chunks finished per compressed-tile buffer, tiles scattered), waited for
+//         with a short polling loop.  Every wait is for work with smaller ticket numbers (or for the
+//         bookkeepers, whose own waits are for strictly older tiles), so the scheme cannot deadlock.
+//
+// Buffers: stage[tile & 1], raw[tile & 3] (compressed blocks, later the selectors), id[tile & 1].
+//   decode(j) needs: tile j scattered; stage[j & 1] free = copy-out(j-2) complete
+//   copy-out(j) needs: decode(j) complete
+//   load(j) needs: raw[j & 3] free = copy-out(j-4) complete
+//   scatter(j) needs: id[j & 1] free = decode(j-2) complete
+//
+// Stage layout: word (chunk, e, p) at chunk*1024 + e*64 + p with chunk = id / 64 and
+// p = (id % 64) ^ ((id / 32) % 8): the bank of an entry is p % 32 whatever e is, so
+//   * the copy-out look-ups of 32 consecutive ids never conflict (id / 32 is warp-uniform),
+//   * the decode stores of a same-mode group conflict only by chance (the XOR spreads the
+//     adversarial distribution M, where all ids of a group are congruent mod 8).
+// A stage is 4 KiB-aligned in the shared window and an entry row is 256 bytes, so the address of
+// entry e of block id is base(id) | e << 8: with the selector bytes pre-biased by byte 1 of
+// base(id), ONE byte permute builds the address of a pixel (bytes 0, 2, 3 from base(id), byte 1
+// from the selector word).  The selectors overwrite the block's own slot of the compressed tile.
+constexpr int FLOW_TB = 1024, FLOW_NT = 1024, FLOW_NB = 9, FLOW_CAP = FLOW_TB + FLOW_NB * 32;
+constexpr int FLOW_BOOK = 4, FLOW_BT = FLOW_BOOK * 32, FLOW_PER = FLOW_TB / FLOW_BT;
+constexpr int FLOW_DEC = (FLOW_TB + FLOW_NB * 31 + 31) / 32, FLOW_OUT = FLOW_TB / 32, FLOW_ITEMS = FLOW_DEC + FLOW_OUT;
+constexpr int FLOW_SPIN_LIMIT = 1 << 22;	// polls before a wait gives up and flags the launch as failed
+struct Bc7FlowSmem {
+	uint32_t stage[2][FLOW_TB * 16];	// [tile & 1]
+	uint4 raw[4][FLOW_TB];			// [tile & 3] compressed blocks, later the selectors
+	uint16_t id[2][FLOW_CAP];		// [tile & 1] tile-local block index per sorted slot
+	int start[2][16];			// [tile & 1] first sorted slot of bin b; [NB] = padded total
+	int count[2][16];			// [tile & 1] per-mode histogram
+	int ticket;				// next work item
+	int book_done;				// tiles scattered
+	int dec_cnt[2];				// decode slots finished, per stage buffer (monotonic)
+	int out_cnt[4];				// copy-out chunks finished, per compressed-tile buffer (monotonic)
+	int error;
+	uint8_t bin_lut[256];			// byte 0 of a block -> bin (mode, or 8 = invalid under mode_mask / flags)
+	Bc7PaletteTables tables;
+};
+constexpr size_t FLOW_SMEM_BYTES = sizeof(Bc7FlowSmem) + 4096;	// + alignment slack
+
+__device__ __forceinline__ void st_shared_u32(uint32_t addr, uint32_t v) {
+	asm volatile("st.shared.u32 [%0], %1;" :: "r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_shared_u32(uint32_t addr) {
+	uint32_t v;
+	asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+	return v;
+}
+// shared-window byte address of entry 0 of block id (tile-local index)
+__device__ __forceinline__ uint32_t pal_base(uint32_t stage_base, uint32_t id) {
+	return stage_base + ((id >> 6) << 12) + ((((id & 63u) ^ ((id >> 5) & 7u))) << 2);
+}
+// acquire side of a counter dependency: poll until *counter >= target
+__device__ __forceinline__ void flow_wait(const int *counter, int target, int *error) {
+	const volatile int *c = counter;
+	if (*c < target) {
+		int spins = 0;
+		while (*c < target && *(volatile int *)error == 0) {	// (the error flag is sticky: a failed launch ends quickly)
+			__nanosleep(64);
+			if (++spins > FLOW_SPIN_LIMIT)
+				*(volatile int *)error = 1;
+		}
+	}
+	__threadfence_block();
+}
+// release side: the warp's shared-memory writes become visible, then one lane bumps the counter
+__device__ __forceinline__ void flow_signal(int *counter, int lane) {
+	__threadfence_block();
+	__syncwarp();
+	if (lane == 0)
+		atomicAdd(counter, 1);
+}
+
+template <int LAYOUT, int PC>
+__global__ void __launch_bounds__(FLOW_NT, 1)
+decode_bc7_flow_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, uint32_t n_blocks, int width,
+int height, int wib, uint32_t mode_mask, uint32_t flags, uint32_t post_op, uint32_t *invalid_flag, uint32_t *invalid_map) {
+	using S = SortTraits<F_BPTC>;
+	using SM = Bc7FlowSmem;
+	constexpr int NB = FLOW_NB, TB = FLOW_TB, BT = FLOW_BT, PER = FLOW_PER;
+	static_assert(NB == S::NUM_BINS, "bins");
+	static_assert(PC == PC_NATIVE || PC == PC_PACK3, "BC7 post classes");
+	constexpr int OWO = post_words<16, PC>();		// words of a stored tile
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	const uint32_t window = (uint32_t)__cvta_generic_to_shared(smem_raw);
+	SM &sm = *reinterpret_cast<SM *>(smem_raw + ((0u - window) & 4095u));
+	const uint32_t stage_base0 = (uint32_t)__cvta_generic_to_shared(sm.stage);	// multiple of 4096
+	const int tid = threadIdx.x, lane = tid & 31;
+	const uint32_t n_tiles = (n_blocks + TB - 1) / TB;
+	// tiles of this CTA: tile(j) = blockIdx.x + j * gridDim.x, j = 0 .. n_local-1
+	const int n_local = blockIdx.x < n_tiles ? (int)((n_tiles - 1 - blockIdx.x) / gridDim.x) + 1 : 0;
+	const bool swap_rb = (post_op & POST_SWAP_RB) != 0;
+	const size_t pitch = (size_t)width * (OWO / 4);
+	if (tid < 32)
+		(&sm.count[0][0])[tid] = 0;
+	if (tid < 16)
+		(&sm.ticket)[tid < 9 ? tid : 0] = 0;		// ticket, book_done, dec_cnt[2], out_cnt[4], error
+	bptc_tables_load(sm.tables.packed);
+	if (tid < 64) {
+		sm.tables.sub2[tid] = bc7_subset_bytes(bptc_two_global[tid] & 0xFFFFu, 1);
+		sm.tables.sub3[tid] = bc7_subset_bytes(bptc_three_global[tid].x, 2);
+	}
+	if (tid < 256) {
+		uint4 probe;
+		probe.x = (uint32_t)tid; probe.y = probe.z = probe.w = 0u;
+		sm.bin_lut[tid] = (uint8_t)S::bin_of(probe, mode_mask, flags);
+	}
+	__syncthreads();
+	auto tile_of = [&](int j) { return blockIdx.x + (uint32_t)j * gridDim.x; };
+	auto blocks_in = [&](int j) { return min((uint32_t)TB, n_blocks - tile_of(j) * TB); };
+
+	// ================= bookkeepers: load, classify, histogram, bin starts, scatter =================
+	if (tid < BT) {
+		auto issue_load = [&](int j) {
+			const uint32_t tile0 = tile_of(j) * TB;
+#pragma unroll
+			for (int k = 0; k < PER; k++) {
+				const uint32_t id = k * BT + tid, i = tile0 + id;
+				if (i < n_blocks)
+					cp_async_16(&sm.raw[j & 3][raw_slot(id)], src + (size_t)i * 16);
+			}
+			asm volatile("cp.async.commit_group;" ::: "memory");
+		};
+		if (n_local > 0)
+			issue_load(0);
+		for (int b = 0; b < n_local; b++) {
+			// one tile ahead: its buffer held tile b-3, whose selectors the copy-out must have consumed
+			if (b + 1 < n_local) {
+				if (b + 1 >= 4)
+					flow_wait(&sm.out_cnt[(b + 1) & 3], FLOW_OUT * ((b - 3) / 4 + 1), &sm.error);
+				issue_load(b + 1);
+				asm volatile("cp.async.wait_group 1;" ::: "memory");
+			}
+			else
+				asm volatile("cp.async.wait_group 0;" ::: "memory");
+			// id[b & 1], start[b & 1] are free once every decode slot of tile b-2 has finished
+			if (b >= 2)
+				flow_wait(&sm.dec_cnt[b & 1], FLOW_DEC * ((b - 2) / 2 + 1), &sm.error);
+			const uint32_t n_here = blocks_in(b);
+			int *count = sm.count[b & 1];
+			int bin[PER], off[PER];
+#pragma unroll
+			for (int k = 0; k < PER; k++) {
+				const uint32_t id = k * BT + tid;
+				bin[k] = -1;
+				if (id < n_here)
+					bin[k] = sm.bin_lut[reinterpret_cast<const uint8_t *>(&sm.raw[b & 3][raw_slot(id)])[0]];
+			}
+#pragma unroll
+			for (int k = 0; k < PER; k++) {
+				const unsigned peers = __match_any_sync(0xFFFFFFFFu, bin[k]);
+				const int leader = __ffs((int)peers) - 1;
+				int base = 0;
+				if (lane == leader && bin[k] >= 0)
+					base = atomicAdd(&count[bin[k]], __popc(peers));
+				base = __shfl_sync(0xFFFFFFFFu, base, leader);
+				off[k] = base + __popc(peers & ((1u << lane) - 1u));
+			}
+			asm volatile("bar.sync 1, %0;" :: "n"(FLOW_BT) : "memory");	// histogram complete; everyone's copies landed
+			const int my_count = lane < NB ? count[lane] : 0;
+			const int padded = (my_count + 31) & ~31;
+			int st = padded;
+#pragma unroll
+			for (int d = 1; d < 16; d *= 2) {
+				const int t = __shfl_up_sync(0xFFFFFFFFu, st, d);
+				if (lane >= d)
+					st += t;
+			}
+			st -= padded;			// lane b: first sorted slot of bin b; lane NB: the padded total
+			if (tid < 16)
+				sm.start[b & 1][tid] = st;
+			uint16_t *ids = sm.id[b & 1];
+			// padding slots at the end of every bin get the sentinel (one warp per bin)
+			for (int q = tid >> 5; q < NB; q += FLOW_BOOK) {
+				const int c = __shfl_sync(0xFFFFFFFFu, my_count, q), s0 = __shfl_sync(0xFFFFFFFFu, st, q);
+				if (lane < ((-c) & 31))
+					ids[s0 + c + lane] = (uint16_t)SLOT_EMPTY;
+			}
+#pragma unroll
+			for (int k = 0; k < PER; k++) {
+				const int s0 = __shfl_sync(0xFFFFFFFFu, st, bin[k] & 31);
+				if (bin[k] >= 0)
+					ids[s0 + off[k]] = (uint16_t)(k * BT + tid);
+			}
+			asm volatile("bar.sync 1, %0;" :: "n"(FLOW_BT) : "memory");	// scatter complete, histogram consumed
+			if (tid < 16)
+				count[tid] = 0;			// for tile b+2
+			if (tid == 0) {
+				__threadfence_block();
+				*(volatile int *)&sm.book_done = b + 1;
+			}
+		}
+	}
+
+	// ================= workers: decode groups and copy-out chunks from the ticket =================
+	bool bad = false;
+	auto draw = [&]() {
+		int t = 0;
+		if (lane == 0)
+			t = atomicAdd(&sm.ticket, 1);
+		return __shfl_sync(0xFFFFFFFFu, t, 0);
+	};
+	int t_next = draw();
+	while (true) {
+		const int t = t_next;
+		const int j = t / FLOW_ITEMS, r = t - j * FLOW_ITEMS;	// tile of the decode slots; copy-out chunks belong to tile j-1
+		if (j > n_local)
+			break;
+		t_next = draw();
+		if (r < FLOW_DEC) {
+			if (j >= n_local)
+				continue;
+			// ---- decode slot r of tile j
+			flow_wait(&sm.book_done, j + 1, &sm.error);
+			const int start_cur = sm.start[j & 1][lane & 15];
+			const int n_dec = __shfl_sync(0xFFFFFFFFu, start_cur, NB);
+			const int g = r * 32;
+			if (g < n_dec) {
+				if (j >= 2)		// stage[j & 1] held tile j-2
+					flow_wait(&sm.out_cnt[(j - 2) & 3], FLOW_OUT * ((j - 2) / 4 + 1), &sm.error);
+				const uint32_t id = sm.id[j & 1][g + lane];
+				// the group's bin from its position: number of bins that start at or before g (uniform)
+				const int mode = __popc(__ballot_sync(0xFFFFFFFFu, lane < NB && start_cur <= g)) - 1;
+				if (id != SLOT_EMPTY) {
+					uint4 *raw_dec = sm.raw[j & 3];
+					const uint32_t rs = raw_slot(id);
+					const uint4 w = raw_dec[rs];
+					const uint32_t base = pal_base(stage_base0 + (uint32_t)(j & 1) * (TB * 64u), id);
+					const uint32_t bias = prmt(base, 0u, 0x1111);	// byte 1 of the address in every byte
+					if (mode == 8) {
+						bad = true;
+						mark_invalid(invalid_map, tile_of(j) * TB + id);
+						st_shared_u32(base, invalid_fill(post_op));
+						raw_dec[rs] = make_uint4(bias, bias, bias, bias);
+					}
+					else {
+						bc7_palette(w, mode, sm.tables, swap_rb, [&](uint32_t (&pal)[16], uint32_t (&sel)[4], auto ne_) {
+							constexpr int NE = decltype(ne_)::value;
+							if (post_op & (POST_FLIP16 | POST_FLIP8)) {	// (never set for RGBA8 targets by the API)
+								const uint32_t top = (post_op & POST_FLIP16) ? 0x80008000u : 0x80808080u;
+#pragma unroll
+								for (int e = 0; e < NE; e++)
+									pal[e] ^= top;
+							}
+#pragma unroll
+							for (int e = 0; e < NE; e++)
+								st_shared_u32(base + e * 256, pal[e]);
+							raw_dec[rs] = make_uint4(sel[0] + bias, sel[1] + bias, sel[2] + bias, sel[3] + bias);
+						});
+					}
+				}
+			}
+			flow_signal(&sm.dec_cnt[j & 1], lane);
+		}
+		else {
+			if (j < 1)
+				continue;
+			// ---- copy-out chunk of tile j-1: 32 consecutive blocks, lane <-> block
+			const int jj = j - 1, g = (r - FLOW_DEC) * 32;
+			flow_wait(&sm.dec_cnt[jj & 1], FLOW_DEC * (jj / 2 + 1), &sm.error);
+			const uint32_t n_here = blocks_in(jj), tile0 = tile_of(jj) * TB;
+			const uint32_t cid = (uint32_t)g + lane;
+			// block coordinates of the chunk's first block (uniform), then per lane
+			const uint32_t i0 = tile0 + (uint32_t)g;
+			const uint32_t by0 = LAYOUT == LAYOUT_LINEAR ? i0 / (uint32_t)wib : 0u, bx0 = i0 - by0 * (uint32_t)wib;
+			if (cid < n_here) {
+				const uint4 s4 = sm.raw[jj & 3][raw_slot(cid)];
+				const uint32_t base = pal_base(stage_base0 + (uint32_t)(jj & 1) * (TB * 64u), cid);
+				const uint32_t sw[4] = { s4.x, s4.y, s4.z, s4.w };
+				uint32_t px[16];
+#pragma unroll
+				for (int q = 0; q < 4; q++) {
+					px[4 * q + 0] = ld_shared_u32(prmt(sw[q], base, 0x7604));
+					px[4 * q + 1] = ld_shared_u32(prmt(sw[q], base, 0x7614));
+					px[4 * q + 2] = ld_shared_u32(prmt(sw[q], base, 0x7624));
+					px[4 * q + 3] = ld_shared_u32(prmt(sw[q], base, 0x7634));
+				}
+				uint32_t q[OWO];
+				if constexpr (PC == PC_PACK3)
+					repack<PC_PACK3, 16>(px, q);
+				else {
+#pragma unroll
+					for (int k = 0; k < 16; k++)
+						q[k] = px[k];
+				}
+				if (LAYOUT == LAYOUT_TILED) {
+					uint8_t *out = dst + (size_t)(tile0 + cid) * (OWO * 4);
+					if (PC == PC_NATIVE && (((uintptr_t)dst) & 31u) == 0) {
+						st_stream_v8(out, q[0], q[1], q[2], q[3], q[4], q[5], q[6], q[7]);
+						st_stream_v8(out + 32, q[OWO - 8], q[OWO - 7], q[OWO - 6], q[OWO - 5], q[OWO - 4], q[OWO - 3], q[OWO - 2], q[OWO - 1]);
+					}
+					else {
+#pragma unroll
+						for (int c = 0; c < OWO / 4; c++)
+							st_stream_v4(out + 16 * c, q[4 * c], q[4 * c + 1], q[4 * c + 2], q[4 * c + 3]);
+					}
+				}
+				else {
+					uint32_t bx = bx0 + lane, by = by0;
+					while (bx >= (uint32_t)wib) {	// a chunk may wrap over block rows
+						bx -= (uint32_t)wib;
+						by++;
+					}
+					uint8_t *pp = dst + (size_t)by * 4 * pitch + bx * (uint32_t)OWO;	// OWO bytes per pixel row of a block
+					const int rows = height - (int)by * 4;	// >= 4 except in a clipped last block row (texture.c:117-120)
+#pragma unroll
+					for (int rr = 0; rr < 4; rr++) {
+						if (rr < rows) {
+							if constexpr (PC == PC_PACK3) {
+								st_stream_u32(pp, q[3 * rr]);
+								st_stream_u32(pp + 4, q[3 * rr + 1]);
+								st_stream_u32(pp + 8, q[3 * rr + 2]);
+							}
+							else
+								st_stream_v4(pp, q[4 * rr], q[4 * rr + 1], q[4 * rr + 2], q[4 * rr + 3]);
+						}
+						pp += pitch;
+					}
+				}
+			}
+			flow_signal(&sm.out_cnt[jj & 3], lane);
+		}
+	}
+	if (*(volatile int *)&sm.error && invalid_flag != nullptr)
+		*(volatile uint32_t *)invalid_flag = 0x7FFFFFFFu;	// a dependency wait gave up: the output is not trustworthy
+	report_invalid(bad, invalid_flag);
+}
+
 // ---- host-side launcher ---------------------------------------------------------------------
 static std::atomic<uint64_t> g_launches{0};
 
@@ -907,6 +1253,29 @@ cudaStream_t stream) {
 		a.width, a.height, a.wib, a.mode_mask, a.flags, a.post_op, a.invalid, a.invalid_map);
 }
 
+// DETEXB200_BC7_KERNEL=flow selects the palette-staged dataflow kernel for BC7 instead of
+// decode_sorted_kernel.  It is bit-exact (tests/test_gpu_parity.py runs the BC7 cases under it too)
+// but measured slower (profiles/README.md, "BC7 palette / dataflow experiment"), so it is not the default.
+static bool bc7_flow_kernel() {
+	static const bool v = [] { const char *e = getenv("DETEXB200_BC7_KERNEL"); return e && e[0] == 'f'; }();
+	return v;
+}
+template <int LAYOUT, int PC>
+static void launch_bc7_flow(const uint8_t *src, uint8_t *dst, uint32_t n_blocks, const DecodeArgs &a, cudaStream_t stream) {
+	static std::atomic<bool> configured[64];
+	int dev = 0;
+	cudaGetDevice(&dev);
+	if (!configured[dev & 63].load()) {
+		cudaFuncSetAttribute(decode_bc7_flow_kernel<LAYOUT, PC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FLOW_SMEM_BYTES);
+		configured[dev & 63].store(true);
+	}
+	const uint64_t tiles = ((uint64_t)n_blocks + FLOW_TB - 1) / FLOW_TB;
+	const uint64_t resident = (uint64_t)sm_count();		// persistent: one CTA of 1024 threads per SM
+	const unsigned grid = (unsigned)(tiles < resident ? tiles : resident);
+	decode_bc7_flow_kernel<LAYOUT, PC><<<grid, FLOW_NT, FLOW_SMEM_BYTES, stream>>>(src, dst, n_blocks,
+		a.width, a.height, a.wib, a.mode_mask, a.flags, a.post_op, a.invalid, a.invalid_map);
+}
+
 template <int F, int PC>
 static cudaError_t launch_format(const DecodeArgs &a, cudaStream_t stream) {
 	using T = FormatTraits<F>;
@@ -927,6 +1296,16 @@ static cudaError_t launch_format(const DecodeArgs &a, cudaStream_t stream) {
 			const uint64_t tiles = (n_blocks + TB - 1) / TB;
 			const uint64_t resident = (uint64_t)sm_count() * 2;		// persistent: two CTAs per SM
 			const unsigned grid = (unsigned)(tiles < resident ? tiles : resident);
+			if constexpr (F == F_BPTC && (PC == PC_NATIVE || PC == PC_PACK3)) {
+				if (bc7_flow_kernel()) {
+					if (a.layout == LAYOUT_TILED)
+						launch_bc7_flow<LAYOUT_TILED, PC>(src, dst, (uint32_t)n_blocks, a, stream);
+					else
+						launch_bc7_flow<LAYOUT_LINEAR, PC>(src, dst, (uint32_t)n_blocks, a, stream);
+					count_launch();
+					return cudaGetLastError();
+				}
+			}
 			constexpr bool ST = SortTraits<F>::STAGE_OUTPUT;
 			if (a.layout == LAYOUT_TILED && (PC != PC_NATIVE || (tiled_direct() && aligned32)))
 				launch_sorted<F, LAYOUT_TILED, false, PC>(grid, src, dst, (uint32_t)n_blocks, a, stream);

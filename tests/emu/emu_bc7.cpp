@@ -1,0 +1,78 @@
+/*
+ * TEST INFRASTRUCTURE ONLY: the BC7 palette decoder of detex_b200/csrc/decode_bptc_palette.cuh
+ * compiled for the CPU (host_emu.h) behind a C entry point, for tests/test_emu_bc7.py.
+ */
+#define DETEXB200_HOST_EMU 1
+#include "decode_bptc_palette.cuh"
+#include <cstring>
+
+using namespace detexb200;
+
+static Bc7PaletteTables g_tab;
+static bool g_tab_ready = false;
+
+static void tables_init() {
+	if (g_tab_ready)
+		return;
+	for (int i = 0; i < 64; i++) {
+		g_tab.packed.two[i] = bptc_two_global[i];
+		g_tab.packed.three[i] = bptc_three_global[i];
+		g_tab.sub2[i] = bc7_subset_bytes(bptc_two_global[i] & 0xFFFFu, 1);
+		g_tab.sub3[i] = bc7_subset_bytes(bptc_three_global[i].x, 2);
+	}
+	g_tab_ready = true;
+}
+
+extern "C" {
+
+/* n blocks -> n tiles of 16 RGBA8 pixels (TILED layout); valid[i] = 0 for an invalid block (tile
+   zero-filled like texture.c:90-93).  path 0: palette + selectors, path 1: the per-pixel decoder
+   (decode_bptc).  entries_out (optional): palette entries per block. */
+int emu_bc7_decode(const uint8_t *blocks, int n, int swap_rb, int path, uint8_t *pixels, uint8_t *valid,
+int *entries_out) {
+	tables_init();
+	for (int i = 0; i < n; i++) {
+		uint4 w;
+		memcpy(&w, blocks + 16 * (size_t)i, 16);
+		uint32_t px[16];
+		bool ok;
+		int entries = 16;
+		if (path == 1) {
+			ok = decode_bptc(w, 0xFFFFFFFFu, 0u, g_tab.packed, px);
+			if (ok && swap_rb)
+				for (int k = 0; k < 16; k++)
+					px[k] = prmt(px[k], 0u, 0x3012);
+		}
+		else {
+			const int mode = bc7_mode_of(w);
+			ok = mode >= 0;
+			if (ok) {
+				int rc = 0;
+				bc7_palette(w, mode, g_tab, swap_rb != 0, [&](uint32_t (&pal)[16], uint32_t (&sel)[4], auto ne_) {
+					constexpr int NE = decltype(ne_)::value;
+					entries = NE;
+					uint32_t stored[16];
+					for (int k = 0; k < 16; k++)	/* only the first NE entries reach the stage */
+						stored[k] = k < NE ? pal[k] : 0xDEADBEEFu;
+					for (int k = 0; k < 16; k++) {
+						const uint32_t s = (sel[k >> 2] >> (8 * (k & 3))) & 0xFFu;
+						if ((int)s >= NE)
+							rc = -(i + 1);	/* selector out of range */
+						px[k] = stored[s & 15u];
+					}
+				});
+				if (rc)
+					return rc;
+			}
+		}
+		if (!ok)
+			memset(px, 0, sizeof px);
+		memcpy(pixels + 64 * (size_t)i, px, 64);
+		valid[i] = ok ? 1 : 0;
+		if (entries_out)
+			entries_out[i] = entries;
+	}
+	return 0;
+}
+
+}

@@ -1,0 +1,49 @@
+/*
+ * TEST INFRASTRUCTURE ONLY.  Lets the register-level arithmetic of the CUDA decoders
+ * (detex_b200/csrc/decode_*.cuh) compile for the CPU with a plain C++ compiler: the CUDA
+ * keywords become no-ops and the handful of intrinsics the decoders use are restated with
+ * their PTX semantics.  tests/test_emu_bc7.py runs the result against the oracle, so that a
+ * change to a decoder can be checked bit-for-bit in a container without a GPU.  Nothing here
+ * is part of, or reachable from, libdetex_b200.so.
+ */
+#pragma once
+#include <cstdint>
+#include <algorithm>
+
+#define __device__
+#define __host__
+#define __global__
+#define __forceinline__ inline
+#define __restrict__
+
+struct uint2 { uint32_t x, y; };
+struct uint4 { uint32_t x, y, z, w; };
+static inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { return uint4{ x, y, z, w }; }
+static inline uint2 make_uint2(uint32_t x, uint32_t y) { return uint2{ x, y }; }
+
+/* prmt.b32 (default mode): result byte i = byte (sel nibble i & 7) of {b:a}; nibble bit 3
+   replicates that byte's sign bit */
+static inline uint32_t __byte_perm(uint32_t a, uint32_t b, uint32_t sel) {
+	const uint64_t v = ((uint64_t)b << 32) | a;
+	uint32_t r = 0;
+	for (int i = 0; i < 4; i++) {
+		const uint32_t n = (sel >> (4 * i)) & 0xFu;
+		uint32_t byte = (uint32_t)(v >> (8 * (n & 7u))) & 0xFFu;
+		if (n & 8u)
+			byte = (byte & 0x80u) ? 0xFFu : 0u;
+		r |= byte << (8 * i);
+	}
+	return r;
+}
+/* shf.r.wrap: low word of {hi:lo} >> (shift & 31) */
+static inline uint32_t __funnelshift_r(uint32_t lo, uint32_t hi, uint32_t shift) {
+	const uint64_t v = ((uint64_t)hi << 32) | lo;
+	return (uint32_t)(v >> (shift & 31u));
+}
+static inline int __ffs(int v) { return v == 0 ? 0 : __builtin_ctz((unsigned)v) + 1; }
+static inline int __popc(unsigned v) { return __builtin_popcount(v); }
+using std::min;
+using std::max;
+/* single-thread stand-ins for the launch geometry (table loaders loop over them) */
+struct EmuDim3 { unsigned x, y, z; };
+static const EmuDim3 threadIdx = { 0, 0, 0 }, blockDim = { 1, 1, 1 }, blockIdx = { 0, 0, 0 }, gridDim = { 1, 1, 1 };

@@ -19,6 +19,7 @@ def main():
     ap.add_argument("--blocks", type=int, default=1 << 22)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--modes", default="U", help="U, M or both (M only affects BC7/BC6H)")
+    ap.add_argument("--bc7-single-modes", default="", help="comma list of BC7 modes: one run per mode with EVERY block in that mode")
     args = ap.parse_args()
     peak, _ = measured_peak()
     dev = torch.device("cuda", 0)
@@ -33,8 +34,12 @@ def main():
         dists = ["U"]
         if fmt in ("BPTC", "BPTC_FLOAT", "BPTC_SIGNED_FLOAT") and args.modes in ("M", "both"):
             dists = ["M"] if args.modes == "M" else ["U", "M"]
+        if fmt == "BPTC" and args.bc7_single_modes:
+            dists += ["m%s" % m for m in args.bc7_single_modes.split(",")]
         for dist in dists:
             force = 0 if dist == "U" else (8 if fmt == "BPTC" else 14)
+            if dist.startswith("m"):
+                force = 100 + int(dist[1:])
             n_sets = max(2, int(600e6 // (n * (bs + 16 * ps))) + 1)
             sets = []
             for k in range(n_sets):
@@ -57,7 +62,7 @@ def main():
                 ms = e0.elapsed_time(e1) / args.steps
                 gbs = n * ALGO_BYTES[fmt] / ms / 1e6
                 rows.append(dict(format=fmt, dist=dist, layout=lname, us=ms * 1e3, gblocks_s=n / ms / 1e6, gbs=gbs, frac=gbs / peak))
-                print("%-20s %s %-6s %8.1f us  %7.2f Gblk/s  %7.0f GB/s  %5.1f%% of measured peak" %
+                print("%-20s %-2s %-6s %8.1f us  %7.2f Gblk/s  %7.0f GB/s  %5.1f%% of measured peak" %
                       (fmt, dist, lname, ms * 1e3, n / ms / 1e6, gbs, 100 * gbs / peak), flush=True)
             del sets
             torch.cuda.empty_cache()
