@@ -655,6 +655,7 @@ struct SortedSmem {
 	uint4 raw[2][TB];		// double-buffered compressed tile, filled by cp.async
 	uint16_t id[CAP];		// tile-local block index in each sorted slot
 	int count[2][16];		// per-mode histogram, double-buffered across tiles
+	uint8_t bin_lut[256];		// byte 0 of a block -> bin under this launch's mode_mask / flags
 	BptcTables tables;
 };
 
@@ -687,7 +688,7 @@ int height, int wib, uint32_t mode_mask, uint32_t flags, uint32_t post_op, uint3
 	constexpr int OW = T::OUT_WORDS, NB = S::NUM_BINS, TB = SM::TB, PER = TB / SORT_THREADS, CHUNKS = SM::CHUNKS;
 	constexpr int CPR = CHUNKS / 4;			// 16-byte chunks per pixel row of one block
 	static_assert(T::BLOCK_WORDS == 4, "sorted kernel handles 16-byte blocks");
-	static_assert(TB % SORT_THREADS == 0 && NB <= 16, "tile / bin limits");
+	static_assert(TB % SORT_THREADS == 0 && NB <= 16 && NB <= SORT_WARPS, "tile / bin limits");
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	SM &sm = *reinterpret_cast<SM *>(smem_raw);
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -695,6 +696,12 @@ int height, int wib, uint32_t mode_mask, uint32_t flags, uint32_t post_op, uint3
 	if (tid < 32)
 		(&sm.count[0][0])[tid] = 0;
 	bptc_tables_load(sm.tables);
+	// the bin of a block depends on its first byte only (BC7: lowest set bit; BC6H: 2 / 5 mode bits)
+	if (tid < 256) {
+		uint4 probe;
+		probe.x = (uint32_t)tid; probe.y = probe.z = probe.w = 0u;
+		sm.bin_lut[tid] = (uint8_t)S::bin_of(probe, mode_mask, flags);
+	}
 
 	auto issue_tile_load = [&](uint32_t tile, int buf) {
 #pragma unroll
@@ -716,17 +723,14 @@ int height, int wib, uint32_t mode_mask, uint32_t flags, uint32_t post_op, uint3
 			issue_tile_load(tile + gridDim.x, cur ^ 1);
 		if (tid < 16)
 			sm.count[cur ^ 1][tid] = 0;
-		// mark every sorted slot empty; the scatter below overwrites the occupied ones
-		for (int q = tid; q < SM::CAP / 2; q += SORT_THREADS)
-			reinterpret_cast<uint32_t *>(sm.id)[q] = SLOT_EMPTY | (SLOT_EMPTY << 16);
-		// ---- sort: classify, histogram
+		// ---- sort: classify (first byte through the bin table), histogram
 		int bin[PER], off[PER];
 #pragma unroll
 		for (int k = 0; k < PER; k++) {
 			const uint32_t id = k * SORT_THREADS + tid;
 			bin[k] = -1;
 			if (id < n_here)
-				bin[k] = S::bin_of(sm.raw[cur][raw_slot(id)], mode_mask, flags);
+				bin[k] = sm.bin_lut[reinterpret_cast<const uint8_t *>(&sm.raw[cur][raw_slot(id)])[0]];
 		}
 #pragma unroll
 		for (int k = 0; k < PER; k++) {
@@ -751,6 +755,13 @@ int height, int wib, uint32_t mode_mask, uint32_t flags, uint32_t post_op, uint3
 		}
 		start -= padded;		// lane NB holds the padded total
 		const int total = __shfl_sync(0xFFFFFFFFu, start, NB);
+		// the padding slots at the end of every bin get the sentinel (one warp per bin); the occupied
+		// slots are written by the scatter, so the array needs no clearing pass
+		if (S::PAD_BINS && warp < NB) {
+			const int c = __shfl_sync(0xFFFFFFFFu, my_count, warp), st = __shfl_sync(0xFFFFFFFFu, start, warp);
+			if (lane < ((-c) & 31))
+				sm.id[st + c + lane] = (uint16_t)SLOT_EMPTY;
+		}
 #pragma unroll
 		for (int k = 0; k < PER; k++) {
 			const int st = __shfl_sync(0xFFFFFFFFu, start, bin[k] & 31);
@@ -827,6 +838,7 @@ int height, int wib, uint32_t mode_mask, uint32_t flags, uint32_t post_op, uint3
 			constexpr int ROW_BYTES = post_words<OW, PC>();	// bytes of one stored pixel row of one block
 			const size_t pitch = (size_t)width * (ROW_BYTES / 4);
 			const uint32_t by0 = tile0 / (uint32_t)wib, bx0 = tile0 - by0 * (uint32_t)wib;	// uniform
+			uint8_t *const row0 = dst + (size_t)by0 * 4 * pitch;
 			// thread t owns row positions p = t, t+512, ... (p = id*CPR + half) for all 4 pixel rows
 #pragma unroll
 			for (int j = 0; j < TB * CPR / SORT_THREADS; j++) {
@@ -837,20 +849,22 @@ int height, int wib, uint32_t mode_mask, uint32_t flags, uint32_t post_op, uint3
 						bx -= (uint32_t)wib;
 						by++;
 					}
-					uint8_t *out = dst + (size_t)by * 4 * pitch + (size_t)bx * ROW_BYTES + half * 16;
-					const int rows = min(4, height - (int)by * 4);
+					uint8_t *out = row0 + (size_t)(by - by0) * 4 * pitch + bx * (uint32_t)ROW_BYTES + half * 16;
+					const int rows = height - (int)by * 4;	// >= 4 except in a clipped last block row
 #pragma unroll
-					for (int r = 0; r < 4; r++)
+					for (int r = 0; r < 4; r++) {
 						if (r < rows) {
 							const uint4 v = sm.out[stage_slot<TB, CHUNKS>(id, r * CPR + half)];
 							if constexpr (PC == PC_PACK3) {		// four RGBX8 pixels -> 12 bytes
-								st_stream_u32(out + r * pitch, prmt(v.x, v.y, 0x4210));
-								st_stream_u32(out + r * pitch + 4, prmt(v.y, v.z, 0x5421));
-								st_stream_u32(out + r * pitch + 8, prmt(v.z, v.w, 0x6542));
+								st_stream_u32(out, prmt(v.x, v.y, 0x4210));
+								st_stream_u32(out + 4, prmt(v.y, v.z, 0x5421));
+								st_stream_u32(out + 8, prmt(v.z, v.w, 0x6542));
 							}
 							else
-								st_stream_v4(out + r * pitch, v.x, v.y, v.z, v.w);
+								st_stream_v4(out, v.x, v.y, v.z, v.w);
 						}
+						out += pitch;
+					}
 				}
 			}
 		}

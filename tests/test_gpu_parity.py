@@ -5,6 +5,9 @@ half-float bit patterns through integer arithmetic, so their tolerance is 0 ULP 
 Also checks the committed golden vectors and the edge cases of the reference API
 (clipping, invalid blocks, flags / mode masks, error messages)."""
 import ctypes as C
+import os
+import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -343,3 +346,14 @@ def test_config_mixed_tiled_reduced(cpu):
         want, _, _ = H.cpu_decode(cpu, fmt, d_blocks.cpu().numpy(), 8000, 4000, linear=False, threads=16)
         assert D.hash_device(d_out.data_ptr(), d_out.numel()) == H.tree_hash(want), fmt
         assert np.array_equal(d_out.cpu().numpy(), want), fmt
+
+
+def test_bc7_flow_kernel():
+    """The alternative BC7 kernel (palette + selectors, barrier-free dataflow; kernels.cu
+    decode_bc7_flow_kernel) is selected per process with DETEXB200_BC7_KERNEL=flow: check it in a
+    child process (tests/bc7_flow_check.py)."""
+    here = os.path.dirname(os.path.abspath(__file__))
+    env = dict(os.environ, DETEXB200_BC7_KERNEL="flow")
+    r = subprocess.run([sys.executable, os.path.join(here, "bc7_flow_check.py")], env=env, capture_output=True,
+                       text=True, timeout=600)
+    assert r.returncode == 0 and r.stdout.strip().startswith("OK"), r.stdout[-2000:] + r.stderr[-4000:]
