@@ -1,9 +1,10 @@
 /*
  * TEST INFRASTRUCTURE ONLY: the BC7 palette decoder of detex_b200/csrc/decode_bptc_palette.cuh
- * compiled for the CPU (host_emu.h) behind a C entry point, for tests/test_emu_bc7.py.
+ * compiled for the CPU (host_emu.h) behind a C entry point, for tests/test_emu_bptc.py.
  */
 #define DETEXB200_HOST_EMU 1
 #include "decode_bptc_palette.cuh"
+#include "decode_bptc_float.cuh"
 #include <cstring>
 
 using namespace detexb200;
@@ -24,6 +25,24 @@ static void tables_init() {
 }
 
 extern "C" {
+
+/* BC6H: n blocks -> n tiles of 16 (SIGNED_)FLOAT_RGBX16 pixels (128 bytes, TILED); valid[i] = 0 and a
+   zero tile for an invalid block */
+int emu_bc6h_decode(const uint8_t *blocks, int n, int is_signed, uint8_t *pixels, uint8_t *valid) {
+	tables_init();
+	for (int i = 0; i < n; i++) {
+		uint4 w;
+		memcpy(&w, blocks + 16 * (size_t)i, 16);
+		uint32_t px[32];
+		const bool ok = is_signed ? decode_bptc_float<true>(w, 0xFFFFFFFFu, 0u, g_tab.packed, px)
+					  : decode_bptc_float<false>(w, 0xFFFFFFFFu, 0u, g_tab.packed, px);
+		if (!ok)
+			memset(px, 0, sizeof px);
+		memcpy(pixels + 128 * (size_t)i, px, 128);
+		valid[i] = ok ? 1 : 0;
+	}
+	return 0;
+}
 
 /* n blocks -> n tiles of 16 RGBA8 pixels (TILED layout); valid[i] = 0 for an invalid block (tile
    zero-filled like texture.c:90-93).  path 0: palette + selectors, path 1: the per-pixel decoder

@@ -2,7 +2,7 @@
  * TEST INFRASTRUCTURE ONLY.  Lets the register-level arithmetic of the CUDA decoders
  * (detex_b200/csrc/decode_*.cuh) compile for the CPU with a plain C++ compiler: the CUDA
  * keywords become no-ops and the handful of intrinsics the decoders use are restated with
- * their PTX semantics.  tests/test_emu_bc7.py runs the result against the oracle, so that a
+ * their PTX semantics.  tests/test_emu_bptc.py runs the result against the oracle, so that a
  * change to a decoder can be checked bit-for-bit in a container without a GPU.  Nothing here
  * is part of, or reachable from, libdetex_b200.so.
  */
@@ -47,3 +47,11 @@ using std::max;
 /* single-thread stand-ins for the launch geometry (table loaders loop over them) */
 struct EmuDim3 { unsigned x, y, z; };
 static const EmuDim3 threadIdx = { 0, 0, 0 }, blockDim = { 1, 1, 1 }, blockIdx = { 0, 0, 0 }, gridDim = { 1, 1, 1 };
+static inline uint32_t __brev(uint32_t v) {
+	uint32_t r = 0;
+	for (int i = 0; i < 32; i++)
+		r |= ((v >> i) & 1u) << (31 - i);
+	return r;
+}
+static inline uint32_t __umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
+static inline int __mulhi(int a, int b) { return (int)(((int64_t)a * b) >> 32); }

@@ -17,13 +17,15 @@ EMU = os.path.join(ROOT, "tests", "emu")
 
 @pytest.fixture(scope="module")
 def emu(tmp_path_factory):
-    so = str(tmp_path_factory.mktemp("emu") / "libemu_bc7.so")
+    so = str(tmp_path_factory.mktemp("emu") / "libemu_bptc.so")
     subprocess.run(["g++", "-std=c++17", "-O1", "-fPIC", "-shared", "-I", EMU, "-I",
-                    os.path.join(ROOT, "detex_b200", "csrc"), "-o", so, os.path.join(EMU, "emu_bc7.cpp")],
+                    os.path.join(ROOT, "detex_b200", "csrc"), "-o", so, os.path.join(EMU, "emu_bptc.cpp")],
                    check=True)
     lib = C.CDLL(so)
     lib.emu_bc7_decode.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.emu_bc7_decode.restype = C.c_int
+    lib.emu_bc6h_decode.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    lib.emu_bc6h_decode.restype = C.c_int
     return lib
 
 
@@ -98,3 +100,32 @@ def test_bc7_emulated_extreme_endpoints(emu, cpu):
     want, _ = _oracle_tiles(cpu, b)
     got, _, _ = _emu_decode(emu, b)
     assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("fmt", ["BPTC_FLOAT", "BPTC_SIGNED_FLOAT"])
+def test_bc6h_emulated_decoder_matches_oracle(emu, cpu, fmt):
+    """BC6H (decode_bptc_float.cuh) on the CPU: uniform blocks (12.5 % invalid), every forced mode,
+    every partition set, extreme payloads"""
+    def check(b):
+        n = b.size // 16
+        got = np.empty(n * 128, dtype=np.uint8)
+        valid = np.empty(n, dtype=np.uint8)
+        b = np.ascontiguousarray(b)
+        assert emu.emu_bc6h_decode(b.ctypes.data, n, int(fmt == "BPTC_SIGNED_FLOAT"), got.ctypes.data, valid.ctypes.data) == 0
+        want, ok, _ = H.cpu_decode(cpu, fmt, b, 4 * n, 4, linear=False)
+        assert np.array_equal(got, want)
+        assert bool(valid.all()) == ok
+    base = H.synth_blocks(fmt, 32768, seed=31)
+    check(base)
+    for m in range(14):
+        check(H.force_modes(fmt, base[:16 * 8192], [m]))
+    blocks = H.force_modes(fmt, H.synth_blocks(fmt, 14 * 32 * 8, seed=37)).reshape(-1, 16)
+    for i in range(blocks.shape[0]):            # partition field at bits 77-81
+        v = int.from_bytes(blocks[i].tobytes(), "little")
+        v = (v & ~(0x1F << 77)) | (((i // 14) % 32) << 77)
+        blocks[i] = np.frombuffer(v.to_bytes(16, "little"), dtype=np.uint8)
+    check(blocks.reshape(-1))
+    rows = []
+    for fill in (0x00, 0xFF, 0xAA, 0x55, 0x0F, 0xF0, 0x7F, 0x80):
+        rows += [bytes([fill] * 16)] * 14
+    check(H.force_modes(fmt, np.frombuffer(b"".join(rows), dtype=np.uint8).copy(), None))
