@@ -12,6 +12,6 @@ from .lib import (  # noqa: F401
     DetexError, load, pixel_size, block_size, native_pixel_format,
     detexDecompressBlock, detexDecompressBlockFormat, detexDecompressTextureLinear,
     detexDecompressTextureTiled, detexConvertPixels, detexGetErrorMessage,
-    decode_device, generate_blocks_device, hash_device, convert_pixels_device, launch_count,
+    decode_device, decode_hdr_device, generate_blocks_device, hash_device, convert_pixels_device, launch_count,
     load_texture_file_to_device, DeviceImage,
 )

@@ -128,10 +128,16 @@ bool is_compressed_format(uint32_t tf) {
 }
 
 // Enqueue decode (+ optional conversion through d_tmp) of a block range on a stream.
+// hdr: the decoded pixels are taken as the _HDR twin of the native format (detexb200DecodeHDRDevice):
+// the conversion applies the calling thread's HDR parameters, and an invalid block leaves the
+// conversion of zero pixels, as the reference's decode + detexConvertPixels sequence does.
+constexpr uint32_t PIXEL_FORMAT_HDR_BIT = 0x4000;	// detex.h:123
 int enqueue_decode(uint32_t tf, const void *d_blocks, int width, int height, int wib, int hib, void *d_pixels,
 uint32_t pf, int layout, uint32_t mode_mask, uint32_t flags, uint32_t *d_invalid, void *d_tmp, uint32_t *d_map,
-cudaStream_t stream) {
-	const uint32_t native = tf & 0xFFFF;
+cudaStream_t stream, bool hdr = false) {
+	const uint32_t native = hdr ? ((tf & 0xFFFF) | PIXEL_FORMAT_HDR_BIT) : (tf & 0xFFFF);
+	if (hdr)
+		d_map = nullptr;
 	DecodeArgs a;
 	a.blocks = d_blocks;
 	a.width = width;
@@ -145,6 +151,10 @@ cudaStream_t stream) {
 	a.post_op = 0;
 	a.post_class = 0;
 	a.invalid_map = nullptr;
+	a.tone_min = 0.0f;
+	a.tone_max = 1.0f;
+	a.tone_hdr = 0;
+	a.tone_zero_target = hdr ? 0u : 1u;
 	cudaError_t e;
 	// Conversions the kernels do while storing: R<->B swap, sign flip, dropping the fourth component,
 	// 16 -> 8 bit.  Repacked tiles need a 32-byte aligned target (else: separate conversion pass).
@@ -152,6 +162,11 @@ cudaStream_t stream) {
 	if (fuse.ok && (fuse.post_class == 0 || (((uintptr_t)d_pixels) & 31u) == 0)) {
 		a.post_op = fuse.post_op;
 		a.post_class = fuse.post_class;
+		if (fuse.tone_hdr) {
+			float gamma;
+			get_hdr_parameters(&gamma, &a.tone_min, &a.tone_max);
+			a.tone_hdr = 1;
+		}
 		a.pixels = d_pixels;
 		if ((e = launch_decode((int)(tf >> 24), a, stream)) != cudaSuccess)
 			return cuda_fail("decode kernel launch", e);
@@ -369,15 +384,15 @@ uint8_t *pixel_buffer, uint32_t pf, bool set_message) {
 // =============================================================================================
 extern "C" {
 
-int detexb200DecodeDevice(uint32_t tf, const void *d_blocks, int width, int height, int wib, int hib,
-void *d_pixels, uint32_t pf, int layout, uint32_t mode_mask, uint32_t flags, uint32_t *d_invalid, void *stream) {
-	if (!validate_decode_args("detexb200DecodeDevice", tf, d_blocks, d_pixels, wib, hib, width, height, layout))
+static int decode_device(const char *who, uint32_t tf, const void *d_blocks, int width, int height, int wib, int hib,
+void *d_pixels, uint32_t pf, int layout, uint32_t mode_mask, uint32_t flags, uint32_t *d_invalid, void *stream, bool hdr) {
+	if (!validate_decode_args(who, tf, d_blocks, d_pixels, wib, hib, width, height, layout))
 		return DETEXB200_EINVAL;
 	if (((uintptr_t)d_blocks & 15u) != 0) {
-		set_error("detexb200DecodeDevice: block array must be 16-byte aligned");
+		set_error("%s: block array must be 16-byte aligned", who);
 		return DETEXB200_EINVAL;
 	}
-	const uint32_t native = tf & 0xFFFF;
+	const uint32_t native = hdr ? ((tf & 0xFFFF) | PIXEL_FORMAT_HDR_BIT) : (tf & 0xFFFF);
 	void *tmp = nullptr;
 	cudaStream_t s = (cudaStream_t)stream;
 	if (pf != native && !convert_supported(native, pf)) {
@@ -386,7 +401,7 @@ void *d_pixels, uint32_t pf, int layout, uint32_t mode_mask, uint32_t flags, uin
 	}
 	const FusedConversion fuse = convert_fused(native, pf);
 	if (fuse.ok && (fuse.post_class == 0 || (((uintptr_t)d_pixels) & 31u) == 0))
-		return enqueue_decode(tf, d_blocks, width, height, wib, hib, d_pixels, pf, layout, mode_mask, flags, d_invalid, nullptr, nullptr, s);
+		return enqueue_decode(tf, d_blocks, width, height, wib, hib, d_pixels, pf, layout, mode_mask, flags, d_invalid, nullptr, nullptr, s, hdr);
 	// Decode + conversion pass, slab by slab through ONE scratch buffer small enough to stay in the
 	// 126 MB L2: the native-format pixels of a slab are read back by the conversion kernel before
 	// they are evicted, so HBM sees the compressed input and the converted output only.
@@ -412,7 +427,7 @@ void *d_pixels, uint32_t pf, int layout, uint32_t mode_mask, uint32_t flags, uin
 			if (slab_h < 0)
 				slab_h = 0;
 			rc = enqueue_decode(tf, (const uint8_t *)d_blocks + (size_t)r0 * wib * bb, width, slab_h, wib, rows,
-				(uint8_t *)d_pixels + (size_t)r0 * 4 * width * ps, pf, layout, mode_mask, flags, d_invalid, tmp, map, s);
+				(uint8_t *)d_pixels + (size_t)r0 * 4 * width * ps, pf, layout, mode_mask, flags, d_invalid, tmp, map, s, hdr);
 		}
 	}
 	else {
@@ -423,10 +438,34 @@ void *d_pixels, uint32_t pf, int layout, uint32_t mode_mask, uint32_t flags, uin
 		for (uint64_t b0 = 0; b0 < n_blocks && rc == DETEXB200_OK; b0 += per_slab) {
 			const uint64_t count = (n_blocks - b0) < per_slab ? (n_blocks - b0) : per_slab;
 			rc = enqueue_decode(tf, (const uint8_t *)d_blocks + b0 * bb, (int)count * 4, 4, (int)count, 1,
-				(uint8_t *)d_pixels + b0 * 16 * ps, pf, layout, mode_mask, flags, d_invalid, tmp, map, s);
+				(uint8_t *)d_pixels + b0 * 16 * ps, pf, layout, mode_mask, flags, d_invalid, tmp, map, s, hdr);
 		}
 	}
 	cudaFreeAsync(tmp, s);
+	return rc;
+}
+
+int detexb200DecodeDevice(uint32_t tf, const void *d_blocks, int width, int height, int wib, int hib,
+void *d_pixels, uint32_t pf, int layout, uint32_t mode_mask, uint32_t flags, uint32_t *d_invalid, void *stream) {
+	return decode_device("detexb200DecodeDevice", tf, d_blocks, width, height, wib, hib, d_pixels, pf, layout, mode_mask,
+		flags, d_invalid, stream, false);
+}
+
+int detexb200DecodeHDRDevice(uint32_t tf, const void *d_blocks, int width, int height, int wib, int hib,
+void *d_pixels, uint32_t pf, int layout, float gamma, float range_min, float range_max, uint32_t *d_invalid,
+void *stream) {
+	const uint32_t native = tf & 0xFFFF;
+	// the formats that have an _HDR twin in the conversion table: FLOAT_RGBX16 (BC6H unsigned)
+	if (!is_compressed_format(tf) || native != 0x2721u) {
+		set_error("detexb200DecodeHDRDevice: texture format 0x%08X does not decode to an HDR pixel format", tf);
+		return DETEXB200_EINVAL;
+	}
+	float g0, lo0, hi0;
+	get_hdr_parameters(&g0, &lo0, &hi0);
+	set_hdr_parameters(gamma, range_min, range_max);
+	const int rc = decode_device("detexb200DecodeHDRDevice", tf, d_blocks, width, height, wib, hib, d_pixels, pf, layout,
+		0xFFFFFFFFu, 0u, d_invalid, stream, true);
+	set_hdr_parameters(g0, lo0, hi0);
 	return rc;
 }
 

@@ -16,6 +16,7 @@
 #include "common.cuh"
 #include "launch.h"
 #include <cstring>
+#include <cstdlib>
 
 namespace detexb200 {
 
@@ -163,12 +164,32 @@ bool convert_supported(uint32_t s, uint32_t d) {
 	return convert_plan(s, d, steps) >= 0;
 }
 
+// ---- HDR parameters (reference hdr.c:26-38: thread-local gamma and range) -----------------------
+struct HdrParams { float gamma, range_min, range_max; };
+static thread_local HdrParams g_hdr = { 1.0f, 0.0f, 1.0f };
+void set_hdr_parameters(float gamma, float range_min, float range_max) { g_hdr = { gamma, range_min, range_max }; }
+void get_hdr_parameters(float *gamma, float *range_min, float *range_max) {
+	*gamma = g_hdr.gamma;
+	*range_min = g_hdr.range_min;
+	*range_max = g_hdr.range_max;
+}
+
 // Which conversions the decode kernels absorb into their store epilogue (kernels.cu, "post op" and
 // "post class"): relabelling steps anywhere, at most one R <-> B swap of four-component pixels, at
 // most one sign flip, and -- last -- at most one step that shrinks the pixel: dropping the fourth
 // component, or narrowing one / two 16-bit components to 8 bits.
+// BC6H's way to 8-bit pixels is a class of its own (tone.cuh): FLOAT_RGBX16[_HDR] -> RGBX16 -> RGBX8,
+// after which relabelling, one R <-> B swap and dropping X may still follow.  With the HDR source
+// format the range parameters of the calling thread apply; gamma other than 1 is not fused.
+// DETEXB200_TONE_FUSION=0 in the environment sends the BC6H -> 8-bit targets through the separate
+// conversion pass instead (A/B measurements).
+static bool tone_fusion() {
+	static const bool v = [] { const char *e = getenv("DETEXB200_TONE_FUSION"); return !(e && e[0] == '0'); }();
+	return v;
+}
+
 FusedConversion convert_fused(uint32_t s, uint32_t d) {
-	FusedConversion f = { false, 0u, 0 };
+	FusedConversion f = { false, 0u, 0, false };
 	if (s == d) {
 		f.ok = true;
 		return f;
@@ -177,12 +198,37 @@ FusedConversion convert_fused(uint32_t s, uint32_t d) {
 	const int n = convert_plan(s, d, steps);
 	if (n <= 0)
 		return f;
-	bool shrunk = false;
+	bool shrunk = false, toned = false;
 	for (int i = 0; i < n; i++) {
 		const TableEntry &e = conversion_table[steps[i]];
 		const int ps_in = pixel_bytes(e.source), ps_out = pixel_bytes(e.target), cs = component_bytes(e.source);
+		if (toned) {					// on RGBX8 pixels, after the tone step
+			if (e.op == ST_KEEP && ps_in == ps_out)
+				continue;
+			if (e.op == ST_SWAP_RB && f.post_class == 3 && !(f.post_op & 1u)) {
+				f.post_op |= 1u;
+				continue;
+			}
+			if (e.op == ST_KEEP && e.source == PF_RGBX8 && e.target == PF_RGB8 && f.post_class == 3) {
+				f.post_class = 4;
+				continue;
+			}
+			return f;
+		}
 		if (shrunk)
 			return f;				// nothing may follow the size change
+		if ((e.op == ST_HALF_TO_INT || e.op == ST_HALF_HDR_TO_INT) && e.target == PF_RGBX16 && f.post_op == 0u && tone_fusion() &&
+		    i + 1 < n && conversion_table[steps[i + 1]].op == ST_NARROW && conversion_table[steps[i + 1]].target == PF_RGBX8) {
+			if (e.op == ST_HALF_HDR_TO_INT) {
+				if (g_hdr.gamma != 1.0f)
+					return f;
+				f.tone_hdr = true;
+			}
+			f.post_class = 3;
+			toned = true;
+			i++;
+			continue;
+		}
 		if (e.op == ST_KEEP && ps_in == ps_out)
 			continue;
 		if (e.op == ST_SWAP_RB && ps_in / cs == 4 && !(f.post_op & 1u)) {
@@ -208,11 +254,6 @@ FusedConversion convert_fused(uint32_t s, uint32_t d) {
 	f.ok = true;
 	return f;
 }
-
-// ---- HDR parameters (reference hdr.c:26-38: thread-local gamma and range) -----------------------
-struct HdrParams { float gamma, range_min, range_max; };
-static thread_local HdrParams g_hdr = { 1.0f, 0.0f, 1.0f };
-void set_hdr_parameters(float gamma, float range_min, float range_max) { g_hdr = { gamma, range_min, range_max }; }
 
 // ---- device side ---------------------------------------------------------------------------------
 struct ConvertProgram {

@@ -26,6 +26,7 @@
 #include "decode_bptc.cuh"
 #include "decode_bptc_palette.cuh"
 #include "decode_bptc_float.cuh"
+#include "tone.cuh"
 #include "launch.h"
 
 namespace detexb200 {
@@ -96,9 +97,14 @@ uint32_t mode_mask, uint32_t flags, const BptcTables *tab, uint32_t (&px)[Format
 //     PC_PACK3      drop the fourth component: RGBX8/RGBA8 -> RGB8 (convert.c:671-690),
 //                   FLOAT_RGBX16 -> FLOAT_RGB16 (convert.c:700-716);
 //     PC_NARROW     16-bit -> 8-bit components (v + 127) * 255 / 65535: R16 -> R8, RG16 -> RG8
-//                   (convert.c:263-290).
+//                   (convert.c:263-290);
+//     PC_TONE8      BC6H only: half -> 16-bit integer (optionally rescaled by the HDR range) -> 8 bit,
+//                   FLOAT_RGBX16 -> RGBX8 / RGBA8 (tone.cuh); POST_SWAP_RB then acts
+//                   on the 8-bit pixels (-> BGRX8 / BGRA8);
+//     PC_TONE8_PACK3  the same followed by dropping the fourth component (-> RGB8).
 constexpr uint32_t POST_NONE = 0, POST_SWAP_RB = 1, POST_FLIP16 = 2, POST_FLIP8 = 4;
-constexpr int PC_NATIVE = 0, PC_PACK3 = 1, PC_NARROW = 2;
+constexpr int PC_NATIVE = 0, PC_PACK3 = 1, PC_NARROW = 2, PC_TONE8 = 3, PC_TONE8_PACK3 = 4;
+constexpr bool is_tone_class(int pc) { return pc == PC_TONE8 || pc == PC_TONE8_PACK3; }
 
 template <int OW>
 __device__ __forceinline__ void apply_post_op(uint32_t (&px)[OW], uint32_t post_op) {
@@ -128,7 +134,9 @@ __device__ __forceinline__ void apply_post_op(uint32_t (&px)[OW], uint32_t post_
 }
 
 // words per decoded tile after the post class
-template <int OW, int PC> constexpr int post_words() { return PC == PC_PACK3 ? OW * 3 / 4 : (PC == PC_NARROW ? OW / 2 : OW); }
+template <int OW, int PC> constexpr int post_words() {
+	return PC == PC_PACK3 ? OW * 3 / 4 : (PC == PC_NARROW || PC == PC_TONE8 ? OW / 2 : (PC == PC_TONE8_PACK3 ? OW * 3 / 8 : OW));
+}
 // which (format, class) pairs exist: PACK3 for the four-component 8-bit formats and BC6H unsigned,
 // NARROW for the 16-bit one- and two-component formats
 template <int F, int PC> constexpr bool post_class_valid() {
@@ -137,6 +145,8 @@ template <int F, int PC> constexpr bool post_class_valid() {
 		return true;
 	if (PC == PC_PACK3)
 		return (OW == 16 && F != F_EAC_RG11 && F != F_EAC_SIGNED_RG11 && F != F_SIGNED_RGTC2) || F == F_BPTC_FLOAT;
+	if (is_tone_class(PC))
+		return F == F_BPTC_FLOAT;
 	return F == F_EAC_R11 || F == F_EAC_SIGNED_R11 || F == F_EAC_RG11 || F == F_EAC_SIGNED_RG11 ||
 		F == F_SIGNED_RGTC1 || F == F_SIGNED_RGTC2;
 }
@@ -179,17 +189,55 @@ __device__ __forceinline__ void repack(const uint32_t (&px)[OW], uint32_t (&q)[p
 	}
 }
 
+// What the tone classes need besides the pixels: the (uniform) tone parameters and whether the block
+// was valid -- an invalid block is zero in the target format or the conversion of zero pixels,
+// ToneArgs::zero_target.  Empty for every other class.
+template <int PC> struct EmitCtx { __device__ __forceinline__ EmitCtx(const ToneArgs &) {} };
+struct EmitCtxTone {
+	Tone tone;
+	bool zero_target;
+	__device__ __forceinline__ EmitCtxTone(const ToneArgs &a) : tone(tone_setup(a)), zero_target(a.zero_target != 0u) {}
+};
+template <> struct EmitCtx<PC_TONE8> : EmitCtxTone { using EmitCtxTone::EmitCtxTone; };
+template <> struct EmitCtx<PC_TONE8_PACK3> : EmitCtxTone { using EmitCtxTone::EmitCtxTone; };
+
+// 16 FLOAT_RGBX16 pixels -> 16 RGBX8 / BGRX8 pixels (tone classes): tone map, invalid rule, swap
+template <int PC>
+__device__ __forceinline__ void tone_tile(const uint32_t (&px)[32], uint32_t (&t)[16], uint32_t post_op, const EmitCtx<PC> &ctx, bool ok) {
+	tone8_tile(px, t, ctx.tone);
+	if (!ok && ctx.zero_target) {
+#pragma unroll
+		for (int k = 0; k < 16; k++)
+			t[k] = 0u;
+	}
+	apply_post_op<16>(t, post_op & POST_SWAP_RB);
+}
+
 // post_op, then hand the words that go to memory to store(words): the decoded array itself for
-// the native class, a repacked one otherwise.
+// the native class, a repacked one otherwise.  ok: the block was valid (its pixels are already
+// filled with invalid_fill() otherwise).
 template <int PC, int OW, typename Store>
-__device__ __forceinline__ void emit(uint32_t (&px)[OW], uint32_t post_op, Store &&store) {
-	apply_post_op<OW>(px, post_op);
-	if constexpr (PC == PC_NATIVE)
-		store(px);
+__device__ __forceinline__ void emit(uint32_t (&px)[OW], uint32_t post_op, const EmitCtx<PC> &ctx, bool ok, Store &&store) {
+	if constexpr (is_tone_class(PC)) {
+		uint32_t t[16];
+		tone_tile<PC>(px, t, post_op, ctx, ok);
+		if constexpr (PC == PC_TONE8)
+			store(t);
+		else {
+			uint32_t q[12];
+			repack<PC_PACK3, 16>(t, q);
+			store(q);
+		}
+	}
 	else {
-		uint32_t q[post_words<OW, PC>()];
-		repack<PC, OW>(px, q);
-		store(q);
+		apply_post_op<OW>(px, post_op);
+		if constexpr (PC == PC_NATIVE)
+			store(px);
+		else {
+			uint32_t q[post_words<OW, PC>()];
+			repack<PC, OW>(px, q);
+			store(q);
+		}
 	}
 }
 
@@ -326,9 +374,10 @@ __device__ __forceinline__ void store_linear_rows(uint8_t *dst, size_t pitch, in
 template <int F, bool DIRECT, int PC>
 __global__ void __launch_bounds__(CTA_THREADS, min_ctas<F>())
 decode_tiled_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, uint32_t n_blocks,
-uint32_t mode_mask, uint32_t flags, uint32_t post_op, uint32_t *invalid_flag, uint32_t *invalid_map) {
+uint32_t mode_mask, uint32_t flags, uint32_t post_op, uint32_t *invalid_flag, uint32_t *invalid_map, ToneArgs tone_args) {
 	using T = FormatTraits<F>;
 	using D = DeferTraits<F>;
+	const EmitCtx<PC> ctx(tone_args);
 	constexpr int BW = T::BLOCK_WORDS, OW = T::OUT_WORDS, OWO = post_words<OW, PC>(), CHUNKS = OWO / 4;
 	static_assert(PC == PC_NATIVE || DIRECT, "repacked tiles are stored directly");
 	__shared__ BptcTables tables;
@@ -372,7 +421,7 @@ uint32_t mode_mask, uint32_t flags, uint32_t post_op, uint32_t *invalid_flag, ui
 					px[w] = invalid_fill(post_op);
 			}
 			const unsigned rare_mask = D::ENABLED ? __ballot_sync(0xFFFFFFFFu, rare) : 0u;
-			emit<PC>(px, post_op, [&](auto &w) {
+			emit<PC>(px, post_op, ctx, ok, [&](auto &w) {
 				if (tile >= n_tiles)
 					return;
 				uint8_t *tile_out = dst + (size_t)first * (OWO * 4);
@@ -443,7 +492,7 @@ uint32_t mode_mask, uint32_t flags, uint32_t post_op, uint32_t *invalid_flag, ui
 					for (int k = 0; k < OW; k++)
 						qx[k] = invalid_fill(post_op);
 				}
-				emit<PC>(qx, post_op, [&](auto &w) {
+				emit<PC>(qx, post_op, ctx, true, [&](auto &w) {	// (deferral exists for the ETC2 family only)
 					uint8_t *out = dst + (size_t)j * (OWO * 4);
 #pragma unroll
 					for (int c = 0; c < CHUNKS; c++)
@@ -465,9 +514,11 @@ uint32_t mode_mask, uint32_t flags, uint32_t post_op, uint32_t *invalid_flag, ui
 template <int F, int PC>
 __global__ void __launch_bounds__(CTA_THREADS, min_ctas<F>())
 decode_linear_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, int width, int height,
-int wib, int hib, uint32_t mode_mask, uint32_t flags, uint32_t post_op, uint32_t *invalid_flag, uint32_t *invalid_map) {
+int wib, int hib, uint32_t mode_mask, uint32_t flags, uint32_t post_op, uint32_t *invalid_flag, uint32_t *invalid_map,
+ToneArgs tone_args) {
 	using T = FormatTraits<F>;
 	using D = DeferTraits<F>;
+	const EmitCtx<PC> ctx(tone_args);
 	constexpr int BW = T::BLOCK_WORDS, OW = T::OUT_WORDS, ROW_BYTES = post_words<OW, PC>();
 	__shared__ BptcTables tables;
 	__shared__ uint32_t queue[D::ENABLED ? CTA_THREADS * DEFER_ITERS : 1];
@@ -502,14 +553,15 @@ int wib, int hib, uint32_t mode_mask, uint32_t flags, uint32_t post_op, uint32_t
 					queue[atomicAdd(&queue_n, 1)] = (uint32_t)by * (uint32_t)wib + (uint32_t)bx;
 				else {
 					uint32_t px[OW];
-					if (!decode_block<F, D::ENABLED ? ETC_PATHS_NO_PLANAR : ETC_PATHS_ALL>(blk, mode_mask, flags, &tables, px)) {
+					const bool ok = decode_block<F, D::ENABLED ? ETC_PATHS_NO_PLANAR : ETC_PATHS_ALL>(blk, mode_mask, flags, &tables, px);
+					if (!ok) {
 						bad = true;
 						mark_invalid(invalid_map, (uint32_t)by * (uint32_t)wib + (uint32_t)bx);
 #pragma unroll
 						for (int j = 0; j < OW; j++)
 							px[j] = invalid_fill(post_op);
 					}
-					emit<PC>(px, post_op, [&](auto &w) { store_linear_rows(dst, pitch, bx, by, height, w); });
+					emit<PC>(px, post_op, ctx, ok, [&](auto &w) { store_linear_rows(dst, pitch, bx, by, height, w); });
 				}
 			}
 		}
@@ -529,7 +581,7 @@ int wib, int hib, uint32_t mode_mask, uint32_t flags, uint32_t post_op, uint32_t
 					for (int jj = 0; jj < OW; jj++)
 						qp[jj] = invalid_fill(post_op);
 				}
-				emit<PC>(qp, post_op, [&](auto &w) { store_linear_rows(dst, pitch, qx_, qy, height, w); });
+				emit<PC>(qp, post_op, ctx, true, [&](auto &w) { store_linear_rows(dst, pitch, qx_, qy, height, w); });
 			}
 			__syncthreads();
 			if (tid == 0)
@@ -546,8 +598,10 @@ int wib, int hib, uint32_t mode_mask, uint32_t flags, uint32_t post_op, uint32_t
 template <int F, int PC>
 __global__ void __launch_bounds__(CTA_THREADS)
 decode_linear_clipped_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, int width, int height,
-int wib, int hib, uint32_t mode_mask, uint32_t flags, uint32_t post_op, uint32_t *invalid_flag, uint32_t *invalid_map) {
+int wib, int hib, uint32_t mode_mask, uint32_t flags, uint32_t post_op, uint32_t *invalid_flag, uint32_t *invalid_map,
+ToneArgs tone_args) {
 	using T = FormatTraits<F>;
+	const EmitCtx<PC> ctx(tone_args);
 	constexpr int BW = T::BLOCK_WORDS, OW = T::OUT_WORDS, PS = post_words<OW, PC>() / 4;	// PS = bytes per stored pixel
 	__shared__ BptcTables tables;
 	if constexpr (T::USES_TABLES) {
@@ -560,7 +614,8 @@ int wib, int hib, uint32_t mode_mask, uint32_t flags, uint32_t post_op, uint32_t
 		const int by = (int)(i / (uint32_t)wib), bx = (int)(i % (uint32_t)wib);
 		const auto blk = BlockReg<BW>::load(src + (size_t)i * (BW * 4));
 		uint32_t px[OW];
-		if (!decode_block<F>(blk, mode_mask, flags, &tables, px)) {
+		const bool ok = decode_block<F>(blk, mode_mask, flags, &tables, px);
+		if (!ok) {
 			bad = true;
 			mark_invalid(invalid_map, i);
 #pragma unroll
@@ -568,7 +623,7 @@ int wib, int hib, uint32_t mode_mask, uint32_t flags, uint32_t post_op, uint32_t
 				px[k] = invalid_fill(post_op);
 		}
 		const int rows = min(4, height - by * 4), cols = min(4, width - bx * 4);
-		emit<PC>(px, post_op, [&](auto &w) {
+		emit<PC>(px, post_op, ctx, ok, [&](auto &w) {
 #pragma unroll
 			for (int r = 0; r < 4; r++)
 #pragma unroll
@@ -628,7 +683,14 @@ struct SortTraitsBc6h {
 template <> struct SortTraits<F_BPTC_FLOAT> : SortTraitsBc6h {};
 template <> struct SortTraits<F_BPTC_SIGNED_FLOAT> : SortTraitsBc6h {};
 
-template <int F> constexpr int sort_tile() { return SortTraits<F>::TILE_BLOCKS; }
+// A staged tile of the tone classes is 16 RGBX8 / BGRX8 words per block (the toned pixels are what is
+// parked); every other class stages the decoder's native tile.  A kernel that stages needs 64 bytes of
+// shared memory per block on top of the double-buffered input, which fits two CTAs per SM with tiles
+// of 1024 blocks.
+template <int F, int PC> constexpr int stage_words() { return is_tone_class(PC) ? 16 : FormatTraits<F>::OUT_WORDS; }
+template <int F, bool STAGE> constexpr int sort_tile() {
+	return (STAGE && SortTraits<F>::TILE_BLOCKS > 1024) ? 1024 : SortTraits<F>::TILE_BLOCKS;
+}
 
 constexpr int SORT_THREADS = 512, SORT_WARPS = SORT_THREADS / 32;
 constexpr uint32_t SLOT_EMPTY = 0xFFFFu;		// sorted slot that is bin padding
@@ -647,11 +709,11 @@ __device__ __forceinline__ uint32_t stage_slot(uint32_t id, uint32_t c) {
 	return c * TB + (id ^ (((id >> 3) ^ fc) & 7u));
 }
 
-template <int F>
+template <int F, int PC, bool STAGE>
 struct SortedSmem {
-	static constexpr int TB = sort_tile<F>(), NB = SortTraits<F>::NUM_BINS, CAP = TB + NB * 32;
-	static constexpr int CHUNKS = FormatTraits<F>::OUT_WORDS / 4;	// 16-byte chunks per decoded tile
-	uint4 out[SortTraits<F>::STAGE_OUTPUT ? TB * CHUNKS : 1];	// staged pixels (stage_slot layout)
+	static constexpr int TB = sort_tile<F, STAGE>(), NB = SortTraits<F>::NUM_BINS, CAP = TB + NB * 32;
+	static constexpr int CHUNKS = stage_words<F, PC>() / 4;		// 16-byte chunks per staged tile
+	uint4 out[(SortTraits<F>::STAGE_OUTPUT || STAGE) ? TB * CHUNKS : 1];	// staged pixels (stage_slot layout)
 	uint4 raw[2][TB];		// double-buffered compressed tile, filled by cp.async
 	uint16_t id[CAP];		// tile-local block index in each sorted slot
 	int count[2][16];		// per-mode histogram, double-buffered across tiles
@@ -681,10 +743,12 @@ __device__ __forceinline__ uint32_t raw_slot(uint32_t id) { return id ^ ((id >> 
 template <int F, int LAYOUT, bool STAGE, int PC>
 __global__ void __launch_bounds__(SORT_THREADS, 2)
 decode_sorted_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, uint32_t n_blocks, int width,
-int height, int wib, uint32_t mode_mask, uint32_t flags, uint32_t post_op, uint32_t *invalid_flag, uint32_t *invalid_map) {
+int height, int wib, uint32_t mode_mask, uint32_t flags, uint32_t post_op, uint32_t *invalid_flag, uint32_t *invalid_map,
+ToneArgs tone_args) {
 	using T = FormatTraits<F>;
 	using S = SortTraits<F>;
-	using SM = SortedSmem<F>;
+	using SM = SortedSmem<F, PC, STAGE>;
+	const EmitCtx<PC> ctx(tone_args);
 	constexpr int OW = T::OUT_WORDS, NB = S::NUM_BINS, TB = SM::TB, PER = TB / SORT_THREADS, CHUNKS = SM::CHUNKS;
 	constexpr int CPR = CHUNKS / 4;			// 16-byte chunks per pixel row of one block
 	static_assert(T::BLOCK_WORDS == 4, "sorted kernel handles 16-byte blocks");
@@ -781,14 +845,23 @@ int height, int wib, uint32_t mode_mask, uint32_t flags, uint32_t post_op, uint3
 			if (live) {
 				const uint4 w = sm.raw[cur][raw_slot(id)];
 				uint32_t px[OW];
-				if (!decode_block<F>(w, mode_mask, flags, &sm.tables, px)) {
+				const bool ok = decode_block<F>(w, mode_mask, flags, &sm.tables, px);
+				if (!ok) {
 					bad = true;
 					mark_invalid(invalid_map, tile0 + id);
 #pragma unroll
 					for (int k = 0; k < OW; k++)
 						px[k] = invalid_fill(post_op);
 				}
-				if constexpr (STAGE) {
+				if constexpr (STAGE && is_tone_class(PC)) {
+					// the toned 8-bit pixels are what is staged; dropping X is left to the copy-out
+					uint32_t t[16];
+					tone_tile<PC>(px, t, post_op, ctx, ok);
+#pragma unroll
+					for (int c = 0; c < 4; c++)
+						sm.out[stage_slot<TB, 4>(id, c)] = make_uint4(t[4 * c], t[4 * c + 1], t[4 * c + 2], t[4 * c + 3]);
+				}
+				else if constexpr (STAGE) {
 					// staged in the native layout; a post class is applied by the copy-out below
 					apply_post_op<OW>(px, post_op);
 #pragma unroll
@@ -796,7 +869,7 @@ int height, int wib, uint32_t mode_mask, uint32_t flags, uint32_t post_op, uint3
 						sm.out[stage_slot<TB, CHUNKS>(id, c)] = make_uint4(px[4 * c], px[4 * c + 1], px[4 * c + 2], px[4 * c + 3]);
 				}
 				else {
-					emit<PC>(px, post_op, [&](auto &w) {
+					emit<PC>(px, post_op, ctx, ok, [&](auto &w) {
 						constexpr int OWO = post_words<OW, PC>(), CH = OWO / 4;
 						if (LAYOUT == LAYOUT_TILED) {
 							uint8_t *out = dst + (size_t)(tile0 + id) * (OWO * 4);
@@ -825,10 +898,11 @@ int height, int wib, uint32_t mode_mask, uint32_t flags, uint32_t post_op, uint3
 			continue;		// direct stores: the barrier at the loop top is enough
 		__syncthreads();
 		// ---- store
-		static_assert(!STAGE || PC == PC_NATIVE || (PC == PC_PACK3 && LAYOUT == LAYOUT_LINEAR && OW == 16),
-			"staged copy-out repacks RGB8 rows only");
+		constexpr bool PACK_ROWS = (PC == PC_PACK3 && OW == 16) || PC == PC_TONE8_PACK3;	// RGBX8 stage -> RGB8 rows
+		static_assert(!STAGE || PC == PC_NATIVE || (PC == PC_TONE8 && LAYOUT == LAYOUT_LINEAR) ||
+			(PACK_ROWS && LAYOUT == LAYOUT_LINEAR), "staged copy-out repacks RGB8 rows only");
 		if (LAYOUT == LAYOUT_TILED) {
-			uint8_t *out = dst + (size_t)tile0 * (OW * 4);
+			uint8_t *out = dst + (size_t)tile0 * (CHUNKS * 16);
 			for (uint32_t q = tid; q < n_here * CHUNKS; q += SORT_THREADS) {
 				const uint4 v = sm.out[stage_slot<TB, CHUNKS>(q / CHUNKS, q % CHUNKS)];
 				st_stream_v4(out + (size_t)q * 16, v.x, v.y, v.z, v.w);
@@ -855,7 +929,7 @@ int height, int wib, uint32_t mode_mask, uint32_t flags, uint32_t post_op, uint3
 					for (int r = 0; r < 4; r++) {
 						if (r < rows) {
 							const uint4 v = sm.out[stage_slot<TB, CHUNKS>(id, r * CPR + half)];
-							if constexpr (PC == PC_PACK3) {		// four RGBX8 pixels -> 12 bytes
+							if constexpr (PACK_ROWS) {		// four RGBX8 pixels -> 12 bytes
 								st_stream_u32(out, prmt(v.x, v.y, 0x4210));
 								st_stream_u32(out + 4, prmt(v.y, v.z, 0x5421));
 								st_stream_u32(out + 8, prmt(v.z, v.w, 0x6542));
@@ -1252,10 +1326,22 @@ static bool tiled_direct() {
 
 // One instantiation of the sorted kernel: opt in to > 48 KiB of dynamic shared memory once per
 // device, then launch.
+static ToneArgs tone_args_of(const DecodeArgs &a) {
+	ToneArgs t;
+	t.range_min = a.tone_min;
+	t.range_max = a.tone_max;
+	t.hdr = a.tone_hdr;
+	t.zero_target = a.tone_zero_target;
+	return t;
+}
+
 template <int F, int LAYOUT, bool STAGE, int PC>
-static void launch_sorted(unsigned grid, const uint8_t *src, uint8_t *dst, uint32_t n_blocks, const DecodeArgs &a,
-cudaStream_t stream) {
-	const size_t smem = sizeof(SortedSmem<F>);
+static void launch_sorted(const uint8_t *src, uint8_t *dst, uint32_t n_blocks, const DecodeArgs &a, cudaStream_t stream) {
+	using SM = SortedSmem<F, PC, STAGE>;
+	const size_t smem = sizeof(SM);
+	const uint64_t tiles = ((uint64_t)n_blocks + SM::TB - 1) / SM::TB;
+	const uint64_t resident = (uint64_t)sm_count() * 2;		// persistent: two CTAs per SM
+	const unsigned grid = (unsigned)(tiles < resident ? tiles : resident);
 	static std::atomic<bool> configured[64];
 	int dev = 0;
 	cudaGetDevice(&dev);
@@ -1264,7 +1350,7 @@ cudaStream_t stream) {
 		configured[dev & 63].store(true);
 	}
 	decode_sorted_kernel<F, LAYOUT, STAGE, PC><<<grid, SORT_THREADS, smem, stream>>>(src, dst, n_blocks,
-		a.width, a.height, a.wib, a.mode_mask, a.flags, a.post_op, a.invalid, a.invalid_map);
+		a.width, a.height, a.wib, a.mode_mask, a.flags, a.post_op, a.invalid, a.invalid_map, tone_args_of(a));
 }
 
 // DETEXB200_BC7_KERNEL=flow selects the palette-staged dataflow kernel for BC7 instead of
@@ -1305,11 +1391,8 @@ static cudaError_t launch_format(const DecodeArgs &a, cudaStream_t stream) {
 	if constexpr (SortTraits<F>::ENABLED) {
 		// multi-mode formats: mode-sorted kernel whenever there is enough work to sort
 		const bool linear_ok = a.layout == LAYOUT_TILED || (a.width % 4 == 0);
-		constexpr int TB = sort_tile<F>();
+		constexpr int TB = SortTraits<F>::TILE_BLOCKS;
 		if (n_blocks >= (uint64_t)TB && aligned_out && linear_ok && !force_unsorted()) {
-			const uint64_t tiles = (n_blocks + TB - 1) / TB;
-			const uint64_t resident = (uint64_t)sm_count() * 2;		// persistent: two CTAs per SM
-			const unsigned grid = (unsigned)(tiles < resident ? tiles : resident);
 			if constexpr (F == F_BPTC && (PC == PC_NATIVE || PC == PC_PACK3)) {
 				if (bc7_flow_kernel()) {
 					if (a.layout == LAYOUT_TILED)
@@ -1320,13 +1403,15 @@ static cudaError_t launch_format(const DecodeArgs &a, cudaStream_t stream) {
 					return cudaGetLastError();
 				}
 			}
+			// LINEAR rows of 16 bytes or less per block are half sectors when written by lanes in sorted
+			// order: those tiles (BC7, the toned BC6H classes) are staged and copied out in image order
 			constexpr bool ST = SortTraits<F>::STAGE_OUTPUT;
 			if (a.layout == LAYOUT_TILED && (PC != PC_NATIVE || (tiled_direct() && aligned32)))
-				launch_sorted<F, LAYOUT_TILED, false, PC>(grid, src, dst, (uint32_t)n_blocks, a, stream);
+				launch_sorted<F, LAYOUT_TILED, false, PC>(src, dst, (uint32_t)n_blocks, a, stream);
 			else if (a.layout == LAYOUT_TILED)
-				launch_sorted<F, LAYOUT_TILED, ST, PC_NATIVE>(grid, src, dst, (uint32_t)n_blocks, a, stream);
+				launch_sorted<F, LAYOUT_TILED, ST, PC_NATIVE>(src, dst, (uint32_t)n_blocks, a, stream);
 			else
-				launch_sorted<F, LAYOUT_LINEAR, ST, PC>(grid, src, dst, (uint32_t)n_blocks, a, stream);
+				launch_sorted<F, LAYOUT_LINEAR, ST || is_tone_class(PC), PC>(src, dst, (uint32_t)n_blocks, a, stream);
 			count_launch();
 			return cudaGetLastError();
 		}
@@ -1343,14 +1428,14 @@ static cudaError_t launch_format(const DecodeArgs &a, cudaStream_t stream) {
 		if constexpr (PC != PC_NATIVE || CAN_DIRECT) {
 			if (PC != PC_NATIVE || (aligned32 && tiled_direct())) {
 				decode_tiled_kernel<F, true, PC><<<grid, CTA_THREADS, 0, stream>>>(src, dst, (uint32_t)n_blocks,
-					a.mode_mask, a.flags, a.post_op, a.invalid, a.invalid_map);
+					a.mode_mask, a.flags, a.post_op, a.invalid, a.invalid_map, tone_args_of(a));
 				launched = true;
 			}
 		}
 		if constexpr (PC == PC_NATIVE) {
 			if (!launched)
 				decode_tiled_kernel<F, false, PC_NATIVE><<<grid, CTA_THREADS, 0, stream>>>(src, dst, (uint32_t)n_blocks,
-					a.mode_mask, a.flags, a.post_op, a.invalid, a.invalid_map);
+					a.mode_mask, a.flags, a.post_op, a.invalid, a.invalid_map, tone_args_of(a));
 		}
 	}
 	else {
@@ -1367,14 +1452,14 @@ static cudaError_t launch_format(const DecodeArgs &a, cudaStream_t stream) {
 				gy = 65535u;
 			dim3 grid((unsigned)((a.wib + tx - 1) / tx), gy);
 			decode_linear_kernel<F, PC><<<grid, block, 0, stream>>>(src, dst, a.width, a.height, a.wib, a.hib,
-				a.mode_mask, a.flags, a.post_op, a.invalid, a.invalid_map);
+				a.mode_mask, a.flags, a.post_op, a.invalid, a.invalid_map, tone_args_of(a));
 		}
 		else {
 			const uint64_t want = (n_blocks + CTA_THREADS - 1) / CTA_THREADS;
 			const uint64_t cap = (uint64_t)sm_count() * 8 * 16;
 			const unsigned grid = (unsigned)(want < cap ? want : cap);
 			decode_linear_clipped_kernel<F, PC><<<grid, CTA_THREADS, 0, stream>>>(src, dst, a.width, a.height,
-				a.wib, a.hib, a.mode_mask, a.flags, a.post_op, a.invalid, a.invalid_map);
+				a.wib, a.hib, a.mode_mask, a.flags, a.post_op, a.invalid, a.invalid_map, tone_args_of(a));
 		}
 	}
 	count_launch();
@@ -1393,6 +1478,12 @@ static cudaError_t launch_classes(const DecodeArgs &a, cudaStream_t stream) {
 	if constexpr (post_class_valid<F, PC_NARROW>()) {
 		if (a.post_class == PC_NARROW)
 			return launch_format<F, PC_NARROW>(a, stream);
+	}
+	if constexpr (post_class_valid<F, PC_TONE8>()) {
+		if (a.post_class == PC_TONE8)
+			return launch_format<F, PC_TONE8>(a, stream);
+		if (a.post_class == PC_TONE8_PACK3)
+			return launch_format<F, PC_TONE8_PACK3>(a, stream);
 	}
 	return cudaErrorInvalidValue;
 }

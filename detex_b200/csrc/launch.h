@@ -15,7 +15,13 @@ struct DecodeArgs {
 	int layout;
 	uint32_t mode_mask, flags;
 	uint32_t post_op;	// bit 0: R<->B swap, bit 1: signed<->unsigned 16-bit components, fused into the store
-	int post_class;		// 0 native tile size, 1 drop the fourth component, 2 16-bit -> 8-bit components
+	int post_class;		// 0 native tile size, 1 drop the fourth component, 2 16-bit -> 8-bit components,
+				// 3 BC6H half -> 8-bit RGBX8 (tone.cuh), 4 the same -> RGB8
+	// tone classes only: HDR range (tone_hdr = 1: rescale by [tone_min, tone_max] first, hdr.c:119-141;
+	// 0: plain normalised half, half-float.c:304-312) and what an invalid block leaves behind
+	// (1: zeros in the target format, texture.c:90-93; 0: the conversion of zero pixels)
+	float tone_min, tone_max;
+	uint32_t tone_hdr, tone_zero_target;
 	uint32_t *invalid;	// device flag word or nullptr
 	uint32_t *invalid_map;	// device bitmap, one bit per block, set for invalid blocks; or nullptr
 };
@@ -30,9 +36,11 @@ int convert_plan(uint32_t source_pixel_format, uint32_t target_pixel_format, int
 int conversion_table_size();
 void conversion_table_entry(int index, uint32_t *source_pixel_format, uint32_t *target_pixel_format);
 void set_hdr_parameters(float gamma, float range_min, float range_max);	// thread-local, hdr.c:26-38
+void get_hdr_parameters(float *gamma, float *range_min, float *range_max);
 bool convert_supported(uint32_t source_pixel_format, uint32_t target_pixel_format);
 // A conversion the decode kernels can do while storing: post_op / post_class as in DecodeArgs.
-struct FusedConversion { bool ok; uint32_t post_op; int post_class; };
+// tone_hdr: the tone classes take the HDR range parameters of the calling thread.
+struct FusedConversion { bool ok; uint32_t post_op; int post_class; bool tone_hdr; };
 FusedConversion convert_fused(uint32_t source_pixel_format, uint32_t target_pixel_format);
 // Clear the target pixels of the blocks marked in invalid_map (after a separate conversion pass).
 cudaError_t launch_zero_invalid(const uint32_t *invalid_map, void *pixels, int width, int height, int wib, int hib,

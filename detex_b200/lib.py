@@ -92,6 +92,10 @@ def load():
                                           C.c_void_p, C.c_uint32, C.c_int, C.c_uint32, C.c_uint32,
                                           C.c_void_p, C.c_void_p]
     lib.detexb200DecodeDevice.restype = C.c_int
+    lib.detexb200DecodeHDRDevice.argtypes = [C.c_uint32, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                             C.c_void_p, C.c_uint32, C.c_int, C.c_float, C.c_float, C.c_float,
+                                             C.c_void_p, C.c_void_p]
+    lib.detexb200DecodeHDRDevice.restype = C.c_int
     lib.detexb200ConvertPixelsDevice.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p]
     lib.detexb200ConvertPixelsDevice.restype = C.c_int
     lib.detexb200GenerateBlocksDevice.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_uint64, C.c_uint64, C.c_int, C.c_void_p]
@@ -184,6 +188,17 @@ def decode_device(fmt, d_blocks, width, height, d_pixels, pixel_format=None, lay
     hib = (height + 3) // 4 if hib is None else hib
     _check(load().detexb200DecodeDevice(tf, d_blocks, width, height, wib, hib, d_pixels, pf, layout,
                                         mode_mask, flags, d_invalid, stream))
+
+
+def decode_hdr_device(fmt, d_blocks, width, height, d_pixels, pixel_format, gamma=1.0, range_min=0.0, range_max=1.0,
+                      layout=LAYOUT_LINEAR, d_invalid=0, stream=0, wib=None, hib=None):
+    """detexb200DecodeHDRDevice: BC6H blocks -> HDR-converted pixels (decode, then the conversion from the
+    _HDR twin of the native format under the given gamma / range) on raw device pointers."""
+    tf = _tf(fmt)
+    wib = (width + 3) // 4 if wib is None else wib
+    hib = (height + 3) // 4 if hib is None else hib
+    _check(load().detexb200DecodeHDRDevice(tf, d_blocks, width, height, wib, hib, d_pixels, pixel_format, layout,
+                                           gamma, range_min, range_max, d_invalid, stream))
 
 
 def convert_pixels_device(d_src, nu_pixels, source_pixel_format, d_dst, target_pixel_format, stream=0):

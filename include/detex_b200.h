@@ -66,6 +66,26 @@ DETEXB200_API int detexb200DecodeDevice(uint32_t texture_format, const void *d_b
 	uint32_t mode_mask, uint32_t flags, uint32_t *d_invalid, void *stream);
 
 /*
+ * BC6H straight to displayable pixels: the bytes the reference produces with
+ *     detexDecompressTextureLinear / ...Tiled(texture, tmp, DETEX_PIXEL_FORMAT_FLOAT_RGBX16);
+ *     detexSetHDRParameters(gamma, range_min, range_max);                        (hdr.c:34-38)
+ *     detexConvertPixels(tmp, n, DETEX_PIXEL_FORMAT_FLOAT_RGBX16_HDR, out, pixel_format);
+ * i.e. the decoded half floats go through the HDR half -> 16-bit integer step (hdr.c:119-171)
+ * and whatever the conversion chain to pixel_format holds after it.  An invalid block leaves the
+ * conversion of zero pixels (that is what the sequence above does), and *d_invalid is raised.
+ * texture_format must be DETEX_TEXTURE_FORMAT_BPTC_FLOAT (the only compressed format whose pixel
+ * format has an _HDR twin).  For gamma == 1 and pixel_format RGBX8, RGBA8, BGRX8, BGRA8 or RGB8
+ * the whole chain runs inside the decode kernel (one pass over HBM: 16 bytes in, 64 or 48 out
+ * per block); other targets and gamma values go through the L2-resident conversion pass of
+ * detexb200DecodeDevice.  The HDR parameters of the calling thread (detexSetHDRParameters) are
+ * left unchanged.
+ */
+DETEXB200_API int detexb200DecodeHDRDevice(uint32_t texture_format, const void *d_blocks,
+	int width, int height, int width_in_blocks, int height_in_blocks,
+	void *d_pixels, uint32_t pixel_format, int layout,
+	float gamma, float range_min, float range_max, uint32_t *d_invalid, void *stream);
+
+/*
  * Convert nu_pixels pixels between two pixel formats on the device
  * (reference convert.c:1082-1166 for the supported pairs).
  * d_src and d_dst may be equal when both formats have the same pixel size.

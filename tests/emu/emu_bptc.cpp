@@ -5,6 +5,7 @@
 #define DETEXB200_HOST_EMU 1
 #include "decode_bptc_palette.cuh"
 #include "decode_bptc_float.cuh"
+#include "tone.cuh"
 #include <cstring>
 
 using namespace detexb200;
@@ -25,6 +26,23 @@ static void tables_init() {
 }
 
 extern "C" {
+
+/* tone.cuh: n tiles of 16 FLOAT_RGBX16 pixels (128 bytes each) -> n tiles of 16 RGBX8 pixels (64 bytes),
+   the fused BC6H -> 8-bit chain with the given range parameters (hdr = 0: plain normalised half) */
+void emu_tone8_tiles(const uint8_t *tiles, int n, int hdr, float range_min, float range_max, uint8_t *out) {
+	ToneArgs a;
+	a.range_min = range_min;
+	a.range_max = range_max;
+	a.hdr = (uint32_t)hdr;
+	a.zero_target = 0;
+	const Tone t = tone_setup(a);
+	for (int i = 0; i < n; i++) {
+		uint32_t px[32], q[16];
+		memcpy(px, tiles + 128 * (size_t)i, 128);
+		tone8_tile(px, q, t);
+		memcpy(out + 64 * (size_t)i, q, 64);
+	}
+}
 
 /* BC6H: n blocks -> n tiles of 16 (SIGNED_)FLOAT_RGBX16 pixels (128 bytes, TILED); valid[i] = 0 and a
    zero tile for an invalid block */

@@ -8,6 +8,9 @@
  */
 #pragma once
 #include <cstdint>
+#include <cstring>
+#include <cmath>
+#include <cfenv>
 #include <algorithm>
 
 #define __device__
@@ -55,3 +58,20 @@ static inline uint32_t __brev(uint32_t v) {
 }
 static inline uint32_t __umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
 static inline int __mulhi(int a, int b) { return (int)(((int64_t)a * b) >> 32); }
+
+/* float intrinsics with an explicit rounding mode (tone.cuh): evaluated through volatile operands
+   under fesetround so that the host compiler can neither fold nor reorder them */
+static inline float __uint_as_float(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
+static inline uint32_t __float_as_uint(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+template <typename Op> static inline float emu_rounded(int mode, Op op) {
+	const int old = fegetround();
+	fesetround(mode);
+	volatile float r = op();
+	fesetround(old);
+	return r;
+}
+static inline float __fmul_rn(float a, float b) { volatile float x = a, y = b; return emu_rounded(FE_TONEAREST, [&] { return x * y; }); }
+static inline float __fmul_rd(float a, float b) { volatile float x = a, y = b; return emu_rounded(FE_DOWNWARD, [&] { return x * y; }); }
+static inline float __fadd_rd(float a, float b) { volatile float x = a, y = b; return emu_rounded(FE_DOWNWARD, [&] { return x + y; }); }
+static inline float __fsub_rd(float a, float b) { volatile float x = a, y = b; return emu_rounded(FE_DOWNWARD, [&] { return x - y; }); }
+static inline float __fdiv_rd(float a, float b) { volatile float x = a, y = b; return emu_rounded(FE_DOWNWARD, [&] { return x / y; }); }

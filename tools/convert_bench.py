@@ -31,10 +31,12 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--pixels", type=int, default=1 << 25)
     ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--only", default="", help="comma-separated compressed formats: decode cases only, of these formats")
     args = ap.parse_args()
+    only = [f for f in args.only.split(",") if f]
     peak, _ = measured_peak()
     n = args.pixels
-    for a, b in (("RGBA8", "BGRA8"), ("RGBA8", "RGB8"), ("FLOAT_RGBX16", "FLOAT_RGB16"), ("R16", "R8"),
+    for a, b in () if only else (("RGBA8", "BGRA8"), ("RGBA8", "RGB8"), ("FLOAT_RGBX16", "FLOAT_RGB16"), ("R16", "R8"),
                  ("RGBX8", "RGBX16"), ("FLOAT_RGBX32", "FLOAT_RGBX16"), ("FLOAT_RGBX16", "RGBX8"), ("SIGNED_RG16", "RG8")):
         sf, tf = PF[a], PF[b]
         src = torch.randint(0, 255, (n * pixel_size(sf),), dtype=torch.uint8, device="cuda")
@@ -46,7 +48,10 @@ def main():
     wib = hib = 2048
     nb = wib * hib
     for fmt, target in (("BC1", None), ("BC1", "BGRA8"), ("BC1", "RGB8"), ("BPTC", "RGB8"), ("BPTC_FLOAT", None),
-                        ("BPTC_FLOAT", "FLOAT_RGB16"), ("EAC_RG11", "RG8"), ("BC3", "RGBA16")):
+                        ("BPTC_FLOAT", "FLOAT_RGB16"), ("BPTC_FLOAT", "RGBX8"), ("BPTC_FLOAT", "BGRA8"), ("BPTC_FLOAT", "RGB8"),
+                        ("BPTC_FLOAT", "RGBX16"), ("EAC_RG11", "RG8"), ("BC3", "RGBA16")):
+        if only and fmt not in only:
+            continue
         tf = D.FORMATS[fmt]
         bs = D.block_size(tf)
         pf = D.native_pixel_format(tf) if target is None else PF[target]
