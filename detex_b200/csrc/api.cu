@@ -166,6 +166,8 @@ cudaStream_t stream, bool hdr = false) {
 			float gamma;
 			get_hdr_parameters(&gamma, &a.tone_min, &a.tone_max);
 			a.tone_hdr = 1;
+			if (!(a.tone_min == 0.0f && a.tone_max == 1.0f))	// hdr.c:124-131; the rescaling variants of the kernels
+				a.post_class += a.post_class == 7 ? 1 : 2;
 		}
 		a.pixels = d_pixels;
 		if ((e = launch_decode((int)(tf >> 24), a, stream)) != cudaSuccess)

@@ -218,6 +218,17 @@ FusedConversion convert_fused(uint32_t s, uint32_t d) {
 		if (shrunk)
 			return f;				// nothing may follow the size change
 		if ((e.op == ST_HALF_TO_INT || e.op == ST_HALF_HDR_TO_INT) && e.target == PF_RGBX16 && f.post_op == 0u && tone_fusion() &&
+		    i + 1 == n && f.post_class == 0) {	// the 16-bit stage on its own: target RGBX16
+			if (e.op == ST_HALF_HDR_TO_INT) {
+				if (g_hdr.gamma != 1.0f)
+					return f;
+				f.tone_hdr = true;
+			}
+			f.post_class = 7;
+			shrunk = true;
+			continue;
+		}
+		if ((e.op == ST_HALF_TO_INT || e.op == ST_HALF_HDR_TO_INT) && e.target == PF_RGBX16 && f.post_op == 0u && tone_fusion() &&
 		    i + 1 < n && conversion_table[steps[i + 1]].op == ST_NARROW && conversion_table[steps[i + 1]].target == PF_RGBX8) {
 			if (e.op == ST_HALF_HDR_TO_INT) {
 				if (g_hdr.gamma != 1.0f)

@@ -150,9 +150,33 @@ __device__ __forceinline__ int sext_runtime(uint32_t v, int bits) {
 // Shared tail: delta decode, unquantise, expand indices, interpolate, emit.
 // NS = 2 for detex modes 0-9 (3-bit indices from stream bit 82), 1 for modes 10-13
 // (4-bit indices from bit 65).
-template <bool SIGNED, int NS>
+// What becomes of a pixel: sink(i, v_r, v_g, v_b) receives the three interpolated 16-bit values of
+// pixel i (InterpolateFloat's result, before the final scaling to a half-float pattern).  The native
+// sink below finishes them into FLOAT_RGBX16 / SIGNED_FLOAT_RGBX16 words; tone.cuh has a sink that
+// goes on to 8-bit pixels.
+template <bool SIGNED>
+struct Bc6hHalfSink {
+	uint32_t (&px)[32];
+	__device__ __forceinline__ void operator()(int i, int v0, int v1, int v2) const {
+		const int v[3] = { v0, v1, v2 };
+		uint32_t h[3];
+#pragma unroll
+		for (int c = 0; c < 3; c++) {
+			if (SIGNED) {					// :577-613
+				const int mag = ((v[c] < 0 ? -v[c] : v[c]) * 31) >> 5;
+				h[c] = (uint32_t)mag | ((v[c] < 0 && mag != 0) ? 0x8000u : 0u);
+			}
+			else
+				h[c] = (uint32_t)((v[c] * 31) >> 6);	// :616-621 (v >= 0)
+		}
+		px[2 * i] = (h[0] & 0xFFFFu) | (h[1] << 16);		// Q10: R | G<<16 | B<<32, X = 0
+		px[2 * i + 1] = h[2] & 0xFFFFu;
+	}
+};
+
+template <bool SIGNED, int NS, typename Sink>
 __device__ __forceinline__ void bc6h_finish(const uint4 &w, const Bc6hRaw &raw, int epb, int dr, int dg, int db,
-const BptcTables &tab, uint32_t (&px)[32]) {
+const BptcTables &tab, const Sink &sink) {
 	constexpr int NE = 2 * NS, IB = NS == 1 ? 4 : 3;
 	const uint32_t epmask = epb >= 32 ? 0xFFFFFFFFu : ((1u << epb) - 1u);
 	const int delta_bits[3] = { dr, dg, db };
@@ -227,7 +251,7 @@ const BptcTables &tab, uint32_t (&px)[32]) {
 	for (int i = 0; i < 16; i++) {
 		const uint32_t bit = NS == 2 ? ((subset_bits >> i) & 1u) : 0u;
 		const int wgt = (int)bptc_weight<IB>((uint32_t)(s >> (i * IB)) & ((1u << IB) - 1u));
-		uint32_t h[3];
+		int v[3];
 #pragma unroll
 		for (int c = 0; c < 3; c++) {
 			int a = a_c[0][c], k = k_c[0][c];
@@ -235,16 +259,9 @@ const BptcTables &tab, uint32_t (&px)[32]) {
 				a = (int)mad_u32(bit, da[c], (uint32_t)a);
 				k = (int)mad_u32(bit, dk[c], (uint32_t)k);
 			}
-			const int v = (a + wgt * k) >> 6;		// InterpolateFloat, :97-108 (Q18)
-			if (SIGNED) {					// :577-613
-				const int mag = ((v < 0 ? -v : v) * 31) >> 5;
-				h[c] = (uint32_t)mag | ((v < 0 && mag != 0) ? 0x8000u : 0u);
-			}
-			else
-				h[c] = (uint32_t)((v * 31) >> 6);	// :616-621 (v >= 0)
+			v[c] = (a + wgt * k) >> 6;			// InterpolateFloat, :97-108 (Q18)
 		}
-		px[2 * i] = (h[0] & 0xFFFFu) | (h[1] << 16);		// Q10: R | G<<16 | B<<32, X = 0
-		px[2 * i + 1] = h[2] & 0xFFFFu;
+		sink(i, v[0], v[1], v[2]);
 	}
 }
 
@@ -260,9 +277,8 @@ __device__ __forceinline__ int bc6h_mode(uint32_t w0) {
 	return code < 16u ? 10 + (int)(code >> 2) : -1;
 }
 
-template <bool SIGNED>
-__device__ __forceinline__ bool decode_bptc_float(const uint4 blk, uint32_t mode_mask, uint32_t,
-const BptcTables &tab, uint32_t (&px)[32]) {
+template <bool SIGNED, typename Sink>
+__device__ __forceinline__ bool decode_bptc_float_to(const uint4 blk, uint32_t mode_mask, const BptcTables &tab, const Sink &sink) {
 	const int mode = bc6h_mode(blk.x);
 	Bc6hRaw raw;
 	Bc6hModeInfo info = bc6h_mode_info(0);
@@ -274,10 +290,16 @@ const BptcTables &tab, uint32_t (&px)[32]) {
 	default: return false;
 	}
 	if (mode >= 10)
-		bc6h_finish<SIGNED, 1>(blk, raw, info.epb, info.dr, info.dg, info.db, tab, px);
+		bc6h_finish<SIGNED, 1>(blk, raw, info.epb, info.dr, info.dg, info.db, tab, sink);
 	else
-		bc6h_finish<SIGNED, 2>(blk, raw, info.epb, info.dr, info.dg, info.db, tab, px);
+		bc6h_finish<SIGNED, 2>(blk, raw, info.epb, info.dr, info.dg, info.db, tab, sink);
 	return (mode_mask >> mode) & 1u;		// :121
+}
+
+template <bool SIGNED>
+__device__ __forceinline__ bool decode_bptc_float(const uint4 blk, uint32_t mode_mask, uint32_t,
+const BptcTables &tab, uint32_t (&px)[32]) {
+	return decode_bptc_float_to<SIGNED>(blk, mode_mask, tab, Bc6hHalfSink<SIGNED>{ px });
 }
 
 }  // namespace detexb200

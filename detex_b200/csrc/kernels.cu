@@ -101,10 +101,16 @@ uint32_t mode_mask, uint32_t flags, const BptcTables *tab, uint32_t (&px)[Format
 //     PC_TONE8      BC6H only: half -> 16-bit integer (optionally rescaled by the HDR range) -> 8 bit,
 //                   FLOAT_RGBX16 -> RGBX8 / RGBA8 (tone.cuh); POST_SWAP_RB then acts
 //                   on the 8-bit pixels (-> BGRX8 / BGRA8);
-//     PC_TONE8_PACK3  the same followed by dropping the fourth component (-> RGB8).
+//     PC_TONE8_PACK3  the same followed by dropping the fourth component (-> RGB8);
+//     PC_TONE8R, PC_TONE8R_PACK3  the two above with the HDR range rescaling compiled in;
+//     PC_TONE16, PC_TONE16R     BC6H only: the 16-bit stage alone, FLOAT_RGBX16 -> RGBX16 (same tile size).
 constexpr uint32_t POST_NONE = 0, POST_SWAP_RB = 1, POST_FLIP16 = 2, POST_FLIP8 = 4;
-constexpr int PC_NATIVE = 0, PC_PACK3 = 1, PC_NARROW = 2, PC_TONE8 = 3, PC_TONE8_PACK3 = 4;
-constexpr bool is_tone_class(int pc) { return pc == PC_TONE8 || pc == PC_TONE8_PACK3; }
+constexpr int PC_NATIVE = 0, PC_PACK3 = 1, PC_NARROW = 2, PC_TONE8 = 3, PC_TONE8_PACK3 = 4, PC_TONE8R = 5, PC_TONE8R_PACK3 = 6,
+	PC_TONE16 = 7, PC_TONE16R = 8;
+constexpr bool is_tone_class(int pc) { return pc >= PC_TONE8 && pc <= PC_TONE8R_PACK3; }	// the 8-bit ones
+constexpr bool is_tone16_class(int pc) { return pc == PC_TONE16 || pc == PC_TONE16R; }
+constexpr bool tone_rescales(int pc) { return pc == PC_TONE8R || pc == PC_TONE8R_PACK3 || pc == PC_TONE16R; }
+constexpr bool tone_packs3(int pc) { return pc == PC_TONE8_PACK3 || pc == PC_TONE8R_PACK3; }
 
 template <int OW>
 __device__ __forceinline__ void apply_post_op(uint32_t (&px)[OW], uint32_t post_op) {
@@ -135,7 +141,7 @@ __device__ __forceinline__ void apply_post_op(uint32_t (&px)[OW], uint32_t post_
 
 // words per decoded tile after the post class
 template <int OW, int PC> constexpr int post_words() {
-	return PC == PC_PACK3 ? OW * 3 / 4 : (PC == PC_NARROW || PC == PC_TONE8 ? OW / 2 : (PC == PC_TONE8_PACK3 ? OW * 3 / 8 : OW));
+	return PC == PC_PACK3 ? OW * 3 / 4 : (tone_packs3(PC) ? OW * 3 / 8 : (PC == PC_NARROW || is_tone_class(PC) ? OW / 2 : OW));
 }
 // which (format, class) pairs exist: PACK3 for the four-component 8-bit formats and BC6H unsigned,
 // NARROW for the 16-bit one- and two-component formats
@@ -145,7 +151,7 @@ template <int F, int PC> constexpr bool post_class_valid() {
 		return true;
 	if (PC == PC_PACK3)
 		return (OW == 16 && F != F_EAC_RG11 && F != F_EAC_SIGNED_RG11 && F != F_SIGNED_RGTC2) || F == F_BPTC_FLOAT;
-	if (is_tone_class(PC))
+	if (is_tone_class(PC) || is_tone16_class(PC))
 		return F == F_BPTC_FLOAT;
 	return F == F_EAC_R11 || F == F_EAC_SIGNED_R11 || F == F_EAC_RG11 || F == F_EAC_SIGNED_RG11 ||
 		F == F_SIGNED_RGTC1 || F == F_SIGNED_RGTC2;
@@ -200,17 +206,32 @@ struct EmitCtxTone {
 };
 template <> struct EmitCtx<PC_TONE8> : EmitCtxTone { using EmitCtxTone::EmitCtxTone; };
 template <> struct EmitCtx<PC_TONE8_PACK3> : EmitCtxTone { using EmitCtxTone::EmitCtxTone; };
+template <> struct EmitCtx<PC_TONE8R> : EmitCtxTone { using EmitCtxTone::EmitCtxTone; };
+template <> struct EmitCtx<PC_TONE8R_PACK3> : EmitCtxTone { using EmitCtxTone::EmitCtxTone; };
+template <> struct EmitCtx<PC_TONE16> : EmitCtxTone { using EmitCtxTone::EmitCtxTone; };
+template <> struct EmitCtx<PC_TONE16R> : EmitCtxTone { using EmitCtxTone::EmitCtxTone; };
 
-// 16 FLOAT_RGBX16 pixels -> 16 RGBX8 / BGRX8 pixels (tone classes): tone map, invalid rule, swap
+// Tone classes: the decoder's pixel sink has already produced 16 RGBX8 pixels in px[0..15]
+// (decode_px below).  What is left: the invalid rule and the R <-> B swap.
 template <int PC>
 __device__ __forceinline__ void tone_tile(const uint32_t (&px)[32], uint32_t (&t)[16], uint32_t post_op, const EmitCtx<PC> &ctx, bool ok) {
-	tone8_tile(px, t, ctx.tone);
-	if (!ok && ctx.zero_target) {
+	const uint32_t fill = ctx.zero_target ? 0u : tone8_of_zero<tone_rescales(PC)>(ctx.tone);
 #pragma unroll
-		for (int k = 0; k < 16; k++)
-			t[k] = 0u;
-	}
+	for (int k = 0; k < 16; k++)
+		t[k] = ok ? px[k] : fill;
 	apply_post_op<16>(t, post_op & POST_SWAP_RB);
+}
+
+// decode_block for the class: the tone classes decode BC6H through the 8-bit pixel sink (tone.cuh).
+template <int F, int PC, int PATHS = ETC_PATHS_ALL>
+__device__ __forceinline__ bool decode_px(const typename BlockReg<FormatTraits<F>::BLOCK_WORDS>::type &blk,
+uint32_t mode_mask, uint32_t flags, const BptcTables *tab, const EmitCtx<PC> &ctx, uint32_t (&px)[FormatTraits<F>::OUT_WORDS]) {
+	if constexpr (is_tone_class(PC))
+		return decode_bptc_float_tone8<tone_rescales(PC)>(blk, mode_mask, *tab, ctx.tone, px);
+	else if constexpr (is_tone16_class(PC))
+		return decode_bptc_float_tone16<tone_rescales(PC)>(blk, mode_mask, *tab, ctx.tone, px);
+	else
+		return decode_block<F, PATHS>(blk, mode_mask, flags, tab, px);
 }
 
 // post_op, then hand the words that go to memory to store(words): the decoded array itself for
@@ -221,13 +242,23 @@ __device__ __forceinline__ void emit(uint32_t (&px)[OW], uint32_t post_op, const
 	if constexpr (is_tone_class(PC)) {
 		uint32_t t[16];
 		tone_tile<PC>(px, t, post_op, ctx, ok);
-		if constexpr (PC == PC_TONE8)
+		if constexpr (!tone_packs3(PC))
 			store(t);
 		else {
 			uint32_t q[12];
 			repack<PC_PACK3, 16>(t, q);
 			store(q);
 		}
+	}
+	else if constexpr (is_tone16_class(PC)) {
+		// the pixel sink wrote RGBX16 pixels; an invalid block is zero or the conversion of zero pixels
+		if (!ok) {
+			const uint32_t z = ctx.zero_target ? 0u : tone16_of_zero<tone_rescales(PC)>(ctx.tone);
+#pragma unroll
+			for (int k = 0; k < OW; k++)
+				px[k] = z | (z << 16);
+		}
+		store(px);
 	}
 	else {
 		apply_post_op<OW>(px, post_op);
@@ -411,7 +442,7 @@ uint32_t mode_mask, uint32_t flags, uint32_t post_op, uint32_t *invalid_flag, ui
 				if constexpr (D::ENABLED)
 					rare = D::is_rare(blk);
 				if (!rare)
-					ok = decode_block<F, D::ENABLED ? ETC_PATHS_NO_PLANAR : ETC_PATHS_ALL>(blk, mode_mask, flags, &tables, px);
+					ok = decode_px<F, PC, D::ENABLED ? ETC_PATHS_NO_PLANAR : ETC_PATHS_ALL>(blk, mode_mask, flags, &tables, ctx, px);
 			}
 			if (!ok) {
 				bad = true;
@@ -553,7 +584,7 @@ ToneArgs tone_args) {
 					queue[atomicAdd(&queue_n, 1)] = (uint32_t)by * (uint32_t)wib + (uint32_t)bx;
 				else {
 					uint32_t px[OW];
-					const bool ok = decode_block<F, D::ENABLED ? ETC_PATHS_NO_PLANAR : ETC_PATHS_ALL>(blk, mode_mask, flags, &tables, px);
+					const bool ok = decode_px<F, PC, D::ENABLED ? ETC_PATHS_NO_PLANAR : ETC_PATHS_ALL>(blk, mode_mask, flags, &tables, ctx, px);
 					if (!ok) {
 						bad = true;
 						mark_invalid(invalid_map, (uint32_t)by * (uint32_t)wib + (uint32_t)bx);
@@ -614,7 +645,7 @@ ToneArgs tone_args) {
 		const int by = (int)(i / (uint32_t)wib), bx = (int)(i % (uint32_t)wib);
 		const auto blk = BlockReg<BW>::load(src + (size_t)i * (BW * 4));
 		uint32_t px[OW];
-		const bool ok = decode_block<F>(blk, mode_mask, flags, &tables, px);
+		const bool ok = decode_px<F, PC>(blk, mode_mask, flags, &tables, ctx, px);
 		if (!ok) {
 			bad = true;
 			mark_invalid(invalid_map, i);
@@ -740,7 +771,11 @@ __device__ __forceinline__ uint32_t raw_slot(uint32_t id) { return id ^ ((id >> 
 //           holds start[b]), ids scattered to their sorted slots, barrier
 //   decode  each warp takes groups of 32 same-mode blocks -> pixels parked in shared memory
 //   store   barrier, cooperative copy-out, 512 contiguous bytes per warp store instruction
-template <int F, int LAYOUT, bool STAGE, int PC>
+// PAD: bins are padded to a multiple of PAD sorted slots.  32 keeps every warp in one mode; 16 lets a
+// warp hold two half-warps of different modes (BC6H modes share everything after the bit scatter, so a
+// mixed warp costs about a quarter more) and halves the lanes lost to padding, which matters for the
+// 1024-block tiles of the staged BC6H variants (14 modes: 31 % of the slots are padding at 32).
+template <int F, int LAYOUT, bool STAGE, int PC, int PAD = 32>
 __global__ void __launch_bounds__(SORT_THREADS, 2)
 decode_sorted_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, uint32_t n_blocks, int width,
 int height, int wib, uint32_t mode_mask, uint32_t flags, uint32_t post_op, uint32_t *invalid_flag, uint32_t *invalid_map,
@@ -809,7 +844,7 @@ ToneArgs tone_args) {
 		__syncthreads();
 		// padded exclusive scan of the bin counts, redundantly in every warp: lane b <- start[b]
 		const int my_count = lane < NB ? sm.count[cur][lane] : 0;
-		const int padded = S::PAD_BINS ? ((my_count + 31) & ~31) : my_count;
+		const int padded = S::PAD_BINS ? ((my_count + (PAD - 1)) & ~(PAD - 1)) : my_count;
 		int start = padded;
 #pragma unroll
 		for (int d = 1; d < 16; d *= 2) {
@@ -823,7 +858,7 @@ ToneArgs tone_args) {
 		// slots are written by the scatter, so the array needs no clearing pass
 		if (S::PAD_BINS && warp < NB) {
 			const int c = __shfl_sync(0xFFFFFFFFu, my_count, warp), st = __shfl_sync(0xFFFFFFFFu, start, warp);
-			if (lane < ((-c) & 31))
+			if (lane < ((-c) & (PAD - 1)))
 				sm.id[st + c + lane] = (uint16_t)SLOT_EMPTY;
 		}
 #pragma unroll
@@ -836,16 +871,17 @@ ToneArgs tone_args) {
 		// ---- decode: groups of 32 same-mode blocks; padding slots hold the 0xFFFF sentinel.
 		// The next group's ids are fetched before the current group is decoded.
 		int g = warp * 32;
-		uint32_t id_next = g < total ? sm.id[g + lane] : SLOT_EMPTY;
+		// (with PAD < 32 the last group may end inside the warp: slots from total on are not initialised)
+		uint32_t id_next = g + (PAD < 32 ? lane : 0) < total ? sm.id[g + lane] : SLOT_EMPTY;
 		for (; g < total; g += SORT_WARPS * 32) {
 			const uint32_t id = id_next;
 			const int g_next = g + SORT_WARPS * 32;
-			id_next = g_next < total ? sm.id[g_next + lane] : SLOT_EMPTY;
+			id_next = g_next + (PAD < 32 ? lane : 0) < total ? sm.id[g_next + lane] : SLOT_EMPTY;
 			const bool live = id != SLOT_EMPTY;
 			if (live) {
 				const uint4 w = sm.raw[cur][raw_slot(id)];
 				uint32_t px[OW];
-				const bool ok = decode_block<F>(w, mode_mask, flags, &sm.tables, px);
+				const bool ok = decode_px<F, PC>(w, mode_mask, flags, &sm.tables, ctx, px);
 				if (!ok) {
 					bad = true;
 					mark_invalid(invalid_map, tile0 + id);
@@ -898,8 +934,8 @@ ToneArgs tone_args) {
 			continue;		// direct stores: the barrier at the loop top is enough
 		__syncthreads();
 		// ---- store
-		constexpr bool PACK_ROWS = (PC == PC_PACK3 && OW == 16) || PC == PC_TONE8_PACK3;	// RGBX8 stage -> RGB8 rows
-		static_assert(!STAGE || PC == PC_NATIVE || (PC == PC_TONE8 && LAYOUT == LAYOUT_LINEAR) ||
+		constexpr bool PACK_ROWS = (PC == PC_PACK3 && OW == 16) || tone_packs3(PC);	// RGBX8 stage -> RGB8 rows
+		static_assert(!STAGE || PC == PC_NATIVE || (is_tone_class(PC) && LAYOUT == LAYOUT_LINEAR) ||
 			(PACK_ROWS && LAYOUT == LAYOUT_LINEAR), "staged copy-out repacks RGB8 rows only");
 		if (LAYOUT == LAYOUT_TILED) {
 			uint8_t *out = dst + (size_t)tile0 * (CHUNKS * 16);
@@ -1324,6 +1360,19 @@ static bool tiled_direct() {
 	return v;
 }
 
+// Bin padding of the sorted kernels (template parameter PAD of decode_sorted_kernel).  BC7 modes are
+// separate code, so a warp must not mix them: 32.  BC6H modes share everything after the bit scatter:
+// the unsigned direct-store kernels run unpadded (measured, G blocks/s LINEAR / TILED, padded -> unpadded:
+// distribution M 25.2 / 24.4 -> 26.5 / 25.9, U 27.3 / 26.5 -> 27.0 / 26.2); the signed format loses
+// 5-12 % without padding and the staged tone kernels 6 % (1024-block tiles: 20.2 -> 18.9), so they keep 32.
+// DETEXB200_BC6H_PAD=32|1 overrides the choice for unsigned BC6H (A/B measurements).
+template <int F> static int sort_pad() {
+	if (F != F_BPTC_FLOAT)
+		return 32;
+	static const int v = [] { const char *e = getenv("DETEXB200_BC6H_PAD"); return e ? atoi(e) : 1; }();
+	return v;
+}
+
 // One instantiation of the sorted kernel: opt in to > 48 KiB of dynamic shared memory once per
 // device, then launch.
 static ToneArgs tone_args_of(const DecodeArgs &a) {
@@ -1335,7 +1384,7 @@ static ToneArgs tone_args_of(const DecodeArgs &a) {
 	return t;
 }
 
-template <int F, int LAYOUT, bool STAGE, int PC>
+template <int F, int LAYOUT, bool STAGE, int PC, int PAD = 32>
 static void launch_sorted(const uint8_t *src, uint8_t *dst, uint32_t n_blocks, const DecodeArgs &a, cudaStream_t stream) {
 	using SM = SortedSmem<F, PC, STAGE>;
 	const size_t smem = sizeof(SM);
@@ -1346,11 +1395,22 @@ static void launch_sorted(const uint8_t *src, uint8_t *dst, uint32_t n_blocks, c
 	int dev = 0;
 	cudaGetDevice(&dev);
 	if (!configured[dev & 63].load()) {
-		cudaFuncSetAttribute(decode_sorted_kernel<F, LAYOUT, STAGE, PC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		cudaFuncSetAttribute(decode_sorted_kernel<F, LAYOUT, STAGE, PC, PAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 		configured[dev & 63].store(true);
 	}
-	decode_sorted_kernel<F, LAYOUT, STAGE, PC><<<grid, SORT_THREADS, smem, stream>>>(src, dst, n_blocks,
+	decode_sorted_kernel<F, LAYOUT, STAGE, PC, PAD><<<grid, SORT_THREADS, smem, stream>>>(src, dst, n_blocks,
 		a.width, a.height, a.wib, a.mode_mask, a.flags, a.post_op, a.invalid, a.invalid_map, tone_args_of(a));
+}
+
+template <int F, int LAYOUT, bool STAGE, int PC>
+static void launch_sorted_pad(int pad, const uint8_t *src, uint8_t *dst, uint32_t n_blocks, const DecodeArgs &a, cudaStream_t stream) {
+	if constexpr (F == F_BPTC_FLOAT) {
+		if (pad == 1) {
+			launch_sorted<F, LAYOUT, STAGE, PC, 1>(src, dst, n_blocks, a, stream);
+			return;
+		}
+	}
+	launch_sorted<F, LAYOUT, STAGE, PC, 32>(src, dst, n_blocks, a, stream);
 }
 
 // DETEXB200_BC7_KERNEL=flow selects the palette-staged dataflow kernel for BC7 instead of
@@ -1405,13 +1465,17 @@ static cudaError_t launch_format(const DecodeArgs &a, cudaStream_t stream) {
 			}
 			// LINEAR rows of 16 bytes or less per block are half sectors when written by lanes in sorted
 			// order: those tiles (BC7, the toned BC6H classes) are staged and copied out in image order
+			// (measured for the toned classes: staged 20.2 G blocks/s, direct 15.3)
 			constexpr bool ST = SortTraits<F>::STAGE_OUTPUT;
+			const int pad = sort_pad<F>();
 			if (a.layout == LAYOUT_TILED && (PC != PC_NATIVE || (tiled_direct() && aligned32)))
-				launch_sorted<F, LAYOUT_TILED, false, PC>(src, dst, (uint32_t)n_blocks, a, stream);
+				launch_sorted_pad<F, LAYOUT_TILED, false, PC>(pad, src, dst, (uint32_t)n_blocks, a, stream);
 			else if (a.layout == LAYOUT_TILED)
 				launch_sorted<F, LAYOUT_TILED, ST, PC_NATIVE>(src, dst, (uint32_t)n_blocks, a, stream);
+			else if constexpr (is_tone_class(PC))
+				launch_sorted<F, LAYOUT_LINEAR, true, PC>(src, dst, (uint32_t)n_blocks, a, stream);
 			else
-				launch_sorted<F, LAYOUT_LINEAR, ST || is_tone_class(PC), PC>(src, dst, (uint32_t)n_blocks, a, stream);
+				launch_sorted_pad<F, LAYOUT_LINEAR, ST, PC>(pad, src, dst, (uint32_t)n_blocks, a, stream);
 			count_launch();
 			return cudaGetLastError();
 		}
@@ -1484,6 +1548,14 @@ static cudaError_t launch_classes(const DecodeArgs &a, cudaStream_t stream) {
 			return launch_format<F, PC_TONE8>(a, stream);
 		if (a.post_class == PC_TONE8_PACK3)
 			return launch_format<F, PC_TONE8_PACK3>(a, stream);
+		if (a.post_class == PC_TONE8R)
+			return launch_format<F, PC_TONE8R>(a, stream);
+		if (a.post_class == PC_TONE8R_PACK3)
+			return launch_format<F, PC_TONE8R_PACK3>(a, stream);
+		if (a.post_class == PC_TONE16)
+			return launch_format<F, PC_TONE16>(a, stream);
+		if (a.post_class == PC_TONE16R)
+			return launch_format<F, PC_TONE16R>(a, stream);
 	}
 	return cudaErrorInvalidValue;
 }

@@ -4,23 +4,33 @@
 // whole-buffer passes: decode to FLOAT_RGBX16, half -> 16-bit integer (plain:
 // detexConvertNormalizedHalfFloatToUInt16, half-float.c:304-312; with range parameters:
 // detexConvertHDRHalfFloatToUInt16Gamma1, hdr.c:119-141), 16 -> 8 bit (convert.c:300-316).
-// Every step is a per-component function, so the chain is applied here to the decoder's 16 pixels
-// while they are still in registers; HBM sees 16 bytes in and 64 (48) bytes out per block instead
-// of 16 + 128 + 128 + 128 + 64.
+// Every step is a per-component function, so the chain is applied here to the decoder's pixels
+// while they are still in registers (a pixel sink of decode_bptc_float_to); HBM sees 16 bytes in
+// and 64 (48) bytes out per block instead of 16 + 128 + 128 + 128 + 64.  Stopping after the second
+// step gives the RGBX16 target (the HDR step of hdr.c on its own).
 //
-// The arithmetic is the reference's, operation by operation, with its rounding mode
-// (FE_DOWNWARD) spelled out; the only liberties are ones that cannot change a result:
-//   * half -> float as a multiply of the shifted bit pattern by 2^112 (exact for every
-//     non-negative finite half, denormals included; the unsigned BC6H decoder produces nothing
-//     else: (x * 31) >> 6 <= 0x7BFF);
-//   * lrintf(t) under FE_DOWNWARD for 0 <= t < 2^23 read from the mantissa of t + 2^23 rounded
-//     down;
-//   * (v + 127) * 255 / 65535 == ((v + 127) * 65281) >> 24 (kernels.cu, narrow16), folded with the
-//     removal of the 2^23 offset into one multiply-add.
+// The arithmetic is the reference's, with its rounding mode (FE_DOWNWARD) spelled out, restated
+// only where the restatement provably cannot change a result (tests/test_emu_tone.py checks the
+// composition against the compiled reference for every half value the decoder can produce, on the
+// CPU, through tests/emu/host_emu.h):
+//   * half -> float is a multiply of the shifted bit pattern by 2^112: exact for every
+//     non-negative finite half, denormals included, and the unsigned BC6H decoder produces nothing
+//     else ((x * 31) >> 6 <= 0x7BFF); detexClamp0To1 (detex.h:941-948) rides on the multiply that
+//     produces its argument as a .sat modifier (clamps to [0, 1], NaN -> 0: the value the shipped
+//     -Ofast build gives everything that is not above zero);
+//   * u = lrintf(c * 65535.0f + 0.5f) under FE_DOWNWARD is floor(rd(rd(p) + 0.5)) with p = c * 65535.
+//     Rounding down to a grid that contains every integer and every integer + 0.5 (any float grid
+//     below 2^23) moves a value across neither, so u = floor(p + 0.5) with p exact;
+//     fma.rm(c, 131070, 1) = rd(2p + 1), and adding 2^24 (ulp 2) rounds that down to an even integer:
+//     the mantissa field of the sum is floor((2p + 1) / 2) = u.  Two instructions instead of
+//     multiply, add, float -> int;
+//   * (u + 127) * 255 / 65535 == ((u + 127) * 65281) >> 24 (kernels.cu, narrow16), folded with the
+//     removal of the exponent bits into one multiply-add.
 // Gamma other than 1 (powf per component, hdr.c:143-164) is not fused; api.cu sends it through
 // the separate conversion pass.
 #pragma once
 #include "common.cuh"
+#include "decode_bptc_float.cuh"
 
 namespace detexb200 {
 
@@ -38,6 +48,22 @@ struct Tone {
 	bool rescale;
 };
 
+#ifdef DETEXB200_HOST_EMU
+__device__ __forceinline__ float mul_sat(float a, float b) { return emu_sat(__fmul_rn(a, b)); }
+__device__ __forceinline__ float mul_rd_sat(float a, float b) { return emu_sat(__fmul_rd(a, b)); }
+#else
+__device__ __forceinline__ float mul_sat(float a, float b) {
+	float r;
+	asm("mul.rn.sat.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+	return r;
+}
+__device__ __forceinline__ float mul_rd_sat(float a, float b) {
+	float r;
+	asm("mul.rm.sat.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+	return r;
+}
+#endif
+
 __device__ __forceinline__ Tone tone_setup(const ToneArgs &a) {
 	Tone t;
 	t.rescale = a.hdr != 0u && !(a.range_min == 0.0f && a.range_max == 1.0f);	// hdr.c:124-131
@@ -47,31 +73,86 @@ __device__ __forceinline__ Tone tone_setup(const ToneArgs &a) {
 	return t;
 }
 
-// hs = (half bit pattern) << 13, half in [0, 0x7BFF].  Returns a word whose TOP BYTE is the 8-bit
-// component; the lower bytes are garbage.
-__device__ __forceinline__ uint32_t tone8_top(uint32_t hs, const Tone &t) {
-	float f = __fmul_rn(__uint_as_float(hs), 0x1p112f);		// exact
-	if (t.rescale)
-		f = __fmul_rd(__fsub_rd(f, t.lo), t.factor);		// hdr.c:134-136
-	// detexClamp0To1 (detex.h:941-948); NaN (0 * inf when range_min == range_max) and everything
-	// not above zero -> 0 as in the shipped build.  The sign of a zero cannot reach the result.
-	f = fminf(fmaxf(f, 0.0f), 1.0f);
-	const float u = __fadd_rd(__fmul_rd(f, 65535.0f), 0.5f);	// in [0.5, 65535.5]
-	const uint32_t bits = __float_as_uint(__fadd_rd(u, 8388608.0f));	// 0x4B000000 + floor(u)
-	return bits * 65281u + (127u - 0x4B000000u) * 65281u;		// ((floor(u) + 127) * 65281), top byte = / 2^24
+// hs = (half bit pattern) << 13, half in [0, 0x7BFF].  Returns 0x4B800000 + u, u the 16-bit integer
+// component.  RESCALE (compile time: the kernels exist in both variants, kernels.cu "post class")
+// must equal t.rescale.
+template <bool RESCALE>
+__device__ __forceinline__ uint32_t tone16_bits(uint32_t hs, const Tone &t) {
+	float c;
+	if constexpr (RESCALE)
+		c = mul_rd_sat(__fsub_rd(__fmul_rn(__uint_as_float(hs), 0x1p112f), t.lo), t.factor);	// hdr.c:134-136
+	else
+		c = mul_sat(__uint_as_float(hs), 0x1p112f);
+	// u = lrintf(c * 65535 + 0.5) rounding down (see the head of the file)
+	return __float_as_uint(__fadd_rd(__fmaf_rd(c, 131070.0f, 1.0f), 16777216.0f));
 }
 
-// 16 FLOAT_RGBX16 pixels (R | G << 16, B | X << 16 per pixel) -> 16 RGBX8 pixels with X = 0xFF
-// (convert.c:305-309 packs alpha 0xFF).
-__device__ __forceinline__ void tone8_tile(const uint32_t (&px)[32], uint32_t (&q)[16], const Tone &t) {
-#pragma unroll
-	for (int i = 0; i < 16; i++) {
-		const uint32_t lo = px[2 * i], hi = px[2 * i + 1];
-		const uint32_t r = tone8_top((lo << 13) & 0x0FFFE000u, t);
-		const uint32_t g = tone8_top((lo >> 3) & 0x0FFFE000u, t);
-		const uint32_t b = tone8_top((hi << 13) & 0x0FFFE000u, t);
-		q[i] = prmt(prmt(r, g, 0x7773), b | 0xFFu, 0x4710);	// R, G, B, 0xFF
+// The same down to 8 bits: a word whose TOP BYTE is the component; the lower bytes are garbage.
+template <bool RESCALE>
+__device__ __forceinline__ uint32_t tone8_top(uint32_t hs, const Tone &t) {
+	// (u + 127) * 65281: top byte = (u + 127) / 257
+	return tone16_bits<RESCALE>(hs, t) * 65281u + (127u - 0x4B800000u) * 65281u;
+}
+
+// one RGBX8 pixel from three words holding a component in their top byte; X = 0xFF (convert.c:305-309)
+__device__ __forceinline__ uint32_t tone8_pack(uint32_t r, uint32_t g, uint32_t b) {
+	return prmt(prmt(r, g, 0x7773), b | 0xFFu, 0x4710);
+}
+
+// The RGBX8 pixel a zero FLOAT_RGBX16 pixel converts to (what an invalid block leaves behind when
+// the caller asked for decode + conversion semantics).
+template <bool RESCALE>
+__device__ __forceinline__ uint32_t tone8_of_zero(const Tone &t) {
+	const uint32_t z = tone8_top<RESCALE>(0u, t);
+	return tone8_pack(z, z, z);
+}
+
+// Pixel sink of the BC6H decoder: interpolated values -> RGBX8.  The half pattern of a value is
+// (v * 31) >> 6 (decompress-bptc-float.c:616-621); shifted left by 13 that is v * 31 * 128 with the
+// low 13 bits cleared.
+template <int N, bool RESCALE>
+struct Bc6hTone8Sink {
+	uint32_t (&q)[N];		// the first 16 words receive the pixels
+	const Tone &tone;
+	__device__ __forceinline__ void operator()(int i, int v0, int v1, int v2) const {
+		const uint32_t r = tone8_top<RESCALE>(((uint32_t)v0 * 3968u) & 0xFFFFE000u, tone);
+		const uint32_t g = tone8_top<RESCALE>(((uint32_t)v1 * 3968u) & 0xFFFFE000u, tone);
+		const uint32_t b = tone8_top<RESCALE>(((uint32_t)v2 * 3968u) & 0xFFFFE000u, tone);
+		q[i] = tone8_pack(r, g, b);
 	}
+};
+
+// The 16-bit stage alone (target RGBX16): pixels R | G << 16, B | X << 16 with X the conversion of the
+// decoder's zero (FLOAT_RGBX16 -> RGBX16 converts all four components, convert.c:604-608).
+template <bool RESCALE>
+__device__ __forceinline__ uint32_t tone16_of_zero(const Tone &t) {
+	return tone16_bits<RESCALE>(0u, t) & 0xFFFFu;
+}
+template <bool RESCALE>
+struct Bc6hTone16Sink {
+	uint32_t (&q)[32];
+	const Tone &tone;
+	uint32_t x16;
+	__device__ __forceinline__ void operator()(int i, int v0, int v1, int v2) const {
+		const uint32_t r = tone16_bits<RESCALE>(((uint32_t)v0 * 3968u) & 0xFFFFE000u, tone);
+		const uint32_t g = tone16_bits<RESCALE>(((uint32_t)v1 * 3968u) & 0xFFFFE000u, tone);
+		const uint32_t b = tone16_bits<RESCALE>(((uint32_t)v2 * 3968u) & 0xFFFFE000u, tone);
+		q[2 * i] = prmt(r, g, 0x5410);
+		q[2 * i + 1] = prmt(b, x16, 0x5410);
+	}
+};
+template <bool RESCALE>
+__device__ __forceinline__ bool decode_bptc_float_tone16(const uint4 blk, uint32_t mode_mask, const BptcTables &tab,
+const Tone &tone, uint32_t (&q)[32]) {
+	return decode_bptc_float_to<false>(blk, mode_mask, tab, Bc6hTone16Sink<RESCALE>{ q, tone, tone16_of_zero<RESCALE>(tone) });
+}
+
+// BPTC_FLOAT block -> 16 RGBX8 pixels in q[0..15].  Returns false for an invalid block (q is then undefined).
+template <bool RESCALE, int N>
+__device__ __forceinline__ bool decode_bptc_float_tone8(const uint4 blk, uint32_t mode_mask, const BptcTables &tab,
+const Tone &tone, uint32_t (&q)[N]) {
+	static_assert(N >= 16, "room for 16 pixels");
+	return decode_bptc_float_to<false>(blk, mode_mask, tab, Bc6hTone8Sink<N, RESCALE>{ q, tone });
 }
 
 }  // namespace detexb200

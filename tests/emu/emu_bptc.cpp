@@ -27,20 +27,70 @@ static void tables_init() {
 
 extern "C" {
 
-/* tone.cuh: n tiles of 16 FLOAT_RGBX16 pixels (128 bytes each) -> n tiles of 16 RGBX8 pixels (64 bytes),
-   the fused BC6H -> 8-bit chain with the given range parameters (hdr = 0: plain normalised half) */
-void emu_tone8_tiles(const uint8_t *tiles, int n, int hdr, float range_min, float range_max, uint8_t *out) {
+static Tone tone_of(int hdr, float range_min, float range_max) {
 	ToneArgs a;
 	a.range_min = range_min;
 	a.range_max = range_max;
 	a.hdr = (uint32_t)hdr;
 	a.zero_target = 0;
-	const Tone t = tone_setup(a);
+	return tone_setup(a);
+}
+
+/* tone.cuh, the per-component chain: n FLOAT_RGBX16 pixels (non-negative finite halves) -> n RGBX8
+   pixels with the given range parameters (hdr = 0: plain normalised half) */
+void emu_tone8_pixels(const uint8_t *pixels, int n, int hdr, float range_min, float range_max, uint8_t *out) {
+	const Tone t = tone_of(hdr, range_min, range_max);
 	for (int i = 0; i < n; i++) {
-		uint32_t px[32], q[16];
-		memcpy(px, tiles + 128 * (size_t)i, 128);
-		tone8_tile(px, q, t);
+		uint16_t h[4];
+		memcpy(h, pixels + 8 * (size_t)i, 8);
+		const uint32_t q = t.rescale
+			? tone8_pack(tone8_top<true>((uint32_t)h[0] << 13, t), tone8_top<true>((uint32_t)h[1] << 13, t),
+				tone8_top<true>((uint32_t)h[2] << 13, t))
+			: tone8_pack(tone8_top<false>((uint32_t)h[0] << 13, t), tone8_top<false>((uint32_t)h[1] << 13, t),
+				tone8_top<false>((uint32_t)h[2] << 13, t));
+		memcpy(out + 4 * (size_t)i, &q, 4);
+	}
+}
+
+/* tone.cuh, the decoder with the 16-bit pixel sink: n BPTC_FLOAT blocks -> n tiles of 16 RGBX16 pixels; an
+   invalid block gets valid[i] = 0 and the conversion of zero pixels */
+void emu_bc6h_decode_tone16(const uint8_t *blocks, int n, int hdr, float range_min, float range_max, uint8_t *out,
+uint8_t *valid) {
+	tables_init();
+	const Tone t = tone_of(hdr, range_min, range_max);
+	for (int i = 0; i < n; i++) {
+		uint4 w;
+		memcpy(&w, blocks + 16 * (size_t)i, 16);
+		uint32_t q[32];
+		const bool ok = t.rescale ? decode_bptc_float_tone16<true>(w, 0xFFFFFFFFu, g_tab.packed, t, q)
+					  : decode_bptc_float_tone16<false>(w, 0xFFFFFFFFu, g_tab.packed, t, q);
+		if (!ok) {
+			const uint32_t z = t.rescale ? tone16_of_zero<true>(t) : tone16_of_zero<false>(t);
+			for (int k = 0; k < 32; k++)
+				q[k] = z | (z << 16);
+		}
+		memcpy(out + 128 * (size_t)i, q, 128);
+		valid[i] = ok ? 1 : 0;
+	}
+}
+
+/* tone.cuh, the decoder with the 8-bit pixel sink: n BPTC_FLOAT blocks -> n tiles of 16 RGBX8 pixels;
+   an invalid block gets valid[i] = 0 and the conversion of zero pixels */
+void emu_bc6h_decode_tone8(const uint8_t *blocks, int n, int hdr, float range_min, float range_max, uint8_t *out,
+uint8_t *valid) {
+	tables_init();
+	const Tone t = tone_of(hdr, range_min, range_max);
+	for (int i = 0; i < n; i++) {
+		uint4 w;
+		memcpy(&w, blocks + 16 * (size_t)i, 16);
+		uint32_t q[16];
+		const bool ok = t.rescale ? decode_bptc_float_tone8<true>(w, 0xFFFFFFFFu, g_tab.packed, t, q)
+					  : decode_bptc_float_tone8<false>(w, 0xFFFFFFFFu, g_tab.packed, t, q);
+		if (!ok)
+			for (int k = 0; k < 16; k++)
+				q[k] = t.rescale ? tone8_of_zero<true>(t) : tone8_of_zero<false>(t);
 		memcpy(out + 64 * (size_t)i, q, 64);
+		valid[i] = ok ? 1 : 0;
 	}
 }
 

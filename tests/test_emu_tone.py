@@ -31,8 +31,12 @@ def emu(tmp_path_factory):
                     os.path.join(ROOT, "detex_b200", "csrc"), "-o", so, os.path.join(EMU, "emu_bptc.cpp")],
                    check=True)
     lib = C.CDLL(so)
-    lib.emu_tone8_tiles.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_void_p]
-    lib.emu_tone8_tiles.restype = None
+    lib.emu_tone8_pixels.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_void_p]
+    lib.emu_tone8_pixels.restype = None
+    lib.emu_bc6h_decode_tone8.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p]
+    lib.emu_bc6h_decode_tone8.restype = None
+    lib.emu_bc6h_decode_tone16.argtypes = lib.emu_bc6h_decode_tone8.argtypes
+    lib.emu_bc6h_decode_tone16.restype = None
     return lib
 
 
@@ -43,7 +47,7 @@ def cpu():
 
 def all_half_pixels():
     """FLOAT_RGBX16 pixels covering every non-negative finite half in each colour channel
-    (R ascending, G descending, B scrambled), X = 0 as the BC6H decoder writes it; padded to whole tiles"""
+    (R ascending, G descending, B scrambled), X = 0 as the BC6H decoder writes it"""
     n = 0x7C00
     h = np.arange(n, dtype=np.uint16)
     px = np.zeros((n, 4), dtype=np.uint16)
@@ -54,10 +58,9 @@ def all_half_pixels():
 
 
 def emu_tone(emu, src, n, hdr, lo, hi):
-    assert n % 16 == 0
     out = np.empty(n * 4, dtype=np.uint8)
     src = np.ascontiguousarray(src)
-    emu.emu_tone8_tiles(src.ctypes.data, n // 16, int(hdr), lo, hi, out.ctypes.data)
+    emu.emu_tone8_pixels(src.ctypes.data, n, int(hdr), lo, hi, out.ctypes.data)
     return out
 
 
@@ -82,3 +85,37 @@ def test_hdr_chain_every_half(emu, cpu, lo, hi):
     got = emu_tone(emu, src, n, 1, lo, hi)
     bad = np.flatnonzero(got != want)
     assert bad.size == 0, (lo, hi, bad[:8], got[bad[:8]], want[bad[:8]])
+
+
+@pytest.mark.parametrize("hdr,lo,hi", [(0, 0.0, 1.0), (1, 0.0, 2.0), (1, -1.0, 1.0), (1, 0.0, 65504.0)])
+def test_decoder_with_8bit_sink_matches_decode_then_convert(emu, cpu, hdr, lo, hi):
+    """the BC6H decoder writing through the 8-bit pixel sink == decode to FLOAT_RGBX16, then the
+    conversion chain; every mode (forced) and uniform bits (12.5 % invalid blocks)"""
+    for forced in (True, False):
+        b = H.synth_blocks("BPTC_FLOAT", 14 * 1024, seed=41)
+        if forced:
+            b = H.force_modes("BPTC_FLOAT", b)
+        n = b.size // 16
+        px, ok, _ = H.cpu_decode(cpu, "BPTC_FLOAT", b, 4 * n, 4, linear=False)
+        cpu.detexSetHDRParameters(1.0, lo, hi)
+        try:
+            ok_c, want = H.convert_pixels(cpu, px, n * 16, PF["FLOAT_RGBX16_HDR" if hdr else "FLOAT_RGBX16"], PF["RGBX8"])
+        finally:
+            cpu.detexSetHDRParameters(1.0, 0.0, 1.0)
+        assert ok_c
+        got = np.empty(n * 64, dtype=np.uint8)
+        valid = np.empty(n, dtype=np.uint8)
+        b = np.ascontiguousarray(b)
+        emu.emu_bc6h_decode_tone8(b.ctypes.data, n, hdr, lo, hi, got.ctypes.data, valid.ctypes.data)
+        assert np.array_equal(got, want), (hdr, lo, hi, forced)
+        assert bool(valid.all()) == ok
+        assert forced or not ok
+        # the 16-bit stage on its own (target RGBX16)
+        cpu.detexSetHDRParameters(1.0, lo, hi)
+        try:
+            ok_c, want16 = H.convert_pixels(cpu, px, n * 16, PF["FLOAT_RGBX16_HDR" if hdr else "FLOAT_RGBX16"], PF["RGBX16"])
+        finally:
+            cpu.detexSetHDRParameters(1.0, 0.0, 1.0)
+        got16 = np.empty(n * 128, dtype=np.uint8)
+        emu.emu_bc6h_decode_tone16(b.ctypes.data, n, hdr, lo, hi, got16.ctypes.data, valid.ctypes.data)
+        assert ok_c and np.array_equal(got16, want16), (hdr, lo, hi, forced)

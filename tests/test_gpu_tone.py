@@ -13,7 +13,7 @@ import detex_b200 as D  # noqa: E402
 from oracle import harness as H  # noqa: E402
 
 PF = H.PIXEL_FORMATS
-TARGETS_8BIT = ["RGBX8", "RGBA8", "BGRX8", "BGRA8", "RGB8"]
+TARGETS_8BIT = ["RGBX8", "RGBA8", "BGRX8", "BGRA8", "RGB8", "RGBX16"]      # (and the 16-bit stage on its own)
 # (w, h, layout, byte offset of the target): sorted kernel with several tiles per CTA, plain kernels,
 # clipped kernel, and a target that is only 16-byte aligned (falls back to decode + conversion pass)
 SHAPES = [(2048, 1536, D.LAYOUT_LINEAR, 0), (2048, 1536, D.LAYOUT_TILED, 0), (8192, 24, D.LAYOUT_LINEAR, 0),
@@ -94,8 +94,8 @@ HDR_SETS = [(1.0, 0.0, 1.0), (1.0, 0.0, 2.0), (1.0, -1.0, 1.0), (1.0, 0.25, 0.75
 @pytest.mark.parametrize("target", ["RGBX8", "BGRX8", "RGB8", "RGBX16"])
 def test_decode_hdr_device(gamma, lo, hi, target, oracle):
     """detexb200DecodeHDRDevice == decode + detexSetHDRParameters + detexConvertPixels(FLOAT_RGBX16_HDR -> target).
-    gamma 1 with an 8-bit target is one fused launch and bit-exact; gamma 2.2 goes through powf on both
-    sides and may differ by one integer step; RGBX16 is a two-pass target."""
+    gamma 1 is one fused launch and bit-exact; gamma 2.2 goes through the separate conversion pass, with
+    powf on both sides, and may differ by one integer step."""
     pf = PF[target]
     lib = D.lib.load()
     lib.detexSetHDRParameters.argtypes = [C.c_float, C.c_float, C.c_float]
@@ -113,8 +113,7 @@ def test_decode_hdr_device(gamma, lo, hi, target, oracle):
             assert ok == ok_w
             if gamma == 1.0:
                 assert np.array_equal(got, want), (gamma, lo, hi, target, w, h, layout)
-                if target != "RGBX16":
-                    assert launches == 1
+                assert launches == 1
             else:
                 dt = np.uint16 if target == "RGBX16" else np.uint8
                 assert np.abs(got.view(dt).astype(int) - want.view(dt).astype(int)).max() <= 1

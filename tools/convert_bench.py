@@ -47,14 +47,15 @@ def main():
               (a, b, ms * 1e3, n / ms / 1e6, gbs, 100 * gbs / peak))
     wib = hib = 2048
     nb = wib * hib
-    for fmt, target in (("BC1", None), ("BC1", "BGRA8"), ("BC1", "RGB8"), ("BPTC", "RGB8"), ("BPTC_FLOAT", None),
+    for fmt, target in (("BPTC_FLOAT", "hdr:RGBX8"), ("BC1", None), ("BC1", "BGRA8"), ("BC1", "RGB8"), ("BPTC", "RGB8"), ("BPTC_FLOAT", None),
                         ("BPTC_FLOAT", "FLOAT_RGB16"), ("BPTC_FLOAT", "RGBX8"), ("BPTC_FLOAT", "BGRA8"), ("BPTC_FLOAT", "RGB8"),
                         ("BPTC_FLOAT", "RGBX16"), ("EAC_RG11", "RG8"), ("BC3", "RGBA16")):
         if only and fmt not in only:
             continue
         tf = D.FORMATS[fmt]
         bs = D.block_size(tf)
-        pf = D.native_pixel_format(tf) if target is None else PF[target]
+        hdr = target is not None and target.startswith("hdr:")       # detexb200DecodeHDRDevice, range [0, 2]
+        pf = D.native_pixel_format(tf) if target is None else PF[target.split(":")[-1]]
         blocks = torch.empty(nb * bs, dtype=torch.uint8, device="cuda")
         D.generate_blocks_device(blocks.data_ptr(), nb, bs, seed=1, force_modes=(8 if fmt == "BPTC" else 14 if fmt == "BPTC_FLOAT" else 0))
         for layout, lname in ((D.LAYOUT_LINEAR, "linear"), (D.LAYOUT_TILED, "tiled")):
@@ -63,7 +64,11 @@ def main():
 
             def step():
                 k[0] += 1
-                D.decode_device(fmt, blocks.data_ptr(), wib * 4, hib * 4, out[k[0] % 3].data_ptr(), pixel_format=pf, layout=layout)
+                if hdr:
+                    D.decode_hdr_device(fmt, blocks.data_ptr(), wib * 4, hib * 4, out[k[0] % 3].data_ptr(), pf,
+                                        gamma=1.0, range_min=0.0, range_max=2.0, layout=layout)
+                else:
+                    D.decode_device(fmt, blocks.data_ptr(), wib * 4, hib * 4, out[k[0] % 3].data_ptr(), pixel_format=pf, layout=layout)
             ms = timed(step, args.steps)
             gbs = nb * (bs + 16 * pixel_size(pf)) / ms / 1e6
             print("decode  %-10s -> %-12s %-6s %8.1f us  %6.2f Gblk/s  %6.0f GB/s  %5.1f%% of measured peak" %
