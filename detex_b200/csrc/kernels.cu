@@ -377,15 +377,15 @@ __device__ __forceinline__ void store_linear_rows(uint8_t *dst, size_t pitch, in
 				st_stream_u32(p + 8, px[3 * r + 2]);
 			}
 			else if constexpr (ROW_WORDS == 4)
-				st_stream_v4(p, px[4 * r], px[4 * r + 1], px[4 * r + 2], px[4 * r + 3]);
+				st_part_v4(p, px[4 * r], px[4 * r + 1], px[4 * r + 2], px[4 * r + 3]);
 			else if constexpr (ROW_WORDS == 6) {		// 24-byte FLOAT_RGB16 rows: 16 + 8 or 8 + 16 bytes
 				if ((((uintptr_t)p) & 15u) == 0) {
-					st_stream_v4(p, px[6 * r], px[6 * r + 1], px[6 * r + 2], px[6 * r + 3]);
-					st_stream_v2(p + 16, px[6 * r + 4], px[6 * r + 5]);
+					st_part_v4(p, px[6 * r], px[6 * r + 1], px[6 * r + 2], px[6 * r + 3]);
+					st_part_v2(p + 16, px[6 * r + 4], px[6 * r + 5]);
 				}
 				else {
-					st_stream_v2(p, px[6 * r], px[6 * r + 1]);
-					st_stream_v4(p + 8, px[6 * r + 2], px[6 * r + 3], px[6 * r + 4], px[6 * r + 5]);
+					st_part_v2(p, px[6 * r], px[6 * r + 1]);
+					st_part_v4(p + 8, px[6 * r + 2], px[6 * r + 3], px[6 * r + 4], px[6 * r + 5]);
 				}
 			}
 			else if (wide_ok)
@@ -1472,8 +1472,13 @@ static cudaError_t launch_format(const DecodeArgs &a, cudaStream_t stream) {
 				launch_sorted_pad<F, LAYOUT_TILED, false, PC>(pad, src, dst, (uint32_t)n_blocks, a, stream);
 			else if (a.layout == LAYOUT_TILED)
 				launch_sorted<F, LAYOUT_TILED, ST, PC_NATIVE>(src, dst, (uint32_t)n_blocks, a, stream);
-			else if constexpr (is_tone_class(PC))
-				launch_sorted<F, LAYOUT_LINEAR, true, PC>(src, dst, (uint32_t)n_blocks, a, stream);
+			else if constexpr (is_tone_class(PC)) {
+				static const bool stage = [] { const char *e = getenv("DETEXB200_TONE_STAGE"); return !(e && e[0] == '0'); }();
+				if (stage)
+					launch_sorted<F, LAYOUT_LINEAR, true, PC>(src, dst, (uint32_t)n_blocks, a, stream);
+				else
+					launch_sorted<F, LAYOUT_LINEAR, false, PC>(src, dst, (uint32_t)n_blocks, a, stream);
+			}
 			else
 				launch_sorted_pad<F, LAYOUT_LINEAR, ST, PC>(pad, src, dst, (uint32_t)n_blocks, a, stream);
 			count_launch();
