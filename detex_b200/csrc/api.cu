@@ -8,6 +8,7 @@
 //                          CUDA device is usable every call fails with an error message.
 #include <cstdarg>
 #include <cstdio>
+#include <cmath>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -153,7 +154,9 @@ cudaStream_t stream, bool hdr = false) {
 	a.invalid_map = nullptr;
 	a.tone_min = 0.0f;
 	a.tone_max = 1.0f;
-	a.tone_hdr = 0;
+	a.tone_inv_gamma = 1.0f;
+	a.tone_gamma_lo = 0.0f;
+	a.tone_gamma_factor = 1.0f;
 	a.tone_zero_target = hdr ? 0u : 1u;
 	cudaError_t e;
 	// Conversions the kernels do while storing: R<->B swap, sign flip, dropping the fourth component,
@@ -163,11 +166,19 @@ cudaStream_t stream, bool hdr = false) {
 		a.post_op = fuse.post_op;
 		a.post_class = fuse.post_class;
 		if (fuse.tone_hdr) {
+			// which variant of the tone kernels (tone.cuh): plain, HDR range, HDR range + gamma
 			float gamma;
 			get_hdr_parameters(&gamma, &a.tone_min, &a.tone_max);
-			a.tone_hdr = 1;
-			if (!(a.tone_min == 0.0f && a.tone_max == 1.0f))	// hdr.c:124-131; the rescaling variants of the kernels
-				a.post_class += a.post_class == 7 ? 1 : 2;
+			if (gamma != 1.0f) {
+				// corrected range as hdr.c:149-158 computes it (host powf, sign kept)
+				auto spow = [](float v, float ex) { return v >= 0.0f ? powf(v, ex) : -powf(-v, ex); };
+				a.tone_inv_gamma = 1.0f / gamma;
+				a.tone_gamma_lo = spow(a.tone_min, a.tone_inv_gamma);
+				a.tone_gamma_factor = 1.0f / (spow(a.tone_max, a.tone_inv_gamma) - a.tone_gamma_lo);
+				a.post_class += 6;
+			}
+			else if (!(a.tone_min == 0.0f && a.tone_max == 1.0f))	// hdr.c:124-131
+				a.post_class += 3;
 		}
 		a.pixels = d_pixels;
 		if ((e = launch_decode((int)(tf >> 24), a, stream)) != cudaSuccess)

@@ -63,29 +63,6 @@ uint32_t e, uint32_t f, uint32_t g, uint32_t h) {
 __device__ __forceinline__ void st_stream_v2(void *p, uint32_t a, uint32_t b) {
 	asm volatile("st.global.cs.v2.u32 [%0], {%1, %2};" :: "l"(p), "r"(a), "r"(b) : "memory");
 }
-// Stores that cover only part of a 32-byte sector and whose neighbours arrive later from other
-// warps (rows of mode-sorted blocks): experiment switch for the cache policy.
-#ifndef DETEXB200_PARTIAL_ST
-#define DETEXB200_PARTIAL_ST 0
-#endif
-__device__ __forceinline__ void st_part_v4(void *p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-#if DETEXB200_PARTIAL_ST == 0
-	asm volatile("st.global.cs.v4.u32 [%0], {%1, %2, %3, %4};" :: "l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
-#elif DETEXB200_PARTIAL_ST == 1
-	asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" :: "l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
-#else
-	asm volatile("st.global.L1::no_allocate.L2::evict_last.v4.u32 [%0], {%1, %2, %3, %4};" :: "l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
-#endif
-}
-__device__ __forceinline__ void st_part_v2(void *p, uint32_t a, uint32_t b) {
-#if DETEXB200_PARTIAL_ST == 0
-	asm volatile("st.global.cs.v2.u32 [%0], {%1, %2};" :: "l"(p), "r"(a), "r"(b) : "memory");
-#elif DETEXB200_PARTIAL_ST == 1
-	asm volatile("st.global.v2.u32 [%0], {%1, %2};" :: "l"(p), "r"(a), "r"(b) : "memory");
-#else
-	asm volatile("st.global.L1::no_allocate.L2::evict_last.v2.u32 [%0], {%1, %2};" :: "l"(p), "r"(a), "r"(b) : "memory");
-#endif
-}
 __device__ __forceinline__ void st_stream_u32(void *p, uint32_t a) {
 	asm volatile("st.global.cs.u32 [%0], %1;" :: "l"(p), "r"(a) : "memory");
 }

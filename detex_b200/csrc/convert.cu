@@ -178,9 +178,10 @@ void get_hdr_parameters(float *gamma, float *range_min, float *range_max) {
 // "post class"): relabelling steps anywhere, at most one R <-> B swap of four-component pixels, at
 // most one sign flip, and -- last -- at most one step that shrinks the pixel: dropping the fourth
 // component, or narrowing one / two 16-bit components to 8 bits.
-// BC6H's way to 8-bit pixels is a class of its own (tone.cuh): FLOAT_RGBX16[_HDR] -> RGBX16 -> RGBX8,
-// after which relabelling, one R <-> B swap and dropping X may still follow.  With the HDR source
-// format the range parameters of the calling thread apply; gamma other than 1 is not fused.
+// BC6H's way to integer pixels is a class of its own (tone.cuh): FLOAT_RGBX16[_HDR] -> RGBX16 (class 5),
+// -> RGBX8 (class 3), after which relabelling, one R <-> B swap and dropping X (class 4) may still
+// follow.  With the HDR source format the parameters of the calling thread apply (tone_hdr; the
+// caller adds 3 * mode to the class).
 // DETEXB200_TONE_FUSION=0 in the environment sends the BC6H -> 8-bit targets through the separate
 // conversion pass instead (A/B measurements).
 static bool tone_fusion() {
@@ -219,22 +220,16 @@ FusedConversion convert_fused(uint32_t s, uint32_t d) {
 			return f;				// nothing may follow the size change
 		if ((e.op == ST_HALF_TO_INT || e.op == ST_HALF_HDR_TO_INT) && e.target == PF_RGBX16 && f.post_op == 0u && tone_fusion() &&
 		    i + 1 == n && f.post_class == 0) {	// the 16-bit stage on its own: target RGBX16
-			if (e.op == ST_HALF_HDR_TO_INT) {
-				if (g_hdr.gamma != 1.0f)
-					return f;
+			if (e.op == ST_HALF_HDR_TO_INT)
 				f.tone_hdr = true;
-			}
-			f.post_class = 7;
+			f.post_class = 5;
 			shrunk = true;
 			continue;
 		}
 		if ((e.op == ST_HALF_TO_INT || e.op == ST_HALF_HDR_TO_INT) && e.target == PF_RGBX16 && f.post_op == 0u && tone_fusion() &&
 		    i + 1 < n && conversion_table[steps[i + 1]].op == ST_NARROW && conversion_table[steps[i + 1]].target == PF_RGBX8) {
-			if (e.op == ST_HALF_HDR_TO_INT) {
-				if (g_hdr.gamma != 1.0f)
-					return f;
+			if (e.op == ST_HALF_HDR_TO_INT)
 				f.tone_hdr = true;
-			}
 			f.post_class = 3;
 			toned = true;
 			i++;

@@ -98,19 +98,20 @@ uint32_t mode_mask, uint32_t flags, const BptcTables *tab, uint32_t (&px)[Format
 //                   FLOAT_RGBX16 -> FLOAT_RGB16 (convert.c:700-716);
 //     PC_NARROW     16-bit -> 8-bit components (v + 127) * 255 / 65535: R16 -> R8, RG16 -> RG8
 //                   (convert.c:263-290);
-//     PC_TONE8      BC6H only: half -> 16-bit integer (optionally rescaled by the HDR range) -> 8 bit,
-//                   FLOAT_RGBX16 -> RGBX8 / RGBA8 (tone.cuh); POST_SWAP_RB then acts
-//                   on the 8-bit pixels (-> BGRX8 / BGRA8);
-//     PC_TONE8_PACK3  the same followed by dropping the fourth component (-> RGB8);
-//     PC_TONE8R, PC_TONE8R_PACK3  the two above with the HDR range rescaling compiled in;
-//     PC_TONE16, PC_TONE16R     BC6H only: the 16-bit stage alone, FLOAT_RGBX16 -> RGBX16 (same tile size).
+//     tone classes  BC6H only (tone.cuh): half -> 16-bit integer -> 8 bit.  Class =
+//                   PC_TONE_FIRST + 3 * mode + kind, mode = TONE_PLAIN / TONE_RANGE / TONE_GAMMA (how the
+//                   half becomes an integer), kind = TONE_RGBX8 (FLOAT_RGBX16 -> RGBX8 / RGBA8; POST_SWAP_RB
+//                   then acts on the 8-bit pixels -> BGRX8 / BGRA8), TONE_RGB8 (the same, fourth component
+//                   dropped) or TONE_RGBX16 (the 16-bit stage alone, same tile size as native).
 constexpr uint32_t POST_NONE = 0, POST_SWAP_RB = 1, POST_FLIP16 = 2, POST_FLIP8 = 4;
-constexpr int PC_NATIVE = 0, PC_PACK3 = 1, PC_NARROW = 2, PC_TONE8 = 3, PC_TONE8_PACK3 = 4, PC_TONE8R = 5, PC_TONE8R_PACK3 = 6,
-	PC_TONE16 = 7, PC_TONE16R = 8;
-constexpr bool is_tone_class(int pc) { return pc >= PC_TONE8 && pc <= PC_TONE8R_PACK3; }	// the 8-bit ones
-constexpr bool is_tone16_class(int pc) { return pc == PC_TONE16 || pc == PC_TONE16R; }
-constexpr bool tone_rescales(int pc) { return pc == PC_TONE8R || pc == PC_TONE8R_PACK3 || pc == PC_TONE16R; }
-constexpr bool tone_packs3(int pc) { return pc == PC_TONE8_PACK3 || pc == PC_TONE8R_PACK3; }
+constexpr int PC_NATIVE = 0, PC_PACK3 = 1, PC_NARROW = 2, PC_TONE_FIRST = 3, PC_TONE_LAST = 11;
+constexpr int TONE_RGBX8 = 0, TONE_RGB8 = 1, TONE_RGBX16 = 2;
+constexpr bool is_tone_any(int pc) { return pc >= PC_TONE_FIRST && pc <= PC_TONE_LAST; }
+constexpr int tone_kind(int pc) { return (pc - PC_TONE_FIRST) % 3; }
+constexpr int tone_mode(int pc) { return (pc - PC_TONE_FIRST) / 3; }
+constexpr bool is_tone_class(int pc) { return is_tone_any(pc) && tone_kind(pc) != TONE_RGBX16; }	// the 8-bit ones
+constexpr bool is_tone16_class(int pc) { return is_tone_any(pc) && tone_kind(pc) == TONE_RGBX16; }
+constexpr bool tone_packs3(int pc) { return is_tone_any(pc) && tone_kind(pc) == TONE_RGB8; }
 
 template <int OW>
 __device__ __forceinline__ void apply_post_op(uint32_t (&px)[OW], uint32_t post_op) {
@@ -151,7 +152,7 @@ template <int F, int PC> constexpr bool post_class_valid() {
 		return true;
 	if (PC == PC_PACK3)
 		return (OW == 16 && F != F_EAC_RG11 && F != F_EAC_SIGNED_RG11 && F != F_SIGNED_RGTC2) || F == F_BPTC_FLOAT;
-	if (is_tone_class(PC) || is_tone16_class(PC))
+	if (is_tone_any(PC))
 		return F == F_BPTC_FLOAT;
 	return F == F_EAC_R11 || F == F_EAC_SIGNED_R11 || F == F_EAC_RG11 || F == F_EAC_SIGNED_RG11 ||
 		F == F_SIGNED_RGTC1 || F == F_SIGNED_RGTC2;
@@ -198,24 +199,19 @@ __device__ __forceinline__ void repack(const uint32_t (&px)[OW], uint32_t (&q)[p
 // What the tone classes need besides the pixels: the (uniform) tone parameters and whether the block
 // was valid -- an invalid block is zero in the target format or the conversion of zero pixels,
 // ToneArgs::zero_target.  Empty for every other class.
-template <int PC> struct EmitCtx { __device__ __forceinline__ EmitCtx(const ToneArgs &) {} };
-struct EmitCtxTone {
+template <int PC, bool TONE = is_tone_any(PC)> struct EmitCtxImpl { __device__ __forceinline__ EmitCtxImpl(const ToneArgs &) {} };
+template <int PC> struct EmitCtxImpl<PC, true> {
 	Tone tone;
 	bool zero_target;
-	__device__ __forceinline__ EmitCtxTone(const ToneArgs &a) : tone(tone_setup(a)), zero_target(a.zero_target != 0u) {}
+	__device__ __forceinline__ EmitCtxImpl(const ToneArgs &a) : tone(tone_setup<tone_mode(PC)>(a)), zero_target(a.zero_target != 0u) {}
 };
-template <> struct EmitCtx<PC_TONE8> : EmitCtxTone { using EmitCtxTone::EmitCtxTone; };
-template <> struct EmitCtx<PC_TONE8_PACK3> : EmitCtxTone { using EmitCtxTone::EmitCtxTone; };
-template <> struct EmitCtx<PC_TONE8R> : EmitCtxTone { using EmitCtxTone::EmitCtxTone; };
-template <> struct EmitCtx<PC_TONE8R_PACK3> : EmitCtxTone { using EmitCtxTone::EmitCtxTone; };
-template <> struct EmitCtx<PC_TONE16> : EmitCtxTone { using EmitCtxTone::EmitCtxTone; };
-template <> struct EmitCtx<PC_TONE16R> : EmitCtxTone { using EmitCtxTone::EmitCtxTone; };
+template <int PC> using EmitCtx = EmitCtxImpl<PC>;
 
 // Tone classes: the decoder's pixel sink has already produced 16 RGBX8 pixels in px[0..15]
 // (decode_px below).  What is left: the invalid rule and the R <-> B swap.
 template <int PC>
 __device__ __forceinline__ void tone_tile(const uint32_t (&px)[32], uint32_t (&t)[16], uint32_t post_op, const EmitCtx<PC> &ctx, bool ok) {
-	const uint32_t fill = ctx.zero_target ? 0u : tone8_of_zero<tone_rescales(PC)>(ctx.tone);
+	const uint32_t fill = ctx.zero_target ? 0u : tone8_of_zero<tone_mode(PC)>(ctx.tone);
 #pragma unroll
 	for (int k = 0; k < 16; k++)
 		t[k] = ok ? px[k] : fill;
@@ -227,9 +223,9 @@ template <int F, int PC, int PATHS = ETC_PATHS_ALL>
 __device__ __forceinline__ bool decode_px(const typename BlockReg<FormatTraits<F>::BLOCK_WORDS>::type &blk,
 uint32_t mode_mask, uint32_t flags, const BptcTables *tab, const EmitCtx<PC> &ctx, uint32_t (&px)[FormatTraits<F>::OUT_WORDS]) {
 	if constexpr (is_tone_class(PC))
-		return decode_bptc_float_tone8<tone_rescales(PC)>(blk, mode_mask, *tab, ctx.tone, px);
+		return decode_bptc_float_tone8<tone_mode(PC)>(blk, mode_mask, *tab, ctx.tone, px);
 	else if constexpr (is_tone16_class(PC))
-		return decode_bptc_float_tone16<tone_rescales(PC)>(blk, mode_mask, *tab, ctx.tone, px);
+		return decode_bptc_float_tone16<tone_mode(PC)>(blk, mode_mask, *tab, ctx.tone, px);
 	else
 		return decode_block<F, PATHS>(blk, mode_mask, flags, tab, px);
 }
@@ -253,7 +249,7 @@ __device__ __forceinline__ void emit(uint32_t (&px)[OW], uint32_t post_op, const
 	else if constexpr (is_tone16_class(PC)) {
 		// the pixel sink wrote RGBX16 pixels; an invalid block is zero or the conversion of zero pixels
 		if (!ok) {
-			const uint32_t z = ctx.zero_target ? 0u : tone16_of_zero<tone_rescales(PC)>(ctx.tone);
+			const uint32_t z = ctx.zero_target ? 0u : tone16_of_zero<tone_mode(PC)>(ctx.tone);
 #pragma unroll
 			for (int k = 0; k < OW; k++)
 				px[k] = z | (z << 16);
@@ -377,15 +373,15 @@ __device__ __forceinline__ void store_linear_rows(uint8_t *dst, size_t pitch, in
 				st_stream_u32(p + 8, px[3 * r + 2]);
 			}
 			else if constexpr (ROW_WORDS == 4)
-				st_part_v4(p, px[4 * r], px[4 * r + 1], px[4 * r + 2], px[4 * r + 3]);
+				st_stream_v4(p, px[4 * r], px[4 * r + 1], px[4 * r + 2], px[4 * r + 3]);
 			else if constexpr (ROW_WORDS == 6) {		// 24-byte FLOAT_RGB16 rows: 16 + 8 or 8 + 16 bytes
 				if ((((uintptr_t)p) & 15u) == 0) {
-					st_part_v4(p, px[6 * r], px[6 * r + 1], px[6 * r + 2], px[6 * r + 3]);
-					st_part_v2(p + 16, px[6 * r + 4], px[6 * r + 5]);
+					st_stream_v4(p, px[6 * r], px[6 * r + 1], px[6 * r + 2], px[6 * r + 3]);
+					st_stream_v2(p + 16, px[6 * r + 4], px[6 * r + 5]);
 				}
 				else {
-					st_part_v2(p, px[6 * r], px[6 * r + 1]);
-					st_part_v4(p + 8, px[6 * r + 2], px[6 * r + 3], px[6 * r + 4], px[6 * r + 5]);
+					st_stream_v2(p, px[6 * r], px[6 * r + 1]);
+					st_stream_v4(p + 8, px[6 * r + 2], px[6 * r + 3], px[6 * r + 4], px[6 * r + 5]);
 				}
 			}
 			else if (wide_ok)
@@ -718,9 +714,15 @@ template <> struct SortTraits<F_BPTC_SIGNED_FLOAT> : SortTraitsBc6h {};
 // parked); every other class stages the decoder's native tile.  A kernel that stages needs 64 bytes of
 // shared memory per block on top of the double-buffered input, which fits two CTAs per SM with tiles
 // of 1024 blocks.
-template <int F, int PC> constexpr int stage_words() { return is_tone_class(PC) ? 16 : FormatTraits<F>::OUT_WORDS; }
-template <int F, bool STAGE> constexpr int sort_tile() {
-	return (STAGE && SortTraits<F>::TILE_BLOCKS > 1024) ? 1024 : SortTraits<F>::TILE_BLOCKS;
+// BC6H -> FLOAT_RGB16 stages the packed 96-byte tile (24-byte rows are partial sectors whichever lane
+// writes them) in tiles of 512 blocks, which keeps two CTAs per SM.
+template <int F, int PC> constexpr bool stages_packed_half3() { return F == F_BPTC_FLOAT && PC == PC_PACK3; }
+template <int F, int PC> constexpr int stage_words() {
+	return is_tone_class(PC) ? 16 : (stages_packed_half3<F, PC>() ? 24 : FormatTraits<F>::OUT_WORDS);
+}
+template <int F, int PC, bool STAGE> constexpr int sort_tile() {
+	return (STAGE && stages_packed_half3<F, PC>()) ? 512 :
+		((STAGE && SortTraits<F>::TILE_BLOCKS > 1024) ? 1024 : SortTraits<F>::TILE_BLOCKS);
 }
 
 constexpr int SORT_THREADS = 512, SORT_WARPS = SORT_THREADS / 32;
@@ -742,7 +744,7 @@ __device__ __forceinline__ uint32_t stage_slot(uint32_t id, uint32_t c) {
 
 template <int F, int PC, bool STAGE>
 struct SortedSmem {
-	static constexpr int TB = sort_tile<F, STAGE>(), NB = SortTraits<F>::NUM_BINS, CAP = TB + NB * 32;
+	static constexpr int TB = sort_tile<F, PC, STAGE>(), NB = SortTraits<F>::NUM_BINS, CAP = TB + NB * 32;
 	static constexpr int CHUNKS = stage_words<F, PC>() / 4;		// 16-byte chunks per staged tile
 	uint4 out[(SortTraits<F>::STAGE_OUTPUT || STAGE) ? TB * CHUNKS : 1];	// staged pixels (stage_slot layout)
 	uint4 raw[2][TB];		// double-buffered compressed tile, filled by cp.async
@@ -897,6 +899,14 @@ ToneArgs tone_args) {
 					for (int c = 0; c < 4; c++)
 						sm.out[stage_slot<TB, 4>(id, c)] = make_uint4(t[4 * c], t[4 * c + 1], t[4 * c + 2], t[4 * c + 3]);
 				}
+				else if constexpr (STAGE && stages_packed_half3<F, PC>()) {
+					apply_post_op<OW>(px, post_op);
+					uint32_t q[24];
+					repack<PC_PACK3, 32>(px, q);
+#pragma unroll
+					for (int c = 0; c < 6; c++)
+						sm.out[stage_slot<TB, 6>(id, c)] = make_uint4(q[4 * c], q[4 * c + 1], q[4 * c + 2], q[4 * c + 3]);
+				}
 				else if constexpr (STAGE) {
 					// staged in the native layout; a post class is applied by the copy-out below
 					apply_post_op<OW>(px, post_op);
@@ -936,8 +946,41 @@ ToneArgs tone_args) {
 		// ---- store
 		constexpr bool PACK_ROWS = (PC == PC_PACK3 && OW == 16) || tone_packs3(PC);	// RGBX8 stage -> RGB8 rows
 		static_assert(!STAGE || PC == PC_NATIVE || (is_tone_class(PC) && LAYOUT == LAYOUT_LINEAR) ||
-			(PACK_ROWS && LAYOUT == LAYOUT_LINEAR), "staged copy-out repacks RGB8 rows only");
-		if (LAYOUT == LAYOUT_TILED) {
+			(PACK_ROWS && LAYOUT == LAYOUT_LINEAR) || (stages_packed_half3<F, PC>() && LAYOUT == LAYOUT_LINEAR),
+			"staged copy-out repacks RGB8 rows only");
+		if constexpr (stages_packed_half3<F, PC>() && LAYOUT == LAYOUT_LINEAR) {
+			// 24-byte rows out of packed 96-byte tiles, in 8-byte pieces: piece q = id * 3 + j of pixel row r
+			// lies at byte 24 r + 8 j of its tile and at row_base + 8 q of the image row, so a warp's 32
+			// pieces are 256 contiguous bytes of the image
+			const size_t pitch = (size_t)width * 6;
+			const uint32_t by0 = tile0 / (uint32_t)wib, bx0 = tile0 - by0 * (uint32_t)wib;	// uniform
+			uint8_t *const row0 = dst + (size_t)by0 * 4 * pitch;
+			const uint8_t *const stage_bytes = reinterpret_cast<const uint8_t *>(sm.out);
+#pragma unroll
+			for (int k = 0; k < TB * 3 / SORT_THREADS; k++) {
+				const uint32_t q = k * SORT_THREADS + tid, id = q / 3u, j = q - id * 3u;
+				if (id < n_here) {
+					uint32_t bx = bx0 + id, by = by0;
+					while (bx >= (uint32_t)wib) {	// tiles may wrap over block rows
+						bx -= (uint32_t)wib;
+						by++;
+					}
+					uint8_t *out = row0 + (size_t)(by - by0) * 4 * pitch + bx * 24u + j * 8u;
+					const int rows = height - (int)by * 4;	// >= 4 except in a clipped last block row
+#pragma unroll
+					for (int r = 0; r < 4; r++) {
+						if (r < rows) {
+							const uint32_t byte = 24u * r + 8u * j;
+							const uint2 v = *reinterpret_cast<const uint2 *>(stage_bytes +
+								(size_t)stage_slot<TB, 6>(id, byte >> 4) * 16 + (byte & 8u));
+							st_stream_v2(out, v.x, v.y);
+						}
+						out += pitch;
+					}
+				}
+			}
+		}
+		else if (LAYOUT == LAYOUT_TILED) {
 			uint8_t *out = dst + (size_t)tile0 * (CHUNKS * 16);
 			for (uint32_t q = tid; q < n_here * CHUNKS; q += SORT_THREADS) {
 				const uint4 v = sm.out[stage_slot<TB, CHUNKS>(q / CHUNKS, q % CHUNKS)];
@@ -1365,12 +1408,10 @@ static bool tiled_direct() {
 // the unsigned direct-store kernels run unpadded (measured, G blocks/s LINEAR / TILED, padded -> unpadded:
 // distribution M 25.2 / 24.4 -> 26.5 / 25.9, U 27.3 / 26.5 -> 27.0 / 26.2); the signed format loses
 // 5-12 % without padding and the staged tone kernels 6 % (1024-block tiles: 20.2 -> 18.9), so they keep 32.
-// DETEXB200_BC6H_PAD=32|1 overrides the choice for unsigned BC6H (A/B measurements).
-template <int F> static int sort_pad() {
-	if (F != F_BPTC_FLOAT)
-		return 32;
-	static const int v = [] { const char *e = getenv("DETEXB200_BC6H_PAD"); return e ? atoi(e) : 1; }();
-	return v;
+// The staged FLOAT_RGB16 kernel (512-block tiles: 14 padded bins would leave 43 % of the lanes idle) also
+// runs unpadded.
+template <int F, int PC, bool STAGE> constexpr int sort_pad() {
+	return (F == F_BPTC_FLOAT && (!STAGE || stages_packed_half3<F, PC>())) ? 1 : 32;
 }
 
 // One instantiation of the sorted kernel: opt in to > 48 KiB of dynamic shared memory once per
@@ -1379,7 +1420,9 @@ static ToneArgs tone_args_of(const DecodeArgs &a) {
 	ToneArgs t;
 	t.range_min = a.tone_min;
 	t.range_max = a.tone_max;
-	t.hdr = a.tone_hdr;
+	t.inv_gamma = a.tone_inv_gamma;
+	t.gamma_lo = a.tone_gamma_lo;
+	t.gamma_factor = a.tone_gamma_factor;
 	t.zero_target = a.tone_zero_target;
 	return t;
 }
@@ -1400,17 +1443,6 @@ static void launch_sorted(const uint8_t *src, uint8_t *dst, uint32_t n_blocks, c
 	}
 	decode_sorted_kernel<F, LAYOUT, STAGE, PC, PAD><<<grid, SORT_THREADS, smem, stream>>>(src, dst, n_blocks,
 		a.width, a.height, a.wib, a.mode_mask, a.flags, a.post_op, a.invalid, a.invalid_map, tone_args_of(a));
-}
-
-template <int F, int LAYOUT, bool STAGE, int PC>
-static void launch_sorted_pad(int pad, const uint8_t *src, uint8_t *dst, uint32_t n_blocks, const DecodeArgs &a, cudaStream_t stream) {
-	if constexpr (F == F_BPTC_FLOAT) {
-		if (pad == 1) {
-			launch_sorted<F, LAYOUT, STAGE, PC, 1>(src, dst, n_blocks, a, stream);
-			return;
-		}
-	}
-	launch_sorted<F, LAYOUT, STAGE, PC, 32>(src, dst, n_blocks, a, stream);
 }
 
 // DETEXB200_BC7_KERNEL=flow selects the palette-staged dataflow kernel for BC7 instead of
@@ -1467,20 +1499,22 @@ static cudaError_t launch_format(const DecodeArgs &a, cudaStream_t stream) {
 			// order: those tiles (BC7, the toned BC6H classes) are staged and copied out in image order
 			// (measured for the toned classes: staged 20.2 G blocks/s, direct 15.3)
 			constexpr bool ST = SortTraits<F>::STAGE_OUTPUT;
-			const int pad = sort_pad<F>();
 			if (a.layout == LAYOUT_TILED && (PC != PC_NATIVE || (tiled_direct() && aligned32)))
-				launch_sorted_pad<F, LAYOUT_TILED, false, PC>(pad, src, dst, (uint32_t)n_blocks, a, stream);
+				launch_sorted<F, LAYOUT_TILED, false, PC, sort_pad<F, PC, false>()>(src, dst, (uint32_t)n_blocks, a, stream);
 			else if (a.layout == LAYOUT_TILED)
-				launch_sorted<F, LAYOUT_TILED, ST, PC_NATIVE>(src, dst, (uint32_t)n_blocks, a, stream);
-			else if constexpr (is_tone_class(PC)) {
-				static const bool stage = [] { const char *e = getenv("DETEXB200_TONE_STAGE"); return !(e && e[0] == '0'); }();
-				if (stage)
-					launch_sorted<F, LAYOUT_LINEAR, true, PC>(src, dst, (uint32_t)n_blocks, a, stream);
-				else
-					launch_sorted<F, LAYOUT_LINEAR, false, PC>(src, dst, (uint32_t)n_blocks, a, stream);
+				launch_sorted<F, LAYOUT_TILED, ST, PC_NATIVE, sort_pad<F, PC_NATIVE, ST>()>(src, dst, (uint32_t)n_blocks, a, stream);
+			else {
+				constexpr bool STL = ST || is_tone_class(PC) || stages_packed_half3<F, PC>();
+				static const bool stage_half3 = [] { const char *e = getenv("DETEXB200_HALF3_STAGE"); return !(e && e[0] == '0'); }();
+				if constexpr (stages_packed_half3<F, PC>()) {
+					if (!stage_half3) {	// A/B: direct 24-byte row stores (partial sectors)
+						launch_sorted<F, LAYOUT_LINEAR, false, PC, 1>(src, dst, (uint32_t)n_blocks, a, stream);
+						count_launch();
+						return cudaGetLastError();
+					}
+				}
+				launch_sorted<F, LAYOUT_LINEAR, STL, PC, sort_pad<F, PC, STL>()>(src, dst, (uint32_t)n_blocks, a, stream);
 			}
-			else
-				launch_sorted_pad<F, LAYOUT_LINEAR, ST, PC>(pad, src, dst, (uint32_t)n_blocks, a, stream);
 			count_launch();
 			return cudaGetLastError();
 		}
@@ -1548,19 +1582,14 @@ static cudaError_t launch_classes(const DecodeArgs &a, cudaStream_t stream) {
 		if (a.post_class == PC_NARROW)
 			return launch_format<F, PC_NARROW>(a, stream);
 	}
-	if constexpr (post_class_valid<F, PC_TONE8>()) {
-		if (a.post_class == PC_TONE8)
-			return launch_format<F, PC_TONE8>(a, stream);
-		if (a.post_class == PC_TONE8_PACK3)
-			return launch_format<F, PC_TONE8_PACK3>(a, stream);
-		if (a.post_class == PC_TONE8R)
-			return launch_format<F, PC_TONE8R>(a, stream);
-		if (a.post_class == PC_TONE8R_PACK3)
-			return launch_format<F, PC_TONE8R_PACK3>(a, stream);
-		if (a.post_class == PC_TONE16)
-			return launch_format<F, PC_TONE16>(a, stream);
-		if (a.post_class == PC_TONE16R)
-			return launch_format<F, PC_TONE16R>(a, stream);
+	if constexpr (post_class_valid<F, PC_TONE_FIRST>()) {
+		switch (a.post_class) {
+#define DETEX_TONE_CASE(K) case PC_TONE_FIRST + K: return launch_format<F, PC_TONE_FIRST + K>(a, stream);
+		DETEX_TONE_CASE(0) DETEX_TONE_CASE(1) DETEX_TONE_CASE(2) DETEX_TONE_CASE(3) DETEX_TONE_CASE(4)
+		DETEX_TONE_CASE(5) DETEX_TONE_CASE(6) DETEX_TONE_CASE(7) DETEX_TONE_CASE(8)
+#undef DETEX_TONE_CASE
+		default: break;
+		}
 	}
 	return cudaErrorInvalidValue;
 }

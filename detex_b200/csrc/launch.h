@@ -16,14 +16,14 @@ struct DecodeArgs {
 	uint32_t mode_mask, flags;
 	uint32_t post_op;	// bit 0: R<->B swap, bit 1: signed<->unsigned 16-bit components, fused into the store
 	int post_class;		// 0 native tile size, 1 drop the fourth component, 2 16-bit -> 8-bit components,
-				// 3 BC6H half -> 8-bit RGBX8 (tone.cuh), 4 the same -> RGB8, 5 / 6 = 3 / 4
-				// with the HDR range rescaling (tone_hdr set and a range other than [0, 1]),
-				// 7 BC6H half -> RGBX16, 8 the same with the rescaling
-	// tone classes only: HDR range (tone_hdr = 1: rescale by [tone_min, tone_max] first, hdr.c:119-141;
-	// 0: plain normalised half, half-float.c:304-312) and what an invalid block leaves behind
-	// (1: zeros in the target format, texture.c:90-93; 0: the conversion of zero pixels)
-	float tone_min, tone_max;
-	uint32_t tone_hdr, tone_zero_target;
+				// 3..11 BC6H half -> integer pixels (tone.cuh): 3 + 3 * mode + kind, mode 0 plain,
+				// 1 HDR range, 2 HDR range + gamma; kind 0 RGBX8, 1 RGB8, 2 RGBX16
+	// tone classes only.  Mode 1: tone_min / tone_max = the HDR range (hdr.c:119-141).  Mode 2: 1 / gamma and
+	// the gamma-corrected range as the reference computes it on the host (hdr.c:149-158).
+	// tone_zero_target: what an invalid block leaves behind (1: zeros in the target format,
+	// texture.c:90-93; 0: the conversion of zero pixels)
+	float tone_min, tone_max, tone_inv_gamma, tone_gamma_lo, tone_gamma_factor;
+	uint32_t tone_zero_target;
 	uint32_t *invalid;	// device flag word or nullptr
 	uint32_t *invalid_map;	// device bitmap, one bit per block, set for invalid blocks; or nullptr
 };

@@ -73,8 +73,7 @@ def load():
     if not os.path.exists(LIB_PATH):
         from . import build as _build
         _build.build()
-    # DETEXB200_LIB: another build of the same library (kernel experiments; development aid)
-    lib = C.CDLL(os.environ.get("DETEXB200_LIB", LIB_PATH))
+    lib = C.CDLL(LIB_PATH)
     blk = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
     for n in FORMAT_NAMES:
         f = getattr(lib, "detexDecompressBlock" + n)

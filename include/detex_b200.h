@@ -74,9 +74,11 @@ DETEXB200_API int detexb200DecodeDevice(uint32_t texture_format, const void *d_b
  * and whatever the conversion chain to pixel_format holds after it.  An invalid block leaves the
  * conversion of zero pixels (that is what the sequence above does), and *d_invalid is raised.
  * texture_format must be DETEX_TEXTURE_FORMAT_BPTC_FLOAT (the only compressed format whose pixel
- * format has an _HDR twin).  For gamma == 1 and pixel_format RGBX8, RGBA8, BGRX8, BGRA8 or RGB8
- * the whole chain runs inside the decode kernel (one pass over HBM: 16 bytes in, 64 or 48 out
- * per block); other targets and gamma values go through the L2-resident conversion pass of
+ * format has an _HDR twin).  For pixel_format RGBX16, RGBX8, RGBA8, BGRX8, BGRA8 and RGB8 the
+ * whole chain runs inside the decode kernel (one pass over HBM: 16 bytes in, 128, 64 or 48 out
+ * per block), bit-exact for gamma == 1; for other gamma values the kernel evaluates the power on
+ * the special-function unit and agrees with the reference's powf table within one integer step
+ * of the target.  Other targets go through the L2-resident conversion pass of
  * detexb200DecodeDevice.  The HDR parameters of the calling thread (detexSetHDRParameters) are
  * left unchanged.
  */

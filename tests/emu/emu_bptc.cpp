@@ -27,27 +27,34 @@ static void tables_init() {
 
 extern "C" {
 
+/* the variant the host picks (api.cu): plain, or HDR range when the range is not [0, 1] */
+static int tone_mode_of(int hdr, float range_min, float range_max) {
+	return (hdr && !(range_min == 0.0f && range_max == 1.0f)) ? TONE_RANGE : TONE_PLAIN;
+}
 static Tone tone_of(int hdr, float range_min, float range_max) {
 	ToneArgs a;
 	a.range_min = range_min;
 	a.range_max = range_max;
-	a.hdr = (uint32_t)hdr;
+	a.inv_gamma = 1.0f;
+	a.gamma_lo = 0.0f;
+	a.gamma_factor = 1.0f;
 	a.zero_target = 0;
-	return tone_setup(a);
+	return tone_mode_of(hdr, range_min, range_max) == TONE_RANGE ? tone_setup<TONE_RANGE>(a) : tone_setup<TONE_PLAIN>(a);
 }
 
 /* tone.cuh, the per-component chain: n FLOAT_RGBX16 pixels (non-negative finite halves) -> n RGBX8
    pixels with the given range parameters (hdr = 0: plain normalised half) */
 void emu_tone8_pixels(const uint8_t *pixels, int n, int hdr, float range_min, float range_max, uint8_t *out) {
 	const Tone t = tone_of(hdr, range_min, range_max);
+	const bool rescale = tone_mode_of(hdr, range_min, range_max) == TONE_RANGE;
 	for (int i = 0; i < n; i++) {
 		uint16_t h[4];
 		memcpy(h, pixels + 8 * (size_t)i, 8);
-		const uint32_t q = t.rescale
-			? tone8_pack(tone8_top<true>((uint32_t)h[0] << 13, t), tone8_top<true>((uint32_t)h[1] << 13, t),
-				tone8_top<true>((uint32_t)h[2] << 13, t))
-			: tone8_pack(tone8_top<false>((uint32_t)h[0] << 13, t), tone8_top<false>((uint32_t)h[1] << 13, t),
-				tone8_top<false>((uint32_t)h[2] << 13, t));
+		const uint32_t q = rescale
+			? tone8_pack(tone8_top<TONE_RANGE>((uint32_t)h[0] << 13, t), tone8_top<TONE_RANGE>((uint32_t)h[1] << 13, t),
+				tone8_top<TONE_RANGE>((uint32_t)h[2] << 13, t))
+			: tone8_pack(tone8_top<TONE_PLAIN>((uint32_t)h[0] << 13, t), tone8_top<TONE_PLAIN>((uint32_t)h[1] << 13, t),
+				tone8_top<TONE_PLAIN>((uint32_t)h[2] << 13, t));
 		memcpy(out + 4 * (size_t)i, &q, 4);
 	}
 }
@@ -58,14 +65,15 @@ void emu_bc6h_decode_tone16(const uint8_t *blocks, int n, int hdr, float range_m
 uint8_t *valid) {
 	tables_init();
 	const Tone t = tone_of(hdr, range_min, range_max);
+	const bool rescale = tone_mode_of(hdr, range_min, range_max) == TONE_RANGE;
 	for (int i = 0; i < n; i++) {
 		uint4 w;
 		memcpy(&w, blocks + 16 * (size_t)i, 16);
 		uint32_t q[32];
-		const bool ok = t.rescale ? decode_bptc_float_tone16<true>(w, 0xFFFFFFFFu, g_tab.packed, t, q)
-					  : decode_bptc_float_tone16<false>(w, 0xFFFFFFFFu, g_tab.packed, t, q);
+		const bool ok = rescale ? decode_bptc_float_tone16<TONE_RANGE>(w, 0xFFFFFFFFu, g_tab.packed, t, q)
+					  : decode_bptc_float_tone16<TONE_PLAIN>(w, 0xFFFFFFFFu, g_tab.packed, t, q);
 		if (!ok) {
-			const uint32_t z = t.rescale ? tone16_of_zero<true>(t) : tone16_of_zero<false>(t);
+			const uint32_t z = rescale ? tone16_of_zero<TONE_RANGE>(t) : tone16_of_zero<TONE_PLAIN>(t);
 			for (int k = 0; k < 32; k++)
 				q[k] = z | (z << 16);
 		}
@@ -80,15 +88,16 @@ void emu_bc6h_decode_tone8(const uint8_t *blocks, int n, int hdr, float range_mi
 uint8_t *valid) {
 	tables_init();
 	const Tone t = tone_of(hdr, range_min, range_max);
+	const bool rescale = tone_mode_of(hdr, range_min, range_max) == TONE_RANGE;
 	for (int i = 0; i < n; i++) {
 		uint4 w;
 		memcpy(&w, blocks + 16 * (size_t)i, 16);
 		uint32_t q[16];
-		const bool ok = t.rescale ? decode_bptc_float_tone8<true>(w, 0xFFFFFFFFu, g_tab.packed, t, q)
-					  : decode_bptc_float_tone8<false>(w, 0xFFFFFFFFu, g_tab.packed, t, q);
+		const bool ok = rescale ? decode_bptc_float_tone8<TONE_RANGE>(w, 0xFFFFFFFFu, g_tab.packed, t, q)
+					  : decode_bptc_float_tone8<TONE_PLAIN>(w, 0xFFFFFFFFu, g_tab.packed, t, q);
 		if (!ok)
 			for (int k = 0; k < 16; k++)
-				q[k] = t.rescale ? tone8_of_zero<true>(t) : tone8_of_zero<false>(t);
+				q[k] = rescale ? tone8_of_zero<TONE_RANGE>(t) : tone8_of_zero<TONE_PLAIN>(t);
 		memcpy(out + 64 * (size_t)i, q, 64);
 		valid[i] = ok ? 1 : 0;
 	}

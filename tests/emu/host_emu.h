@@ -73,6 +73,7 @@ template <typename Op> static inline float emu_rounded(int mode, Op op) {
 static inline float __fmul_rn(float a, float b) { volatile float x = a, y = b; return emu_rounded(FE_TONEAREST, [&] { return x * y; }); }
 static inline float __fmul_rd(float a, float b) { volatile float x = a, y = b; return emu_rounded(FE_DOWNWARD, [&] { return x * y; }); }
 static inline float __fadd_rd(float a, float b) { volatile float x = a, y = b; return emu_rounded(FE_DOWNWARD, [&] { return x + y; }); }
+static inline float __fsub_rn(float a, float b) { volatile float x = a, y = b; return emu_rounded(FE_TONEAREST, [&] { return x - y; }); }
 static inline float __fsub_rd(float a, float b) { volatile float x = a, y = b; return emu_rounded(FE_DOWNWARD, [&] { return x - y; }); }
 static inline float __fdiv_rd(float a, float b) { volatile float x = a, y = b; return emu_rounded(FE_DOWNWARD, [&] { return x / y; }); }
 static inline float __fmaf_rd(float a, float b, float c) { volatile float x = a, y = b, z = c; return emu_rounded(FE_DOWNWARD, [&] { return fmaf(x, y, z); }); }
