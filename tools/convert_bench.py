@@ -32,6 +32,8 @@ def main():
     ap.add_argument("--pixels", type=int, default=1 << 25)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--only", default="", help="comma-separated compressed formats: decode cases only, of these formats")
+    ap.add_argument("--target", default="", help="with --only: run only the case with this target (e.g. RGBX8, hdr:RGBX8, native)")
+    ap.add_argument("--layout", default="", help="linear or tiled: run only this layout")
     args = ap.parse_args()
     only = [f for f in args.only.split(",") if f]
     peak, _ = measured_peak()
@@ -52,6 +54,8 @@ def main():
                         ("BPTC_FLOAT", "RGBX16"), ("EAC_RG11", "RG8"), ("BC3", "RGBA16")):
         if only and fmt not in only:
             continue
+        if args.target and (target or "native") != args.target:
+            continue
         tf = D.FORMATS[fmt]
         bs = D.block_size(tf)
         hdr = target is not None and target.startswith("hdr:")       # detexb200DecodeHDRDevice, range [0, 2]
@@ -59,6 +63,8 @@ def main():
         blocks = torch.empty(nb * bs, dtype=torch.uint8, device="cuda")
         D.generate_blocks_device(blocks.data_ptr(), nb, bs, seed=1, force_modes=(8 if fmt == "BPTC" else 14 if fmt == "BPTC_FLOAT" else 0))
         for layout, lname in ((D.LAYOUT_LINEAR, "linear"), (D.LAYOUT_TILED, "tiled")):
+            if args.layout and lname != args.layout:
+                continue
             out = [torch.empty(nb * 16 * pixel_size(pf), dtype=torch.uint8, device="cuda") for _ in range(3)]
             k = [0]
 
