@@ -211,6 +211,8 @@ def run(out):
     ap.add_argument("--workload", default="bc1", choices=sorted(WORKLOADS))
     ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the host-buffer leg (default min(steps, 10))")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--gather", action="store_true",
+                    help="N > 1: also time the optional final-image gather (NCCL all-gather of the decoded slabs), reported apart")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))
@@ -318,6 +320,31 @@ def run(out):
             a1.record(stream)
             torch.cuda.synchronize()
             part_ms.append(a0.elapsed_time(a1) / args.steps)
+    # optional final-image gather, outside the decode numbers: every rank's decoded slab of
+    # the first part all-gathered into the whole image on every rank, NCCL over NVLink / NVSwitch
+    gather = None
+    if args.gather and world > 1:
+        from detex_b200 import sharding as S
+        slab = parts[0]["sets"][0][1]
+        image = torch.empty(slab.numel() * world, dtype=torch.uint8, device=dev)
+        for _ in range(3):
+            S.gather_image(slab, out=image)
+        torch.cuda.synchronize()
+        dist.barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g_steps = 10
+        g0.record(stream)
+        for _ in range(g_steps):
+            S.gather_image(slab, out=image)
+        g1.record(stream)
+        torch.cuda.synchronize()
+        t = torch.tensor([g0.elapsed_time(g1) / g_steps], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        g_ms = float(t.item())
+        gather = {"op": "all_gather (NCCL) of the decoded slabs into the whole image on every rank",
+                  "slab_bytes_per_rank": int(slab.numel()), "image_bytes": int(image.numel()), "ms": g_ms,
+                  "received_gbs_per_gpu": slab.numel() * (world - 1) / g_ms / 1e6,
+                  "decode_ms_per_step": ms_max / args.steps}
     # sustained loop for the clock sampler (not part of any reported number)
     if rank == 0:
         t_end = time.time() + 1.0
@@ -431,6 +458,8 @@ def run(out):
             "e2e": e2e, "cpu_baseline": cpu_baseline, "gpu_launches": int(launches), "clocks": clocks,
             "parity": parity, "hbm_gbs_per_gpu": step_bytes * args.steps / secs / 1e9,
         }
+        if gather is not None:
+            line["gather"] = gather
         out.emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

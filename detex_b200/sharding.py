@@ -4,6 +4,10 @@ The decode is a pure map over independent blocks, so multi-GPU operation needs n
 collective: rank g owns a contiguous range of blocks (TILED) or of block rows (LINEAR, so that
 its output is a contiguous span of image rows), decodes it locally, and only the 1-bit
 "all blocks valid" result is reduced across ranks.
+
+The one optional exchange is the final-image gather (`gather_image`): when some rank needs the whole
+decoded image, the slabs -- contiguous byte ranges of it -- are all-gathered (NCCL over NVLink /
+NVSwitch on GPUs).  It is not part of the decode and is timed separately (`bench.py --gather`).
 """
 
 
@@ -46,3 +50,41 @@ def all_valid(local_ok, group=None):
         t = t.cuda()
     dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
     return bool(t.item())
+
+
+def gather_image(local, out=None, group=None):
+    """Optional final-image gather: every rank contributes its decoded slab `local`
+    (1-D uint8 tensor; slab r is the r-th contiguous byte range of the image, as linear_shard_view /
+    tiled_shard lay it out) and every rank receives the whole image.  Returns the image (`out` if
+    given: 1-D uint8, total size).  Equal slabs are gathered straight into the image buffer
+    (all_gather_into_tensor, no staging); a ragged last slab goes through one padded staging buffer."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        if out is None:
+            return local
+        out[: local.numel()].copy_(local)
+        return out
+    world = dist.get_world_size(group)
+    sizes = torch.zeros(world, dtype=torch.int64, device=local.device)
+    mine = torch.tensor([local.numel()], dtype=torch.int64, device=local.device)
+    dist.all_gather_into_tensor(sizes, mine, group=group)
+    sizes = [int(x) for x in sizes.tolist()]
+    total = sum(sizes)
+    if out is None:
+        out = torch.empty(total, dtype=local.dtype, device=local.device)
+    if out.numel() < total:
+        raise ValueError("gather_image: output holds %d bytes, the slabs %d" % (out.numel(), total))
+    if len(set(sizes)) == 1:
+        dist.all_gather_into_tensor(out[:total], local.contiguous(), group=group)
+        return out
+    pad = max(sizes)
+    staged = torch.empty(world * pad, dtype=local.dtype, device=local.device)
+    padded = torch.zeros(pad, dtype=local.dtype, device=local.device)
+    padded[: local.numel()].copy_(local)
+    dist.all_gather_into_tensor(staged, padded, group=group)
+    off = 0
+    for r, n in enumerate(sizes):
+        out[off: off + n].copy_(staged[r * pad: r * pad + n])
+        off += n
+    return out

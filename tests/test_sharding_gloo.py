@@ -54,6 +54,12 @@ def _worker(rank, world, port, tmpdir):
     np.save(os.path.join(tmpdir, "out%d.npy" % rank), out)
     ok_all = S.all_valid(ok)
     np.save(os.path.join(tmpdir, "ok%d.npy" % rank), np.array([ok, ok_all]))
+    # optional final-image gather: ragged slabs (18 and 19 block rows), then equal ones
+    import torch
+    full = S.gather_image(torch.from_numpy(out))
+    np.save(os.path.join(tmpdir, "gathered%d.npy" % rank), full.numpy())
+    eq = S.gather_image(torch.full((1000,), rank + 1, dtype=torch.uint8), out=torch.zeros(2048, dtype=torch.uint8))
+    assert eq[:1000].eq(1).all() and eq[1000:2000].eq(2).all() and eq[2000:].eq(0).all()
     dist.barrier()
     dist.destroy_process_group()
 
@@ -71,3 +77,5 @@ def test_two_rank_linear_decode_equals_single_rank(tmp_path):
     oks = [np.load(tmp_path / ("ok%d.npy" % r)) for r in range(world)]
     assert all(bool(o[1]) == ok for o in oks)          # reduced flag == single-rank result
     assert any(not bool(o[0]) for o in oks) == (not ok)
+    for r in range(world):                             # every rank holds the whole image after the gather
+        assert np.array_equal(np.load(tmp_path / ("gathered%d.npy" % r)), want)
