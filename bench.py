@@ -345,6 +345,36 @@ def run(out):
                   "slab_bytes_per_rank": int(slab.numel()), "image_bytes": int(image.numel()), "ms": g_ms,
                   "received_gbs_per_gpu": slab.numel() * (world - 1) / g_ms / 1e6,
                   "decode_ms_per_step": ms_max / args.steps}
+        # the same gather fused into the decode: every rank's kernel stores its slab straight into rank 0's
+        # image through a peer mapping (NVLink stores, no intermediate copy, no collective)
+        try:
+            p = parts[0]
+            peer = S.PeerImage(slab.numel() * world, dev)
+            dst = peer.slab_pointer(0, rank * slab.numel())
+
+            def decode_to_root():
+                D.decode_device(p["tf"], p["sets"][0][0].data_ptr(), p["w"], p["h"], dst, layout=p["layout"],
+                                d_invalid=flag.data_ptr(), stream=sp, wib=p["wib"], hib=p["hib"])
+            for _ in range(3):
+                decode_to_root()
+            torch.cuda.synchronize()
+            dist.barrier()
+            g0.record(stream)
+            for _ in range(g_steps):
+                decode_to_root()
+            g1.record(stream)
+            torch.cuda.synchronize()
+            dist.barrier()
+            t = torch.tensor([g0.elapsed_time(g1) / g_steps], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            same = torch.tensor([1 if (rank != 0 or torch.equal(peer.local, image)) else 0], dtype=torch.int32, device=dev)
+            dist.all_reduce(same, op=dist.ReduceOp.MIN)
+            gather["fused_peer_store"] = {
+                "op": "decode kernels store their slab into rank 0's image through peer-mapped memory",
+                "ms": float(t.item()), "image_equals_all_gather": bool(same.item()),
+                "root_received_gbs": slab.numel() * (world - 1) / float(t.item()) / 1e6}
+        except Exception as exc:        # symmetric memory unavailable on this build / topology
+            gather["fused_peer_store"] = {"unavailable": "%s: %s" % (type(exc).__name__, str(exc)[:200])}
     # sustained loop for the clock sampler (not part of any reported number)
     if rank == 0:
         t_end = time.time() + 1.0

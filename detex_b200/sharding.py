@@ -88,3 +88,32 @@ def gather_image(local, out=None, group=None):
         out[off: off + n].copy_(staged[r * pad: r * pad + n])
         off += n
     return out
+
+
+class PeerImage:
+    """The gather fused into the decode ("peer-mapped destination pointers"): one image
+    buffer per rank in symmetric memory (torch.distributed._symmetric_memory: every rank's buffer is
+    mapped into every other rank's address space over NVLink / NVSwitch).  A rank that passes
+    slab_pointer(dst_rank, offset) as the decode kernels' output pointer makes them store its slab
+    directly into dst_rank's image -- no intermediate copy, no collective; a barrier before the reader
+    touches the image is all the synchronisation there is.  GPU only, one process per GPU."""
+
+    def __init__(self, total_bytes, device, group=None):
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        self.group = group if group is not None else dist.group.WORLD
+        self.total = int(total_bytes)
+        self.local = symm_mem.empty(self.total, dtype=torch.uint8, device=device)
+        self.handle = symm_mem.rendezvous(self.local, self.group)
+        self._views = {}
+
+    def view(self, rank):
+        """rank's image as a tensor in this rank's address space"""
+        import torch
+        if rank not in self._views:
+            self._views[rank] = self.handle.get_buffer(rank, (self.total,), torch.uint8)
+        return self._views[rank]
+
+    def slab_pointer(self, rank, offset):
+        return self.view(rank).data_ptr() + int(offset)
