@@ -720,13 +720,18 @@ template <int F, int PC> constexpr bool stages_packed_half3() { return F == F_BP
 template <int F, int PC> constexpr int stage_words() {
 	return is_tone_class(PC) ? 16 : (stages_packed_half3<F, PC>() ? 24 : FormatTraits<F>::OUT_WORDS);
 }
-template <int F, int PC, bool STAGE> constexpr int sort_tile() {
-	// BC7 kernels that do not stage have the shared memory for 2048-block tiles: half as many bins to
-	// pad per block (measured TILED, distribution U 39.8 -> 45.4 G blocks/s, M 43.5 -> 44.9)
-	if (F == F_BPTC && !STAGE)
+// Tile size.  Kernels that stage their output: 1024 blocks (512 for the packed half tiles), two CTAs per
+// SM.  Kernels that store directly have the shared memory for more: 3072 blocks (2 x 48 KiB of
+// double-buffered input per CTA) mean fewer barriers and fewer padded bins per block -- measured on 8.4 M
+// blocks, 2048 -> 3072, G blocks/s: BC7 TILED U 45.4 -> 47.5, M 44.9 -> 46.3; BC6H TILED U 27.0 -> 29.3,
+// M 26.6 -> 27.9; signed BC6H +3-7 % in both layouts.  Unsigned BC6H LINEAR is the exception (U 28.0 ->
+// 24.3): its tiles then straddle image rows and the write streams lose locality, so it keeps 2048.
+template <int F, int PC, bool STAGE, int LAYOUT> constexpr int sort_tile() {
+	if (STAGE)
+		return stages_packed_half3<F, PC>() ? 512 : 1024;
+	if (F == F_BPTC_FLOAT && LAYOUT == LAYOUT_LINEAR)
 		return 2048;
-	return (STAGE && stages_packed_half3<F, PC>()) ? 512 :
-		((STAGE && SortTraits<F>::TILE_BLOCKS > 1024) ? 1024 : SortTraits<F>::TILE_BLOCKS);
+	return 3072;
 }
 
 constexpr int SORT_THREADS = 512, SORT_WARPS = SORT_THREADS / 32;
@@ -746,9 +751,9 @@ __device__ __forceinline__ uint32_t stage_slot(uint32_t id, uint32_t c) {
 	return c * TB + (id ^ (((id >> 3) ^ fc) & 7u));
 }
 
-template <int F, int PC, bool STAGE>
+template <int F, int PC, bool STAGE, int LAYOUT>
 struct SortedSmem {
-	static constexpr int TB = sort_tile<F, PC, STAGE>(), NB = SortTraits<F>::NUM_BINS, CAP = TB + NB * 32;
+	static constexpr int TB = sort_tile<F, PC, STAGE, LAYOUT>(), NB = SortTraits<F>::NUM_BINS, CAP = TB + NB * 32;
 	static constexpr int CHUNKS = stage_words<F, PC>() / 4;		// 16-byte chunks per staged tile
 	uint4 out[STAGE ? TB * CHUNKS : 1];	// staged pixels (stage_slot layout)
 	uint4 raw[2][TB];		// double-buffered compressed tile, filled by cp.async
@@ -788,7 +793,7 @@ int height, int wib, uint32_t mode_mask, uint32_t flags, uint32_t post_op, uint3
 ToneArgs tone_args) {
 	using T = FormatTraits<F>;
 	using S = SortTraits<F>;
-	using SM = SortedSmem<F, PC, STAGE>;
+	using SM = SortedSmem<F, PC, STAGE, LAYOUT>;
 	const EmitCtx<PC> ctx(tone_args);
 	constexpr int OW = T::OUT_WORDS, NB = S::NUM_BINS, TB = SM::TB, PER = TB / SORT_THREADS, CHUNKS = SM::CHUNKS;
 	constexpr int CPR = CHUNKS / 4;			// 16-byte chunks per pixel row of one block
@@ -1433,7 +1438,7 @@ static ToneArgs tone_args_of(const DecodeArgs &a) {
 
 template <int F, int LAYOUT, bool STAGE, int PC, int PAD = 32>
 static void launch_sorted(const uint8_t *src, uint8_t *dst, uint32_t n_blocks, const DecodeArgs &a, cudaStream_t stream) {
-	using SM = SortedSmem<F, PC, STAGE>;
+	using SM = SortedSmem<F, PC, STAGE, LAYOUT>;
 	const size_t smem = sizeof(SM);
 	const uint64_t tiles = ((uint64_t)n_blocks + SM::TB - 1) / SM::TB;
 	const uint64_t resident = (uint64_t)sm_count() * 2;		// persistent: two CTAs per SM
