@@ -721,17 +721,20 @@ template <int F, int PC> constexpr int stage_words() {
 	return is_tone_class(PC) ? 16 : (stages_packed_half3<F, PC>() ? 24 : FormatTraits<F>::OUT_WORDS);
 }
 // Tile size.  Kernels that stage their output: 1024 blocks (512 for the packed half tiles), two CTAs per
-// SM.  Kernels that store directly have the shared memory for more: 3072 blocks (2 x 48 KiB of
-// double-buffered input per CTA) mean fewer barriers and fewer padded bins per block -- measured on 8.4 M
-// blocks, 2048 -> 3072, G blocks/s: BC7 TILED U 45.4 -> 47.5, M 44.9 -> 46.3; BC6H TILED U 27.0 -> 29.3,
-// M 26.6 -> 27.9; signed BC6H +3-7 % in both layouts.  Unsigned BC6H LINEAR is the exception (U 28.0 ->
-// 24.3): its tiles then straddle image rows and the write streams lose locality, so it keeps 2048.
+// SM.  Kernels that store directly have the shared memory for more (2 x 48 KiB of double-buffered input
+// per CTA at 3072 blocks): fewer barriers and fewer padded bins per block.  Measured, G blocks/s:
+//   BC7 TILED native, 1024 -> 2048 -> 3072: distribution U 39.8 -> 45.4 -> 47.5 (8.4 M blocks; 38.2 -> 43.1 at
+//     4.2 M), M 43.5 -> 44.9 -> 46.3: adopted;
+//   BC7 TILED -> RGB8 (48-byte tiles = partial sectors whose halves come from different warps): 34.3 at
+//     1024, 29.0 at 3072 -- the further apart in time the halves are written, the worse: stays at 1024;
+//   BC6H, 2048 -> 3072: TILED +3-9 % and LINEAR -4 ... -13 % at 8.4 M blocks, +-2 % at 4.2 M: stays at 2048
+//     (SortTraits::TILE_BLOCKS).
 template <int F, int PC, bool STAGE, int LAYOUT> constexpr int sort_tile() {
 	if (STAGE)
 		return stages_packed_half3<F, PC>() ? 512 : 1024;
-	if (F == F_BPTC_FLOAT && LAYOUT == LAYOUT_LINEAR)
-		return 2048;
-	return 3072;
+	if (F == F_BPTC)
+		return PC == PC_NATIVE ? 3072 : 1024;
+	return SortTraits<F>::TILE_BLOCKS;
 }
 
 constexpr int SORT_THREADS = 512, SORT_WARPS = SORT_THREADS / 32;
