@@ -958,7 +958,7 @@ ToneArgs tone_args) {
 		// ---- store
 		constexpr bool PACK_ROWS = (PC == PC_PACK3 && OW == 16) || tone_packs3(PC);	// RGBX8 stage -> RGB8 rows
 		static_assert(!STAGE || PC == PC_NATIVE || (is_tone_class(PC) && LAYOUT == LAYOUT_LINEAR) ||
-			(PACK_ROWS && LAYOUT == LAYOUT_LINEAR) || (stages_packed_half3<F, PC>() && LAYOUT == LAYOUT_LINEAR),
+			PACK_ROWS || (stages_packed_half3<F, PC>() && LAYOUT == LAYOUT_LINEAR),
 			"staged copy-out repacks RGB8 rows only");
 		if constexpr (stages_packed_half3<F, PC>() && LAYOUT == LAYOUT_LINEAR) {
 			// 24-byte rows out of packed 96-byte tiles, in 8-byte pieces: piece q = id * 3 + j of pixel row r
@@ -989,6 +989,28 @@ ToneArgs tone_args) {
 						}
 						out += pitch;
 					}
+				}
+			}
+		}
+		else if constexpr (LAYOUT == LAYOUT_TILED && PACK_ROWS) {
+			// 48-byte RGB8 tiles out of staged RGBX8 tiles: thread <-> block in image order, three 128-bit
+			// stores per tile; a warp completes 1536 contiguous bytes with three back-to-back instructions
+			uint8_t *out = dst + (size_t)tile0 * 48;
+#pragma unroll
+			for (int k = 0; k < TB / SORT_THREADS; k++) {
+				const uint32_t id = k * SORT_THREADS + tid;
+				if (id < n_here) {
+					uint32_t t[16], q[12];
+#pragma unroll
+					for (int r = 0; r < 4; r++) {
+						const uint4 v = sm.out[stage_slot<TB, CHUNKS>(id, r)];
+						t[4 * r] = v.x; t[4 * r + 1] = v.y; t[4 * r + 2] = v.z; t[4 * r + 3] = v.w;
+					}
+					repack<PC_PACK3, 16>(t, q);
+					uint8_t *o = out + (size_t)id * 48;
+#pragma unroll
+					for (int c = 0; c < 3; c++)
+						st_stream_v4(o + 16 * c, q[4 * c], q[4 * c + 1], q[4 * c + 2], q[4 * c + 3]);
 				}
 			}
 		}
@@ -1511,8 +1533,11 @@ static cudaError_t launch_format(const DecodeArgs &a, cudaStream_t stream) {
 			// order: those tiles (BC7, the toned BC6H classes) are staged and copied out in image order
 			// (measured for the toned classes: staged 20.2 G blocks/s, direct 15.3)
 			constexpr bool ST = SortTraits<F>::STAGE_OUTPUT;
+			// 48-byte RGB8 tiles written by lanes in sorted order are partial sectors too: BC7 -> RGB8 TILED is
+			// staged like its LINEAR twin
+			constexpr bool STT = F == F_BPTC && PC == PC_PACK3;
 			if (a.layout == LAYOUT_TILED && (PC != PC_NATIVE || (tiled_direct() && aligned32)))
-				launch_sorted<F, LAYOUT_TILED, false, PC, sort_pad<F, PC, false>()>(src, dst, (uint32_t)n_blocks, a, stream);
+				launch_sorted<F, LAYOUT_TILED, STT, PC, sort_pad<F, PC, STT>()>(src, dst, (uint32_t)n_blocks, a, stream);
 			else if (a.layout == LAYOUT_TILED)
 				launch_sorted<F, LAYOUT_TILED, ST, PC_NATIVE, sort_pad<F, PC_NATIVE, ST>()>(src, dst, (uint32_t)n_blocks, a, stream);
 			else {
