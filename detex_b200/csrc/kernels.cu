@@ -730,6 +730,10 @@ template <int F, int PC> constexpr int stage_words() {
 //   BC6H, 2048 -> 3072: TILED +3-9 % and LINEAR -4 ... -13 % at 8.4 M blocks, +-2 % at 4.2 M: stays at 2048
 //     (SortTraits::TILE_BLOCKS).
 template <int F, int PC, bool STAGE, int LAYOUT> constexpr int sort_tile() {
+#ifdef DETEXB200_SORT_1024
+	if (STAGE)
+		return stages_packed_half3<F, PC>() ? 1024 : 2048;
+#endif
 	if (STAGE)
 		return stages_packed_half3<F, PC>() ? 512 : 1024;
 	if (F == F_BPTC)
@@ -737,7 +741,16 @@ template <int F, int PC, bool STAGE, int LAYOUT> constexpr int sort_tile() {
 	return SortTraits<F>::TILE_BLOCKS;
 }
 
-constexpr int SORT_THREADS = 512, SORT_WARPS = SORT_THREADS / 32;
+// -DDETEXB200_SORT_1024 builds the experiment "ONE CTA of 1024 threads per SM, staged tiles of 2048 blocks
+// (1024 for the packed half tiles)": half the padded bins per block, but no second CTA to fill the SM while
+// one sits at a barrier.  Measured (G blocks/s, 512 x 2 -> 1024 x 1): BC7 LINEAR M 41.8 -> 36.9, U 34.0 ->
+// 32.9, BC7 TILED M 42.5 -> 36.5; only the staged BC6H variants gain (-> RGBX8 LINEAR 20.2 -> 21.0,
+// -> FLOAT_RGB16 LINEAR 15.8 -> 18.1).  Not adopted.
+#ifdef DETEXB200_SORT_1024
+constexpr int SORT_THREADS = 1024, SORT_WARPS = SORT_THREADS / 32, SORT_CTAS = 1;
+#else
+constexpr int SORT_THREADS = 512, SORT_WARPS = SORT_THREADS / 32, SORT_CTAS = 2;
+#endif
 constexpr uint32_t SLOT_EMPTY = 0xFFFFu;		// sorted slot that is bin padding
 
 // Physical 16-byte slot of chunk c of the block with tile-local index id in the staging buffer:
@@ -790,7 +803,7 @@ __device__ __forceinline__ uint32_t raw_slot(uint32_t id) { return id ^ ((id >> 
 // mixed warp costs about a quarter more) and halves the lanes lost to padding, which matters for the
 // 1024-block tiles of the staged BC6H variants (14 modes: 31 % of the slots are padding at 32).
 template <int F, int LAYOUT, bool STAGE, int PC, int PAD = 32>
-__global__ void __launch_bounds__(SORT_THREADS, 2)
+__global__ void __launch_bounds__(SORT_THREADS, SORT_CTAS)
 decode_sorted_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, uint32_t n_blocks, int width,
 int height, int wib, uint32_t mode_mask, uint32_t flags, uint32_t post_op, uint32_t *invalid_flag, uint32_t *invalid_map,
 ToneArgs tone_args) {
@@ -1466,7 +1479,7 @@ static void launch_sorted(const uint8_t *src, uint8_t *dst, uint32_t n_blocks, c
 	using SM = SortedSmem<F, PC, STAGE, LAYOUT>;
 	const size_t smem = sizeof(SM);
 	const uint64_t tiles = ((uint64_t)n_blocks + SM::TB - 1) / SM::TB;
-	const uint64_t resident = (uint64_t)sm_count() * 2;		// persistent: two CTAs per SM
+	const uint64_t resident = (uint64_t)sm_count() * SORT_CTAS;		// persistent: two CTAs per SM
 	const unsigned grid = (unsigned)(tiles < resident ? tiles : resident);
 	static std::atomic<bool> configured[64];
 	int dev = 0;
