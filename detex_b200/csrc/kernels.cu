@@ -3,19 +3,24 @@
 // Replaces the two loops of reference texture.c: detexDecompressTextureTiled
 // (:77-98) and detexDecompressTextureLinear (:105-145).  The work is a pure map over
 // independent 8/16-byte blocks and is bound by HBM traffic (in + out bytes per block,
-// DESIGN.md), so the kernels are organised around the memory system:
+// DESIGN.md) or, for the heavy decoders, by instruction issue, so the kernels are organised
+// around the memory system and around keeping warps convergent:
 //   * one block per lane, fetched with one 64/128-bit non-coherent streaming load,
 //     32 lanes reading 256/512 contiguous bytes;
 //   * all 16 pixels of the block are produced in registers;
 //   * LINEAR layout: lane L of a warp owns block column bx0+L, so for every pixel row
 //     the warp's 32 row segments form one contiguous span of the image row and go out
 //     as full-width vector stores;
-//   * TILED layout: a block's pixels are contiguous (16*ps bytes), so a direct store
-//     would make every lane write 16 bytes at a 16*ps stride (half-empty sectors).
-//     Instead each warp transposes its 32 tiles through an XOR-swizzled,
-//     bank-conflict-free shared-memory buffer and writes 512 contiguous bytes per
-//     store instruction;
-//   * invalid blocks become zero pixels and raise one flag word per CTA (Q16).
+//   * TILED layout: a block's pixels are contiguous (16*ps bytes); every lane writes its own
+//     tile with 256-bit stores (whole 32-byte sectors; 16-byte tiles as one 128-bit store of a
+//     warp-contiguous span).  The older shared-memory transposition is kept for A/B runs;
+//   * BC7 and BC6H, whose modes are different code: a CTA counting-sorts tiles of blocks by
+//     mode in shared memory so that a warp decodes 32 blocks of one mode (decode_sorted_kernel);
+//     outputs whose rows or tiles would be partial sectors when written by lanes in sorted
+//     order are staged in shared memory and copied out in image order;
+//   * conversions to the pixel format the caller asked for run in the store epilogue
+//     ("post op" / "post class" below), including BC6H's half -> 16-bit -> 8-bit chain (tone.cuh);
+//   * invalid blocks become zero pixels and raise one flag word (Q16).
 #include <cstdio>
 #include <cstdlib>
 #include <atomic>

@@ -114,3 +114,21 @@ def test_product_sources_do_not_use_the_oracle():
         for f in files:
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 assert not pat.search(open(os.path.join(root, f)).read()), (root, f)
+
+
+def test_hdr_decode_entry_point_validates_on_the_host():
+    """detexb200DecodeHDRDevice rejects every texture format without an _HDR pixel format before it
+    touches the device (so this runs without a GPU), and the chains it fuses are the reference's."""
+    for fmt in ("BC1", "BPTC", "BPTC_SIGNED_FLOAT", "ETC2"):
+        with pytest.raises(D.DetexError) as e:
+            D.decode_hdr_device(fmt, 256, 16, 16, 512, D.PIXEL_FORMATS["RGBX8"])
+        assert "does not decode to an HDR pixel format" in str(e.value)
+    lib = D.load()
+    out = (C.c_uint32 * 5)()
+    hdr, plain = 0x6721, 0x2721                 # FLOAT_RGBX16_HDR / FLOAT_RGBX16
+    for src in (hdr, plain):
+        assert lib.detexb200ConversionPlan(src, D.PIXEL_FORMATS["RGBX8"], out) == 2
+        assert [out[i] for i in range(3)] == [src, D.PIXEL_FORMATS["RGBX16"], D.PIXEL_FORMATS["RGBX8"]]
+        assert lib.detexb200ConversionPlan(src, D.PIXEL_FORMATS["RGB8"], out) == 3
+        assert [out[i] for i in range(4)] == [src, D.PIXEL_FORMATS["RGBX16"], D.PIXEL_FORMATS["RGBX8"], D.PIXEL_FORMATS["RGB8"]]
+        assert lib.detexb200ConversionPlan(src, D.PIXEL_FORMATS["RGBX16"], out) == 1
