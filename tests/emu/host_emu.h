@@ -79,3 +79,32 @@ static inline float __fdiv_rd(float a, float b) { volatile float x = a, y = b; r
 static inline float __fmaf_rd(float a, float b, float c) { volatile float x = a, y = b, z = c; return emu_rounded(FE_DOWNWARD, [&] { return fmaf(x, y, z); }); }
 /* the .sat modifier of mul.f32: clamp to [0, 1], NaN -> +0 */
 static inline float emu_sat(float f) { return f != f ? 0.0f : (f < 0.0f ? 0.0f : (f > 1.0f ? 1.0f : f)); }
+
+/* ---- S3TC / ETC / EAC decoders (decode_s3tc.cuh, decode_etc.cuh) ---- */
+#define __align__(n) alignas(n)
+template <typename T> static inline T __ldg(const T *p) { return *p; }
+/* per-halfword add / subtract, wrapping (vadd2 / vsub2) */
+static inline uint32_t __vadd2(uint32_t a, uint32_t b) {
+	return ((a + b) & 0xFFFFu) | ((((a >> 16) + (b >> 16)) & 0xFFFFu) << 16);
+}
+static inline uint32_t __vsub2(uint32_t a, uint32_t b) {
+	return ((a - b) & 0xFFFFu) | ((((a >> 16) - (b >> 16)) & 0xFFFFu) << 16);
+}
+/* per signed halfword max(min(a + b, c), 0) and max(min(a, b), 0) (VIADDMNMX.S16x2.RELU / VIMNMX.S16x2.RELU) */
+static inline uint32_t __viaddmin_s16x2_relu(uint32_t a, uint32_t b, uint32_t c) {
+	uint32_t r = 0;
+	for (int k = 0; k < 2; k++) {
+		const int s = (int16_t)(uint16_t)((a >> (16 * k)) + (b >> (16 * k)));
+		const int lim = (int16_t)(uint16_t)(c >> (16 * k));
+		r |= (uint32_t)(uint16_t)std::max(std::min(s, lim), 0) << (16 * k);
+	}
+	return r;
+}
+static inline uint32_t __vimin_s16x2_relu(uint32_t a, uint32_t b) {
+	uint32_t r = 0;
+	for (int k = 0; k < 2; k++) {
+		const int x = (int16_t)(uint16_t)(a >> (16 * k)), y = (int16_t)(uint16_t)(b >> (16 * k));
+		r |= (uint32_t)(uint16_t)std::max(std::min(x, y), 0) << (16 * k);
+	}
+	return r;
+}
