@@ -108,3 +108,7 @@ static inline uint32_t __vimin_s16x2_relu(uint32_t a, uint32_t b) {
 	}
 	return r;
 }
+
+/* ---- pixel-format conversion steps (convert_steps.cuh) ---- */
+static inline int __clz(int v) { return v == 0 ? 32 : __builtin_clz((unsigned)v); }
+static inline int __float2int_rd(float f) { return (int)floorf(f); }
