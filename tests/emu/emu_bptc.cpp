@@ -42,6 +42,27 @@ static Tone tone_of(int hdr, float range_min, float range_max) {
 	return tone_mode_of(hdr, range_min, range_max) == TONE_RANGE ? tone_setup<TONE_RANGE>(a) : tone_setup<TONE_PLAIN>(a);
 }
 
+/* tone.cuh, gamma variant: the host side prepares the corrected range exactly as api.cu does (powf, sign
+   kept, hdr.c:149-158); the per-component power is exp2f(e * log2f(f)) here and MUFU on the device */
+void emu_tone8_pixels_gamma(const uint8_t *pixels, int n, float gamma, float range_min, float range_max, uint8_t *out) {
+	auto spow = [](float v, float ex) { return v >= 0.0f ? powf(v, ex) : -powf(-v, ex); };
+	ToneArgs a;
+	a.range_min = range_min;
+	a.range_max = range_max;
+	a.inv_gamma = 1.0f / gamma;
+	a.gamma_lo = spow(range_min, a.inv_gamma);
+	a.gamma_factor = 1.0f / (spow(range_max, a.inv_gamma) - a.gamma_lo);
+	a.zero_target = 0;
+	const Tone t = tone_setup<TONE_GAMMA>(a);
+	for (int i = 0; i < n; i++) {
+		uint16_t h[4];
+		memcpy(h, pixels + 8 * (size_t)i, 8);
+		const uint32_t q = tone8_pack(tone8_top<TONE_GAMMA>((uint32_t)h[0] << 13, t), tone8_top<TONE_GAMMA>((uint32_t)h[1] << 13, t),
+			tone8_top<TONE_GAMMA>((uint32_t)h[2] << 13, t));
+		memcpy(out + 4 * (size_t)i, &q, 4);
+	}
+}
+
 /* tone.cuh, the per-component chain: n FLOAT_RGBX16 pixels (non-negative finite halves) -> n RGBX8
    pixels with the given range parameters (hdr = 0: plain normalised half) */
 void emu_tone8_pixels(const uint8_t *pixels, int n, int hdr, float range_min, float range_max, uint8_t *out) {

@@ -33,6 +33,8 @@ def emu(tmp_path_factory):
     lib = C.CDLL(so)
     lib.emu_tone8_pixels.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_void_p]
     lib.emu_tone8_pixels.restype = None
+    lib.emu_tone8_pixels_gamma.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_float, C.c_void_p]
+    lib.emu_tone8_pixels_gamma.restype = None
     lib.emu_bc6h_decode_tone8.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p]
     lib.emu_bc6h_decode_tone8.restype = None
     lib.emu_bc6h_decode_tone16.argtypes = lib.emu_bc6h_decode_tone8.argtypes
@@ -119,3 +121,22 @@ def test_decoder_with_8bit_sink_matches_decode_then_convert(emu, cpu, hdr, lo, h
         got16 = np.empty(n * 128, dtype=np.uint8)
         emu.emu_bc6h_decode_tone16(b.ctypes.data, n, hdr, lo, hi, got16.ctypes.data, valid.ctypes.data)
         assert ok_c and np.array_equal(got16, want16), (hdr, lo, hi, forced)
+
+
+@pytest.mark.parametrize("gamma,lo,hi", [(2.2, 0.0, 1.0), (2.2, 0.0, 4.0), (0.45, 0.01, 2.0), (1.8, -0.5, 8.0)])
+def test_gamma_variant_every_half_within_one_step(emu, cpu, gamma, lo, hi):
+    """the gamma variant (hdr.c:143-164) replaces the reference's powf table by 2^(e log2 f): not bit-exact,
+    but never more than one 8-bit step away, for every half value"""
+    src, n = all_half_pixels()
+    cpu.detexSetHDRParameters(gamma, lo, hi)
+    try:
+        # (primed: the special-gamma path inherits its thread's rounding mode, DESIGN.md section 2, deviation 2)
+        ok, want = H.convert_pixels(cpu, src, n, PF["FLOAT_RGBX16_HDR"], PF["RGBX8"], primed=True)
+    finally:
+        cpu.detexSetHDRParameters(1.0, 0.0, 1.0)
+    assert ok
+    got = np.empty(n * 4, dtype=np.uint8)
+    emu.emu_tone8_pixels_gamma(np.ascontiguousarray(src).ctypes.data, n, gamma, lo, hi, got.ctypes.data)
+    d = np.abs(got.astype(int) - want.astype(int))
+    assert d.max() <= 1, (gamma, lo, hi, int(d.max()))
+    assert (d != 0).mean() < 0.01
