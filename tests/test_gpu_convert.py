@@ -183,7 +183,7 @@ def test_device_decode_with_conversion(fmt, target, oracle):
     has a target that is only 16-byte aligned (fused classes fall back to two passes)."""
     pf = H.PIXEL_FORMATS[target]
     tf, bs, ps = H.FORMATS[fmt]
-    for (w, h, layout, shift) in ((2048, 1536, D.LAYOUT_LINEAR, 0), (2048, 1536, D.LAYOUT_TILED, 0), (3000, 20, D.LAYOUT_LINEAR, 0),
+    for (w, h, layout, shift) in ((2048, 1536, D.LAYOUT_LINEAR, 0), (2048, 1536, D.LAYOUT_TILED, 0), (3000, 20, D.LAYOUT_LINEAR, 0), (256, 264, D.LAYOUT_LINEAR, 0),
                                   (250, 61, D.LAYOUT_LINEAR, 0), (256, 64, D.LAYOUT_TILED, 16), (256, 64, D.LAYOUT_LINEAR, 16)):
         wib, hib = (w + 3) // 4, (h + 3) // 4
         b = H.synth_blocks(fmt, wib * hib, seed=21)

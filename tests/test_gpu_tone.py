@@ -18,6 +18,7 @@ TARGETS_8BIT = ["RGBX8", "RGBA8", "BGRX8", "BGRA8", "RGB8", "RGBX16"]      # (an
 # clipped kernel, and a target that is only 16-byte aligned (falls back to decode + conversion pass)
 SHAPES = [(2048, 1536, D.LAYOUT_LINEAR, 0), (2048, 1536, D.LAYOUT_TILED, 0), (8192, 24, D.LAYOUT_LINEAR, 0),
           (3000, 20, D.LAYOUT_LINEAR, 0),       # 750 blocks per row: staged tiles straddle block rows at odd offsets
+          (256, 264, D.LAYOUT_LINEAR, 0),       # 64 blocks per row: a staged tile covers many block rows
           (128, 64, D.LAYOUT_LINEAR, 0), (128, 64, D.LAYOUT_TILED, 0), (250, 61, D.LAYOUT_LINEAR, 0),
           (256, 64, D.LAYOUT_TILED, 16), (256, 64, D.LAYOUT_LINEAR, 16)]
 
@@ -105,7 +106,7 @@ def test_decode_hdr_device(gamma, lo, hi, target, oracle):
     lib.detexSetHDRParameters.restype = None
     lib.detexSetHDRParameters(1.0, 0.125, 0.5)          # the caller's own parameters must survive the call
     try:
-        for (w, h, layout, shift) in SHAPES[:2] + SHAPES[3:7]:
+        for (w, h, layout, shift) in SHAPES[:2] + SHAPES[3:8]:
             b = _blocks(w, h, 77, False)                # uniform bits: 12.5 % invalid blocks
             d_blocks = torch.from_numpy(b.copy()).cuda()
             got, ok, launches = _run(lambda out, flag: D.decode_hdr_device("BPTC_FLOAT", d_blocks.data_ptr(), w, h, out, pf,
