@@ -287,9 +287,142 @@ __device__ __forceinline__ void bc7_decode_mode(const uint4 &w, const BptcTables
 	if constexpr (NS == 3) {
 		d2[0] = a_rb[NS - 1] - a_rb[0];	d2[1] = k_rb[NS - 1] - k_rb[0];	d2[2] = a_ga[NS - 1] - a_ga[0];	d2[3] = k_ga[NS - 1] - k_ga[0];
 	}
+#ifdef DETEXB200_BC7_TABLE2
+	// EXPERIMENT (not the default; prepared for measurement, bit-exactness checked by tests/test_emu_bptc.py
+	// compiled with the macro): modes 3 and 7 -- two subsets, 2-bit indices -- as a byte-table look-up.  A pixel
+	// is one of 2 x 4 colours, so per channel the eight candidates fit two registers and one PRMT per channel
+	// fetches FOUR pixels (selector nibble = index | subset << 2), as the ETC palette engine does; the 4x4 byte
+	// transpose that follows costs less than sixteen per-pixel endpoint selections and interpolations.
+	if constexpr (NS == 2 && IB == 2 && IB2 == 0) {
+		uint32_t tab_r[2], tab_g[2], tab_b[2], tab_a[2];
+#pragma unroll
+		for (int s = 0; s < 2; s++) {
+			const uint32_t t1_rb = a_rb[s] + 21u * k_rb[s], t2_rb = a_rb[s] + 43u * k_rb[s], t3_rb = a_rb[s] + 64u * k_rb[s];
+			const uint32_t t1_ga = a_ga[s] + 21u * k_ga[s], t2_ga = a_ga[s] + 43u * k_ga[s], t3_ga = a_ga[s] + 64u * k_ga[s];
+			const uint32_t rb01 = prmt(a_rb[s], t1_rb, 0x7351), rb23 = prmt(t2_rb, t3_rb, 0x7351);	// R0 R1 B0 B1 / R2 R3 B2 B3
+			const uint32_t ga01 = prmt(a_ga[s], t1_ga, 0x7351), ga23 = prmt(t2_ga, t3_ga, 0x7351);
+			tab_r[s] = prmt(rb01, rb23, 0x5410);
+			tab_b[s] = prmt(rb01, rb23, 0x7632);
+			tab_g[s] = prmt(ga01, ga23, 0x5410);
+			tab_a[s] = prmt(ga01, ga23, 0x7632);
+		}
+		// 2-bit indices and 1-bit subset flags of eight pixels -> eight selector nibbles
+		auto spread2 = [](uint32_t v) {		// 16 bits (8 x 2) -> 8 nibbles
+			v = (v | (v << 8)) & 0x00FF00FFu;
+			v = (v | (v << 4)) & 0x0F0F0F0Fu;
+			return (v | (v << 2)) & 0x33333333u;
+		};
+		auto spread1 = [](uint32_t v) {		// 8 bits -> bit 2 of 8 nibbles
+			v = (v | (v << 12)) & 0x000F000Fu;
+			v = (v | (v << 6)) & 0x03030303u;
+			return ((v | (v << 3)) & 0x11111111u) << 2;
+		};
+		const uint32_t sel01 = spread2(s1 & 0xFFFFu) | spread1(subset_bits & 0xFFu);	// pixel rows 0, 1
+		const uint32_t sel23 = spread2(s1 >> 16) | spread1((subset_bits >> 8) & 0xFFu);	// pixel rows 2, 3
+#pragma unroll
+		for (int y = 0; y < 4; y++) {
+			const uint32_t word = y < 2 ? sel01 : sel23, sel = (y & 1) ? (word >> 16) : word;
+			const uint32_t rq = prmt(tab_r[0], tab_r[1], sel), gq = prmt(tab_g[0], tab_g[1], sel);
+			const uint32_t bq = prmt(tab_b[0], tab_b[1], sel), aq = prmt(tab_a[0], tab_a[1], sel);
+			const uint32_t rg01 = prmt(rq, gq, 0x5140), rg23 = prmt(rq, gq, 0x7362);
+			const uint32_t ba01 = prmt(bq, aq, 0x5140), ba23 = prmt(bq, aq, 0x7362);
+			px[4 * y + 0] = prmt(rg01, ba01, 0x5410);
+			px[4 * y + 1] = prmt(rg01, ba01, 0x7632);
+			px[4 * y + 2] = prmt(rg23, ba23, 0x5410);
+			px[4 * y + 3] = prmt(rg23, ba23, 0x7632);
+		}
+		return;
+	}
+#endif
+#ifdef DETEXB200_BC7_TABLE2
+	// EXPERIMENT, mode 2: three subsets, 2-bit indices, opaque.  Subsets 0 and 1 share one look-up (selector
+	// nibble = index | (subset & 1) << 2), subset 2 gets a second one, and a byte mask (0xFF where the pixel is
+	// in subset 2) picks between them.
+	if constexpr (M == 2) {
+		uint32_t tab_r[3], tab_g[3], tab_b[3];
+#pragma unroll
+		for (int s = 0; s < 3; s++) {
+			const uint32_t t1_rb = a_rb[s] + 21u * k_rb[s], t2_rb = a_rb[s] + 43u * k_rb[s], t3_rb = a_rb[s] + 64u * k_rb[s];
+			const uint32_t t1_ga = a_ga[s] + 21u * k_ga[s], t2_ga = a_ga[s] + 43u * k_ga[s], t3_ga = a_ga[s] + 64u * k_ga[s];
+			const uint32_t rb01 = prmt(a_rb[s], t1_rb, 0x7351), rb23 = prmt(t2_rb, t3_rb, 0x7351);
+			tab_r[s] = prmt(rb01, rb23, 0x5410);
+			tab_b[s] = prmt(rb01, rb23, 0x7632);
+			tab_g[s] = prmt(prmt(a_ga[s], t1_ga, 0x5151), prmt(t2_ga, t3_ga, 0x5151), 0x5410);
+		}
+		auto spread2 = [](uint32_t v) {		// 16 bits (8 x 2) -> 8 nibbles
+			v = (v | (v << 8)) & 0x00FF00FFu;
+			v = (v | (v << 4)) & 0x0F0F0F0Fu;
+			return (v | (v << 2)) & 0x33333333u;
+		};
+		const uint32_t sub1 = subset_bits & 0x55555555u;		// bit 2i: pixel i in subset 1 (subset values 0, 1, 2)
+		const uint32_t sel01 = spread2(s1 & 0xFFFFu) | (spread2(sub1 & 0xFFFFu) << 2);
+		const uint32_t sel23 = spread2(s1 >> 16) | (spread2(sub1 >> 16) << 2);
+#pragma unroll
+		for (int y = 0; y < 4; y++) {
+			const uint32_t word = y < 2 ? sel01 : sel23, sel = (y & 1) ? (word >> 16) : word;
+			// bits 8y+1, +3, +5, +7 of subset_bits: pixel in subset 2 -> 0xFF in its byte
+			const uint32_t in2 = (subset_bits >> (8 * y + 1)) & 0x55u;
+			const uint32_t mask2 = ((in2 * 0x41041u) & 0x01010101u) * 255u;
+			const uint32_t rq = (prmt(tab_r[0], tab_r[1], sel) & ~mask2) | (prmt(tab_r[2], 0u, sel) & mask2);
+			const uint32_t gq = (prmt(tab_g[0], tab_g[1], sel) & ~mask2) | (prmt(tab_g[2], 0u, sel) & mask2);
+			const uint32_t bq = (prmt(tab_b[0], tab_b[1], sel) & ~mask2) | (prmt(tab_b[2], 0u, sel) & mask2);
+			const uint32_t rg01 = prmt(rq, gq, 0x5140), rg23 = prmt(rq, gq, 0x7362);
+			const uint32_t ba01 = prmt(bq, 0xFFFFFFFFu, 0x5140), ba23 = prmt(bq, 0xFFFFFFFFu, 0x7362);
+			px[4 * y + 0] = prmt(rg01, ba01, 0x5410);
+			px[4 * y + 1] = prmt(rg01, ba01, 0x7632);
+			px[4 * y + 2] = prmt(rg23, ba23, 0x5410);
+			px[4 * y + 3] = prmt(rg23, ba23, 0x7632);
+		}
+		return;
+	}
+#endif
 	// mode 4/5: K_ga split into its green lane (sign-extended) and its alpha lane
 	const uint32_t kg0 = (uint32_t)(int)(int16_t)(k_ga[0] & 0xFFFFu), ka0 = k_ga[0] - kg0;
+#ifdef DETEXB200_BC7_TABLE2
+	// EXPERIMENT, mode 5: one subset, 2-bit colour indices and 2-bit alpha indices.  Four candidates per
+	// channel = one register per channel; R, G, B are fetched with the colour selector, A with the alpha
+	// selector, and the rotation (swap A with R / G / B, :497-508) is folded into the selectors of the last
+	// transposing PRMT.
+	if constexpr (M == 5) {
+		const uint32_t c1 = a_rb[0] + 21u * k_rb[0], c2 = a_rb[0] + 43u * k_rb[0], c3 = a_rb[0] + 64u * k_rb[0];
+		const uint32_t g1 = a_ga[0] + 21u * kg0, g2 = a_ga[0] + 43u * kg0, g3 = a_ga[0] + 64u * kg0;	// byte 1 = green
+		const uint32_t l1 = a_ga[0] + 21u * ka0, l2 = a_ga[0] + 43u * ka0, l3 = a_ga[0] + 64u * ka0;	// byte 3 = alpha
+		const uint32_t rb01 = prmt(a_rb[0], c1, 0x7351), rb23 = prmt(c2, c3, 0x7351);
+		const uint32_t tab_r = prmt(rb01, rb23, 0x5410), tab_b = prmt(rb01, rb23, 0x7632);
+		const uint32_t tab_g = prmt(prmt(a_ga[0], g1, 0x5151), prmt(g2, g3, 0x5151), 0x5410);
+		const uint32_t tab_a = prmt(prmt(a_ga[0], l1, 0x7373), prmt(l2, l3, 0x7373), 0x5410);
+		auto spread2 = [](uint32_t v) {		// 16 bits (8 x 2) -> 8 nibbles
+			v = (v | (v << 8)) & 0x00FF00FFu;
+			v = (v | (v << 4)) & 0x0F0F0F0Fu;
+			return (v | (v << 2)) & 0x33333333u;
+		};
+		const uint32_t selc01 = spread2(s1 & 0xFFFFu), selc23 = spread2(s1 >> 16);
+		const uint32_t sela01 = spread2(s2 & 0xFFFFu), sela23 = spread2(s2 >> 16);
+		// {R0 G0 R1 G1} x {B0 A0 B1 A1} -> pixel: byte indices R 0, G 1, B 4, A 5 (+2 for the odd pixel)
+		const uint32_t even = rotation == 0u ? 0x5410u : (rotation == 1u ? 0x0415u : (rotation == 2u ? 0x1450u : 0x4510u));
+		const uint32_t odd = even + 0x2222u;
+#pragma unroll
+		for (int y = 0; y < 4; y++) {
+			const uint32_t wc = y < 2 ? selc01 : selc23, wa = y < 2 ? sela01 : sela23;
+			const uint32_t sc = (y & 1) ? (wc >> 16) : wc, sa = (y & 1) ? (wa >> 16) : wa;
+			const uint32_t rq = prmt(tab_r, 0u, sc), gq = prmt(tab_g, 0u, sc), bq = prmt(tab_b, 0u, sc), aq = prmt(tab_a, 0u, sa);
+			const uint32_t rg01 = prmt(rq, gq, 0x5140), rg23 = prmt(rq, gq, 0x7362);
+			const uint32_t ba01 = prmt(bq, aq, 0x5140), ba23 = prmt(bq, aq, 0x7362);
+			px[4 * y + 0] = prmt(rg01, ba01, even);
+			px[4 * y + 1] = prmt(rg01, ba01, odd);
+			px[4 * y + 2] = prmt(rg23, ba23, even);
+			px[4 * y + 3] = prmt(rg23, ba23, odd);
+		}
+		return;
+	}
+#endif
 
+#ifdef DETEXB200_BC7_TABLE2
+	constexpr bool TABLE_MODE = M == 2 || M == 3 || M == 5 || M == 7;	// handled above
+#else
+	constexpr bool TABLE_MODE = false;
+#endif
+	if constexpr (!TABLE_MODE) {
 #pragma unroll
 	for (int i = 0; i < 16; i++) {
 		uint32_t arb = a_rb[0], krb = k_rb[0], aga = a_ga[0], kga = k_ga[0];
@@ -321,6 +454,7 @@ __device__ __forceinline__ void bc7_decode_mode(const uint4 &w, const BptcTables
 			t_ga = aga + wc * kg0 + wa * ka0;
 		}
 		px[i] = prmt(t_rb, t_ga, gather);
+	}
 	}
 }
 

@@ -88,3 +88,23 @@ def test_per_block_flags_and_masks(emu, cpu, fmt):
                 assert bool(valid[i]) == bool(r), (fmt, flags, mask, i)
                 if r:
                     assert np.array_equal(tiles[i], o[: 16 * ps]), (fmt, flags, mask, i)
+
+
+def test_bc7_byte_table_experiment_is_bit_exact(tmp_path, cpu):
+    """-DDETEXB200_BC7_TABLE2 (decode_bptc.cuh: modes 2, 3, 5, 7 as PRMT byte-table look-ups; prepared for
+    measurement, not the default build): the same bytes as the checker for every mode, 3 x 32 768 blocks each
+    (all 64 partitions, all anchors, all four rotations occur)."""
+    so = str(tmp_path / "libemu_table2.so")
+    subprocess.run(["g++", "-std=c++17", "-O1", "-fPIC", "-shared", "-DDETEXB200_BC7_TABLE2", "-I", EMU, "-I",
+                    os.path.join(ROOT, "detex_b200", "csrc"), "-o", so, os.path.join(EMU, "emu_all.cpp")], check=True)
+    lib = C.CDLL(so)
+    lib.emu_decode.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
+    lib.emu_decode.restype = C.c_int
+    for mode in (2, 3, 5, 7, 0, 1, 4, 6, None):
+        for seed in (1, 2, 3):
+            base = H.synth_blocks("BPTC", 1 << 15, seed=seed)
+            b = base if mode is None else H.force_modes("BPTC", base, [mode])
+            want, ok, _ = H.cpu_decode(cpu, "BPTC", b, 4 * (1 << 15), 4, linear=False)
+            got, valid = _emu(lib, "BPTC", b)
+            assert np.array_equal(got, want), (mode, seed)
+            assert bool(valid.all()) == ok
