@@ -415,10 +415,63 @@ __device__ __forceinline__ void bc7_decode_mode(const uint4 &w, const BptcTables
 		}
 		return;
 	}
+	// EXPERIMENT, mode 4: one subset, a 2-bit and a 3-bit index set; the index selection bit says which of
+	// them drives the colour (:380-385).  Eight candidates per channel (two registers; the 2-bit case fills
+	// entries 4-7 with copies of 0-3), their weights picked per block from the 2- or the 3-bit table.
+	if constexpr (M == 4) {
+		constexpr uint32_t W2[8] = { 0, 21, 43, 64, 0, 21, 43, 64 }, W3[8] = { 0, 9, 18, 27, 37, 46, 55, 64 };
+		uint32_t c[8], g[8], l[8];		// byte 1 / 3 of c: R / B; byte 1 of g: G; byte 3 of l: A
+#pragma unroll
+		for (int j = 0; j < 8; j++) {
+			const uint32_t wc = isb ? W3[j] : W2[j], wa = isb ? W2[j] : W3[j];
+			c[j] = a_rb[0] + wc * k_rb[0];
+			g[j] = a_ga[0] + wc * kg0;
+			l[j] = a_ga[0] + wa * ka0;
+		}
+		uint32_t tab_r[2], tab_g[2], tab_b[2], tab_a[2];
+#pragma unroll
+		for (int h = 0; h < 2; h++) {
+			const uint32_t rb01 = prmt(c[4 * h], c[4 * h + 1], 0x7351), rb23 = prmt(c[4 * h + 2], c[4 * h + 3], 0x7351);
+			tab_r[h] = prmt(rb01, rb23, 0x5410);
+			tab_b[h] = prmt(rb01, rb23, 0x7632);
+			tab_g[h] = prmt(prmt(g[4 * h], g[4 * h + 1], 0x5151), prmt(g[4 * h + 2], g[4 * h + 3], 0x5151), 0x5410);
+			tab_a[h] = prmt(prmt(l[4 * h], l[4 * h + 1], 0x7373), prmt(l[4 * h + 2], l[4 * h + 3], 0x7373), 0x5410);
+		}
+		auto spread2 = [](uint32_t v) {		// 16 bits (8 x 2) -> 8 nibbles
+			v = (v | (v << 8)) & 0x00FF00FFu;
+			v = (v | (v << 4)) & 0x0F0F0F0Fu;
+			return (v | (v << 2)) & 0x33333333u;
+		};
+		auto spread3 = [](uint32_t v) {		// 24 bits (8 x 3) -> 8 nibbles
+			v = (v & 0x00000FFFu) | ((v & 0x00FFF000u) << 4);
+			v = (v & 0x003F003Fu) | ((v & 0x0FC00FC0u) << 2);
+			return (v & 0x07070707u) | ((v & 0x38383838u) << 1);
+		};
+		const uint32_t two01 = spread2(s1 & 0xFFFFu), two23 = spread2(s1 >> 16);
+		const uint32_t three01 = spread3((uint32_t)s2 & 0x00FFFFFFu), three23 = spread3((uint32_t)(s2 >> 24) & 0x00FFFFFFu);
+		const uint32_t selc01 = isb ? three01 : two01, selc23 = isb ? three23 : two23;
+		const uint32_t sela01 = isb ? two01 : three01, sela23 = isb ? two23 : three23;
+		const uint32_t even = rotation == 0u ? 0x5410u : (rotation == 1u ? 0x0415u : (rotation == 2u ? 0x1450u : 0x4510u));
+		const uint32_t odd = even + 0x2222u;
+#pragma unroll
+		for (int y = 0; y < 4; y++) {
+			const uint32_t wc = y < 2 ? selc01 : selc23, wa = y < 2 ? sela01 : sela23;
+			const uint32_t sc = (y & 1) ? (wc >> 16) : wc, sa = (y & 1) ? (wa >> 16) : wa;
+			const uint32_t rq = prmt(tab_r[0], tab_r[1], sc), gq = prmt(tab_g[0], tab_g[1], sc);
+			const uint32_t bq = prmt(tab_b[0], tab_b[1], sc), aq = prmt(tab_a[0], tab_a[1], sa);
+			const uint32_t rg01 = prmt(rq, gq, 0x5140), rg23 = prmt(rq, gq, 0x7362);
+			const uint32_t ba01 = prmt(bq, aq, 0x5140), ba23 = prmt(bq, aq, 0x7362);
+			px[4 * y + 0] = prmt(rg01, ba01, even);
+			px[4 * y + 1] = prmt(rg01, ba01, odd);
+			px[4 * y + 2] = prmt(rg23, ba23, even);
+			px[4 * y + 3] = prmt(rg23, ba23, odd);
+		}
+		return;
+	}
 #endif
 
 #ifdef DETEXB200_BC7_TABLE2
-	constexpr bool TABLE_MODE = M == 2 || M == 3 || M == 5 || M == 7;	// handled above
+	constexpr bool TABLE_MODE = M == 2 || M == 3 || M == 4 || M == 5 || M == 7;	// handled above
 #else
 	constexpr bool TABLE_MODE = false;
 #endif

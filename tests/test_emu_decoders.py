@@ -91,7 +91,7 @@ def test_per_block_flags_and_masks(emu, cpu, fmt):
 
 
 def test_bc7_byte_table_experiment_is_bit_exact(tmp_path, cpu):
-    """-DDETEXB200_BC7_TABLE2 (decode_bptc.cuh: modes 2, 3, 5, 7 as PRMT byte-table look-ups; prepared for
+    """-DDETEXB200_BC7_TABLE2 (decode_bptc.cuh: modes 2, 3, 4, 5, 7 as PRMT byte-table look-ups; prepared for
     measurement, not the default build): the same bytes as the checker for every mode, 3 x 32 768 blocks each
     (all 64 partitions, all anchors, all four rotations occur)."""
     so = str(tmp_path / "libemu_table2.so")
