@@ -13,5 +13,5 @@ from .lib import (  # noqa: F401
     detexDecompressBlock, detexDecompressBlockFormat, detexDecompressTextureLinear,
     detexDecompressTextureTiled, detexConvertPixels, detexGetErrorMessage,
     decode_device, decode_hdr_device, generate_blocks_device, hash_device, convert_pixels_device, launch_count,
-    load_texture_file_to_device, DeviceImage,
+    load_texture_file_to_device, DeviceImage, set_devices, set_host_threads, release_thread_resources, build_id,
 )

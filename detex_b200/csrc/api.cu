@@ -10,7 +10,12 @@
 #include <cstdio>
 #include <cmath>
 #include <cstring>
+#include <atomic>
+#include <condition_variable>
+#include <deque>
+#include <map>
 #include <mutex>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -48,17 +53,99 @@ int cuda_fail(const char *what, cudaError_t e) {
 inline int pixel_size(uint32_t pf) { return 1 + ((pf & 0xF00) >> 8); }
 inline int block_bytes(uint32_t tf) { return 8 + ((tf & DETEX_TEXTURE_FORMAT_128BIT_BLOCK_BIT) >> 20); }
 
-// ---- per-thread device context: streams + grow-only buffers -------------------------------
+// ---- lanes: one stream + its grow-only buffers ----------------------------------------------
+// A lane is the unit of the host-pointer pipeline: a slab of the texture goes host -> d_in -> kernel -> d_out
+// -> host on the lane's stream; work on one lane is ordered by the stream, so its buffers are reused slab after
+// slab without further synchronisation.  The calling thread owns N_STREAMS lanes on its current device (pinned
+// caller buffers: the DMA engines read and write them directly); every thread of the copy pool owns one lane per
+// device it has worked on (pageable caller buffers and multi-device calls, below).
 constexpr int N_STREAMS = 4;
+constexpr size_t SLAB_BYTES = 16u << 20;	// output bytes per slab, pinned single-device path
+constexpr size_t POOL_SLAB_BYTES = 8u << 20;	// ... copy-pool path (more, smaller jobs: smoother tail)
+constexpr size_t POOL_MIN_BYTES = 4u << 20;	// smaller textures are not worth a thread hop
 
-struct Context {
-	bool ready = false, failed = false;
-	int device = -1;			// the context (streams, buffers) belongs to this device
-	cudaStream_t streams[N_STREAMS] = {};
+std::atomic<bool> g_exiting{false};		// set by an atexit handler: no CUDA calls from destructors after it
+
+struct Lane {
+	int device = -1;
+	cudaStream_t stream = nullptr;
+	cudaEvent_t done = nullptr;		// blocking-sync event: pool threads sleep instead of spinning
 	void *d_in = nullptr, *d_out = nullptr, *d_tmp = nullptr;
 	size_t cap_in = 0, cap_out = 0, cap_tmp = 0;
+	void *h_in = nullptr, *h_out = nullptr;	// pinned bounce buffers (pageable caller memory)
+	size_t cap_hin = 0, cap_hout = 0;
 	uint32_t *d_flag = nullptr;
-	uint32_t *h_flag = nullptr;	// pinned
+	uint32_t *h_flag = nullptr;		// pinned
+
+	bool init() {				// on the calling thread's current device
+		if (stream)
+			return true;
+		cudaError_t e;
+		cudaGetDevice(&device);
+		if ((e = cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking)) != cudaSuccess ||
+		    (e = cudaEventCreateWithFlags(&done, cudaEventBlockingSync | cudaEventDisableTiming)) != cudaSuccess ||
+		    (e = cudaMalloc((void **)&d_flag, 4)) != cudaSuccess ||
+		    (e = cudaMallocHost((void **)&h_flag, 4)) != cudaSuccess) {
+			cuda_fail("lane allocation", e);
+			release();
+			return false;
+		}
+		return true;
+	}
+	bool reserve(void **p, size_t *cap, size_t need) {
+		if (need <= *cap)
+			return true;
+		if (*p)
+			cudaFree(*p);		// (synchronises with whatever still uses the old buffer)
+		*p = nullptr;
+		*cap = 0;
+		const size_t want = need + need / 8 + 4096;
+		cudaError_t e = cudaMalloc(p, want);
+		if (e != cudaSuccess) {
+			cuda_fail("cudaMalloc", e);
+			return false;
+		}
+		*cap = want;
+		return true;
+	}
+	bool reserve_host(void **p, size_t *cap, size_t need) {
+		if (need <= *cap)
+			return true;
+		if (*p) {
+			cudaStreamSynchronize(stream);
+			cudaFreeHost(*p);
+		}
+		*p = nullptr;
+		*cap = 0;
+		cudaError_t e = cudaMallocHost(p, need + 4096);
+		if (e != cudaSuccess) {
+			cuda_fail("cudaMallocHost", e);
+			return false;
+		}
+		*cap = need + 4096;
+		return true;
+	}
+	void release() {
+		if (g_exiting.load())
+			return;			// the runtime may be gone: leak rather than call into it
+		if (stream)
+			cudaStreamSynchronize(stream);
+		cudaFree(d_in); cudaFree(d_out); cudaFree(d_tmp); cudaFree(d_flag);
+		cudaFreeHost(h_in); cudaFreeHost(h_out); cudaFreeHost(h_flag);
+		if (done)
+			cudaEventDestroy(done);
+		if (stream)
+			cudaStreamDestroy(stream);
+		(void)cudaGetLastError();	// (cudaErrorCudartUnloading and friends are not the caller's problem)
+		*this = Lane();
+	}
+};
+
+// ---- per-thread device context ----------------------------------------------------------------
+struct Context {
+	bool ready = false, failed = false;
+	int device = -1;			// the context (lanes) belongs to this device
+	Lane lanes[N_STREAMS];
 	void *h_small = nullptr;		// pinned scratch for single-block calls (512 bytes)
 
 	bool init() {
@@ -67,7 +154,7 @@ struct Context {
 			if (cudaGetDevice(&cur) == cudaSuccess && cur == device)
 				return true;
 			set_error("detex_b200: calling thread switched CUDA device (%d -> %d); the host-pointer API keeps "
-				"one device per thread", device, cur);
+				"one device per thread (detexb200ReleaseThreadResources() lets the thread start over)", device, cur);
 			return false;
 		}
 		if (failed)
@@ -80,16 +167,15 @@ struct Context {
 			failed = true;
 			return false;
 		}
+		static std::once_flag exit_hook;
+		std::call_once(exit_hook, [] { atexit([] { g_exiting.store(true); }); });
 		cudaGetDevice(&device);
 		for (int i = 0; i < N_STREAMS; i++)
-			if ((e = cudaStreamCreateWithFlags(&streams[i], cudaStreamNonBlocking)) != cudaSuccess) {
-				cuda_fail("cudaStreamCreate", e);
+			if (!lanes[i].init()) {
 				failed = true;
 				return false;
 			}
-		if ((e = cudaMalloc((void **)&d_flag, 4)) != cudaSuccess ||
-		    (e = cudaMallocHost((void **)&h_flag, 4)) != cudaSuccess ||
-		    (e = cudaMallocHost(&h_small, 512)) != cudaSuccess) {
+		if ((e = cudaMallocHost(&h_small, 512)) != cudaSuccess) {
 			cuda_fail("context allocation", e);
 			failed = true;
 			return false;
@@ -97,28 +183,24 @@ struct Context {
 		ready = true;
 		return true;
 	}
-
-	bool reserve(void **p, size_t *cap, size_t need) {
-		if (need <= *cap)
-			return true;
-		if (*p)
-			cudaFree(*p);
-		*p = nullptr;
-		*cap = 0;
-		const size_t want = need + need / 8 + 4096;
-		cudaError_t e = cudaMalloc(p, want);
-		if (e != cudaSuccess) {
-			cuda_fail("cudaMalloc", e);
-			return false;
-		}
-		*cap = want;
-		return true;
+	// Streams, device buffers and pinned buffers of this thread go back to the driver: at thread exit (the
+	// destructor) or on request (detexb200ReleaseThreadResources).  Nothing is touched once process exit
+	// has begun -- the order in which the CUDA runtime and this library are torn down is not ours to know.
+	void release() {
+		if (!ready || g_exiting.load())
+			return;
+		int cur = -1;
+		const bool switched = cudaGetDevice(&cur) == cudaSuccess && cur != device && cudaSetDevice(device) == cudaSuccess;
+		for (int i = 0; i < N_STREAMS; i++)
+			lanes[i].release();
+		cudaFreeHost(h_small);
+		h_small = nullptr;
+		if (switched)
+			cudaSetDevice(cur);
+		(void)cudaGetLastError();
+		ready = false;
 	}
-
-	~Context() {
-		// Process teardown order is unknowable (the CUDA runtime may already be gone);
-		// leak the handful of per-thread resources rather than risk calling into it.
-	}
+	~Context() { release(); }
 };
 
 thread_local Context g_ctx;
@@ -232,9 +314,266 @@ int width, int height, int layout) {
 	return true;
 }
 
-// Host-pointer texture decode, pipelined over block-row slabs on N_STREAMS streams:
-// slab k: H2D(blocks) -> kernel -> D2H(pixels), all asynchronous on stream k % N.
-// Pinned host buffers are DMA'd directly; pageable ones go through the driver's staging.
+// ---- host-pointer texture decode ----------------------------------------------------------------
+// The texture is cut into slabs (whole block rows for LINEAR, runs of consecutive blocks for TILED); every slab
+// is an independent H2D -> kernel -> D2H chain on one lane.
+struct Slab {
+	size_t in_off, in_len;		// bytes of the caller's block array
+	size_t out_off, out_len;	// bytes of the caller's pixel buffer
+	int width, height, wib, hib;	// geometry handed to the kernels
+};
+
+struct TexCall {
+	uint32_t tf, pf;
+	int layout;
+	const uint8_t *in;
+	uint8_t *out;
+	int bb, ps, ps_native;
+	bool needs_tmp;			// decode + separate conversion pass
+	float gamma, range_min, range_max;	// HDR parameters of the calling thread (hdr.c:26-38)
+};
+
+std::vector<Slab> plan_slabs(const detexTexture *t, int layout, int bb, int ps, size_t slab_bytes) {
+	std::vector<Slab> slabs;
+	const int wib = t->width_in_blocks, hib = t->height_in_blocks;
+	if (layout == DETEXB200_LAYOUT_LINEAR) {
+		const size_t out_row_bytes = (size_t)t->width * 4 * ps;
+		int rows_per_slab = (int)(slab_bytes / (out_row_bytes ? out_row_bytes : 1));
+		// (a slab never holds more than 2^22 blocks, whatever the image width says)
+		const int row_cap = (int)(((size_t)1 << 22) / (size_t)(wib > 0 ? wib : 1));
+		if (rows_per_slab > row_cap)
+			rows_per_slab = row_cap;
+		if (rows_per_slab < 1)
+			rows_per_slab = 1;
+		for (int r0 = 0; r0 < hib; r0 += rows_per_slab) {
+			const int rows = (hib - r0) < rows_per_slab ? (hib - r0) : rows_per_slab;
+			int slab_h = t->height - r0 * 4;
+			if (slab_h > rows * 4)
+				slab_h = rows * 4;
+			if (slab_h < 0)
+				slab_h = 0;
+			Slab s;
+			s.in_off = (size_t)r0 * wib * bb;
+			s.in_len = (size_t)rows * wib * bb;
+			s.out_off = (size_t)r0 * 4 * t->width * ps;
+			s.out_len = (size_t)slab_h * t->width * ps;
+			s.width = t->width;
+			s.height = slab_h;
+			s.wib = wib;
+			s.hib = rows;
+			slabs.push_back(s);
+		}
+	}
+	else {
+		const uint64_t n_blocks = (uint64_t)wib * hib;
+		// a multiple of 1024 blocks: slabs stay 16-byte aligned and tile-aligned for the sorted kernels
+		uint64_t per_slab = (slab_bytes / (16u * ps)) & ~1023ull;
+		if (per_slab < 1024)
+			per_slab = 1024;
+		for (uint64_t b0 = 0; b0 < n_blocks; b0 += per_slab) {
+			const uint64_t count = (n_blocks - b0) < per_slab ? (n_blocks - b0) : per_slab;
+			Slab s;
+			s.in_off = (size_t)b0 * bb;
+			s.in_len = (size_t)count * bb;
+			s.out_off = (size_t)b0 * 16 * ps;
+			s.out_len = (size_t)count * 16 * ps;
+			s.width = (int)count * 4;
+			s.height = 4;
+			s.wib = (int)count;
+			s.hib = 1;
+			slabs.push_back(s);
+		}
+	}
+	return slabs;
+}
+
+// scratch of the decode + conversion pass of one slab: native-format pixels, then one bit per block
+inline size_t tmp_pixel_bytes(const TexCall &c, const Slab &s) {
+	return (((size_t)s.wib * s.hib * 16 * c.ps_native) + 255) & ~(size_t)255;
+}
+inline size_t tmp_bytes(const TexCall &c, const Slab &s) {
+	return tmp_pixel_bytes(c, s) + (((size_t)s.wib * s.hib + 31) / 32 + 64) * 4;
+}
+
+bool reserve_lane(Lane &L, const TexCall &c, size_t max_in, size_t max_out, size_t max_tmp, bool bounce_in, bool bounce_out) {
+	return L.reserve(&L.d_in, &L.cap_in, max_in + 16) && L.reserve(&L.d_out, &L.cap_out, max_out + 32) &&
+		(!c.needs_tmp || L.reserve(&L.d_tmp, &L.cap_tmp, max_tmp)) &&
+		(!bounce_in || L.reserve_host(&L.h_in, &L.cap_hin, max_in)) &&
+		(!bounce_out || L.reserve_host(&L.h_out, &L.cap_hout, max_out));
+}
+
+// H2D -> decode (+ conversion) -> D2H of one slab, enqueued on the lane's stream.  The lane's buffers have been
+// reserved by the caller.
+int enqueue_slab(Lane &L, const TexCall &c, const Slab &s, const void *h_src, void *h_dst) {
+	cudaError_t e;
+	if (s.in_len && (e = cudaMemcpyAsync(L.d_in, h_src, s.in_len, cudaMemcpyHostToDevice, L.stream)) != cudaSuccess)
+		return cuda_fail("host to device copy", e);
+	uint32_t *map = c.needs_tmp ? (uint32_t *)((uint8_t *)L.d_tmp + tmp_pixel_bytes(c, s)) : nullptr;
+	const int rc = enqueue_decode(c.tf, L.d_in, s.width, s.height, s.wib, s.hib, L.d_out, c.pf, c.layout,
+		DETEX_MODE_MASK_ALL, 0, L.d_flag, c.needs_tmp ? L.d_tmp : nullptr, map, L.stream);
+	if (rc != DETEXB200_OK)
+		return rc;
+	if (s.out_len && (e = cudaMemcpyAsync(h_dst, L.d_out, s.out_len, cudaMemcpyDeviceToHost, L.stream)) != cudaSuccess)
+		return cuda_fail("device to host copy", e);
+	return DETEXB200_OK;
+}
+
+// ---- copy pool: pageable caller buffers and multi-device calls --------------------------------------
+// cudaMemcpyAsync on pageable memory is staged by the driver on the calling thread, one copy at a time, and the
+// pipeline above degenerates into a sequence.  Real callers of this API pass malloc'd buffers
+// (detex-convert.c:303-310, ktx.c:142), so that case gets its own machinery: a process-wide pool of threads, each
+// owning a lane with pinned bounce buffers.  A pool thread takes one slab at a time: memcpy blocks -> pinned,
+// H2D, kernel, D2H into pinned, wait (blocking event, the thread sleeps), memcpy pinned -> caller's pixels.  With
+// a handful of threads the host copies of some slabs overlap the DMA transfers of others and the PCIe link stays
+// busy.  The same pool spreads ONE call over several GPUs (detexb200SetDevices / DETEXB200_DEVICES): slab k goes
+// to device k mod G, every device moving its slabs over its own PCIe link.
+struct CallState {
+	std::mutex m;
+	std::condition_variable cv;
+	int pending = 0;
+	int rc = DETEXB200_OK;
+	bool invalid = false;
+	std::string error;
+};
+struct Job {
+	const TexCall *call;
+	const Slab *slab;
+	int device;
+	bool bounce_in, bounce_out;
+	size_t max_in, max_out, max_tmp;
+	CallState *state;
+};
+
+class Pool {
+public:
+	void ensure(int n) {
+		std::lock_guard<std::mutex> g(m_);
+		while ((int)threads_ < n) {
+			std::thread(&Pool::worker, this).detach();
+			threads_++;
+		}
+	}
+	void submit(const Job &j) {
+		{
+			std::lock_guard<std::mutex> g(m_);
+			q_.push_back(j);
+		}
+		cv_.notify_one();
+	}
+private:
+	std::mutex m_;
+	std::condition_variable cv_;
+	std::deque<Job> q_;
+	size_t threads_ = 0;
+
+	static int run(const Job &j, std::map<int, Lane> &lanes, bool *invalid) {
+		const TexCall &c = *j.call;
+		const Slab &s = *j.slab;
+		cudaError_t e;
+		if ((e = cudaSetDevice(j.device)) != cudaSuccess)
+			return cuda_fail("cudaSetDevice", e);
+		Lane &L = lanes[j.device];
+		if (!L.init() || !reserve_lane(L, c, j.max_in, j.max_out, j.max_tmp, j.bounce_in, j.bounce_out))
+			return DETEXB200_ECUDA;
+		set_hdr_parameters(c.gamma, c.range_min, c.range_max);
+		if ((e = cudaMemsetAsync(L.d_flag, 0, 4, L.stream)) != cudaSuccess)
+			return cuda_fail("cudaMemsetAsync", e);
+		const void *src = c.in + s.in_off;
+		if (j.bounce_in) {
+			memcpy(L.h_in, src, s.in_len);
+			src = L.h_in;
+		}
+		void *dst = j.bounce_out ? L.h_out : (void *)(c.out + s.out_off);
+		const int rc = enqueue_slab(L, c, s, src, dst);
+		if (rc != DETEXB200_OK)
+			return rc;
+		if ((e = cudaMemcpyAsync(L.h_flag, L.d_flag, 4, cudaMemcpyDeviceToHost, L.stream)) != cudaSuccess ||
+		    (e = cudaEventRecord(L.done, L.stream)) != cudaSuccess ||
+		    (e = cudaEventSynchronize(L.done)) != cudaSuccess)
+			return cuda_fail("slab pipeline", e);
+		if (j.bounce_out)
+			memcpy(c.out + s.out_off, L.h_out, s.out_len);
+		*invalid = *L.h_flag != 0;
+		return DETEXB200_OK;
+	}
+
+	void worker() {
+		std::map<int, Lane> lanes;		// this thread's lane on every device it has served
+		for (;;) {
+			Job j;
+			{
+				std::unique_lock<std::mutex> g(m_);
+				cv_.wait(g, [&] { return !q_.empty(); });
+				j = q_.front();
+				q_.pop_front();
+			}
+			bool invalid = false;
+			const int rc = run(j, lanes, &invalid);
+			CallState &st = *j.state;
+			std::lock_guard<std::mutex> g(st.m);
+			if (rc != DETEXB200_OK && st.rc == DETEXB200_OK) {
+				st.rc = rc;
+				st.error = g_error;
+			}
+			st.invalid = st.invalid || invalid;
+			if (--st.pending == 0)
+				st.cv.notify_all();
+		}
+	}
+};
+
+Pool &pool() {
+	static Pool *p = new Pool;	// never destroyed: its threads outlive static destruction
+	return *p;
+}
+
+// ---- device set of the host-pointer texture calls ---------------------------------------------------------
+std::mutex g_devices_mutex;
+std::vector<int> g_devices;		// empty: the calling thread's current device
+bool g_devices_from_env = false;
+int g_host_threads = 0;			// 0: default
+
+std::vector<int> device_set() {
+	std::lock_guard<std::mutex> g(g_devices_mutex);
+	if (!g_devices_from_env) {
+		g_devices_from_env = true;
+		if (const char *t = getenv("DETEXB200_HOST_THREADS"))
+			g_host_threads = atoi(t);
+		const char *e = getenv("DETEXB200_DEVICES");
+		if (e && *e && g_devices.empty()) {
+			int n = 0;
+			if (cudaGetDeviceCount(&n) != cudaSuccess)
+				n = 0;
+			if (!strcmp(e, "all"))
+				for (int i = 0; i < n; i++)
+					g_devices.push_back(i);
+			else if (strchr(e, ',') == nullptr && atoi(e) > 0 && e[strspn(e, "0123456789")] == 0 && atoi(e) <= n && e[0] != '0')
+				for (int i = 0; i < atoi(e); i++)	// a count
+					g_devices.push_back(i);
+			else
+				for (const char *p = e; *p;) {		// a list of ordinals
+					char *end;
+					const long d = strtol(p, &end, 10);
+					if (end == p)
+						break;
+					if (d >= 0 && d < n)
+						g_devices.push_back((int)d);
+					p = *end == ',' ? end + 1 : end;
+				}
+		}
+	}
+	return g_devices;
+}
+
+bool host_pointer_is_pinned(const void *p) {
+	cudaPointerAttributes a;
+	if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+		(void)cudaGetLastError();
+		return false;
+	}
+	return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+
 bool decode_texture_host(const detexTexture *t, uint8_t *pixel_buffer, uint32_t pf, int layout, const char *who) {
 	Context &c = g_ctx;
 	if (!c.init())
@@ -251,96 +590,99 @@ bool decode_texture_host(const detexTexture *t, uint8_t *pixel_buffer, uint32_t 
 		set_error("detexConvertPixels: Unable to find conversion path (0x%04X -> 0x%04X)", native, pf);
 		return false;
 	}
-	const int bb = block_bytes(tf), ps = pixel_size(pf), ps_native = pixel_size(native);
-	const size_t in_bytes = n_blocks * bb;
-	const size_t out_bytes = layout == DETEXB200_LAYOUT_LINEAR ? (size_t)t->width * t->height * ps : n_blocks * 16 * ps;
+	TexCall call;
+	call.tf = tf;
+	call.pf = pf;
+	call.layout = layout;
+	call.in = t->data;
+	call.out = pixel_buffer;
+	call.bb = block_bytes(tf);
+	call.ps = pixel_size(pf);
+	call.ps_native = pixel_size(native);
 	const FusedConversion fuse = convert_fused(native, pf);
-	const size_t tmp_bytes = (fuse.ok && fuse.post_class == 0) ? 0 : ((n_blocks * 16 * ps_native + 255) & ~(size_t)255);
-	// behind the scratch pixels: the invalid-block bitmaps of the slabs (slab k of blocks [b, b + n)
-	// uses the words from b / 32 + k on; consecutive slabs never overlap)
-	const size_t map_bytes = tmp_bytes ? (n_blocks / 32 + n_blocks / 1024 + 4096) * 4 : 0;
-	if (!c.reserve(&c.d_in, &c.cap_in, in_bytes) || !c.reserve(&c.d_out, &c.cap_out, out_bytes + 16) ||
-	    (tmp_bytes && !c.reserve(&c.d_tmp, &c.cap_tmp, tmp_bytes + map_bytes)))
-		return false;
-	uint32_t *const map_base = tmp_bytes ? (uint32_t *)((uint8_t *)c.d_tmp + tmp_bytes) : nullptr;
-	cudaError_t e;
-	if ((e = cudaMemsetAsync(c.d_flag, 0, 4, c.streams[0])) != cudaSuccess ||
-	    (e = cudaStreamSynchronize(c.streams[0])) != cudaSuccess) {
-		cuda_fail(who, e);
-		return false;
+	call.needs_tmp = !fuse.ok;	// (a fused class on a misaligned target cannot happen: slabs start at cudaMalloc'd bases)
+	get_hdr_parameters(&call.gamma, &call.range_min, &call.range_max);
+	const size_t in_bytes = n_blocks * call.bb;
+	const size_t out_bytes = layout == DETEXB200_LAYOUT_LINEAR ? (size_t)t->width * t->height * call.ps : n_blocks * 16 * call.ps;
+
+	const std::vector<int> devices = device_set();
+	const bool pinned_in = host_pointer_is_pinned(t->data), pinned_out = host_pointer_is_pinned(pixel_buffer);
+	const bool use_pool = in_bytes + out_bytes >= POOL_MIN_BYTES && (!devices.empty() || !pinned_in || !pinned_out);
+	const std::vector<Slab> slabs = plan_slabs(t, layout, call.bb, call.ps, use_pool ? POOL_SLAB_BYTES : SLAB_BYTES);
+	size_t max_in = 0, max_out = 0, max_tmp = 0;
+	for (const Slab &s : slabs) {
+		max_in = s.in_len > max_in ? s.in_len : max_in;
+		max_out = s.out_len > max_out ? s.out_len : max_out;
+		const size_t tb = call.needs_tmp ? tmp_bytes(call, s) : 0;
+		max_tmp = tb > max_tmp ? tb : max_tmp;
 	}
-	// Slabs of about 16 MiB of output each: whole block rows for LINEAR (at least one row), any
-	// run of consecutive blocks for TILED (a multiple of 1024 so that slabs stay 16-byte aligned
-	// and tile-aligned for the sorted kernels).
-	int rc = DETEXB200_OK;
-	int k = 0;
-	if (layout == DETEXB200_LAYOUT_LINEAR) {
-		const size_t out_row_bytes = (size_t)t->width * 4 * ps;
-		int rows_per_slab = (int)((16u << 20) / (out_row_bytes ? out_row_bytes : 1));
-		if (rows_per_slab < 1)
-			rows_per_slab = 1;
-		for (int r0 = 0; r0 < hib && rc == DETEXB200_OK; r0 += rows_per_slab, k++) {
-			const int rows = (hib - r0) < rows_per_slab ? (hib - r0) : rows_per_slab;
-			cudaStream_t s = c.streams[k % N_STREAMS];
-			const size_t in_off = (size_t)r0 * wib * bb, in_len = (size_t)rows * wib * bb;
-			int slab_h = t->height - r0 * 4;
-			if (slab_h > rows * 4)
-				slab_h = rows * 4;
-			if (slab_h < 0)
-				slab_h = 0;
-			const size_t out_off = (size_t)r0 * 4 * t->width * ps, out_len = (size_t)slab_h * t->width * ps;
-			const size_t tmp_off = (size_t)r0 * 4 * t->width * ps_native;
-			if ((e = cudaMemcpyAsync((uint8_t *)c.d_in + in_off, t->data + in_off, in_len, cudaMemcpyHostToDevice, s)) != cudaSuccess) {
-				rc = cuda_fail("host to device copy", e);
-				break;
-			}
-			rc = enqueue_decode(tf, (uint8_t *)c.d_in + in_off, t->width, slab_h, wib, rows, (uint8_t *)c.d_out + out_off, pf,
-				layout, DETEX_MODE_MASK_ALL, 0, c.d_flag, tmp_bytes ? (uint8_t *)c.d_tmp + tmp_off : nullptr,
-				map_base ? map_base + ((size_t)r0 * wib) / 32 + k : nullptr, s);
-			if (rc != DETEXB200_OK)
-				break;
-			if (out_len && (e = cudaMemcpyAsync(pixel_buffer + out_off, (uint8_t *)c.d_out + out_off, out_len,
-					cudaMemcpyDeviceToHost, s)) != cudaSuccess) {
-				rc = cuda_fail("device to host copy", e);
-				break;
-			}
+	bool invalid = false;
+	if (use_pool) {
+		int cur = 0;
+		cudaGetDevice(&cur);
+		const std::vector<int> devs = devices.empty() ? std::vector<int>(1, cur) : devices;
+		int want = g_host_threads;
+		if (want <= 0) {
+			const int hw = (int)std::thread::hardware_concurrency();
+			want = hw / 2;
+			want = want < 4 ? 4 : (want > 16 ? 16 : want);
+			if (want < 3 * (int)devs.size())
+				want = 3 * (int)devs.size();
 		}
+		if (want > 64)
+			want = 64;
+		pool().ensure(want);
+		CallState st;
+		st.pending = (int)slabs.size();
+		for (size_t k = 0; k < slabs.size(); k++) {
+			Job j;
+			j.call = &call;
+			j.slab = &slabs[k];
+			j.device = devs[k % devs.size()];
+			j.bounce_in = !pinned_in;
+			j.bounce_out = !pinned_out;
+			j.max_in = max_in;
+			j.max_out = max_out;
+			j.max_tmp = max_tmp;
+			j.state = &st;
+			pool().submit(j);
+		}
+		std::unique_lock<std::mutex> g(st.m);
+		st.cv.wait(g, [&] { return st.pending == 0; });
+		if (st.rc != DETEXB200_OK) {
+			g_error = st.error;
+			return false;
+		}
+		invalid = st.invalid;
 	}
 	else {
-		uint64_t per_slab = ((16u << 20) / (16u * ps)) & ~1023ull;
-		if (per_slab < 1024)
-			per_slab = 1024;
-		for (uint64_t b0 = 0; b0 < n_blocks && rc == DETEXB200_OK; b0 += per_slab, k++) {
-			const uint64_t count = (n_blocks - b0) < per_slab ? (n_blocks - b0) : per_slab;
-			cudaStream_t s = c.streams[k % N_STREAMS];
-			const size_t in_off = (size_t)b0 * bb, out_off = (size_t)b0 * 16 * ps, tmp_off = (size_t)b0 * 16 * ps_native;
-			if ((e = cudaMemcpyAsync((uint8_t *)c.d_in + in_off, t->data + in_off, (size_t)count * bb, cudaMemcpyHostToDevice, s)) != cudaSuccess) {
-				rc = cuda_fail("host to device copy", e);
-				break;
-			}
-			rc = enqueue_decode(tf, (uint8_t *)c.d_in + in_off, (int)count * 4, 4, (int)count, 1, (uint8_t *)c.d_out + out_off, pf,
-				layout, DETEX_MODE_MASK_ALL, 0, c.d_flag, tmp_bytes ? (uint8_t *)c.d_tmp + tmp_off : nullptr,
-				map_base ? map_base + b0 / 32 + k : nullptr, s);
-			if (rc != DETEXB200_OK)
-				break;
-			if ((e = cudaMemcpyAsync(pixel_buffer + out_off, (uint8_t *)c.d_out + out_off, (size_t)count * 16 * ps,
-					cudaMemcpyDeviceToHost, s)) != cudaSuccess) {
-				rc = cuda_fail("device to host copy", e);
-				break;
+		cudaError_t e;
+		const int used = (int)(slabs.size() < (size_t)N_STREAMS ? slabs.size() : (size_t)N_STREAMS);
+		for (int i = 0; i < used; i++) {
+			Lane &L = c.lanes[i];
+			if (!reserve_lane(L, call, max_in, max_out, max_tmp, false, false))
+				return false;
+			if ((e = cudaMemsetAsync(L.d_flag, 0, 4, L.stream)) != cudaSuccess) {
+				cuda_fail(who, e);
+				return false;
 			}
 		}
+		int rc = DETEXB200_OK;
+		for (size_t k = 0; k < slabs.size() && rc == DETEXB200_OK; k++)
+			rc = enqueue_slab(c.lanes[k % N_STREAMS], call, slabs[k], t->data + slabs[k].in_off, pixel_buffer + slabs[k].out_off);
+		for (int i = 0; i < used; i++) {
+			Lane &L = c.lanes[i];
+			if (rc == DETEXB200_OK && (e = cudaMemcpyAsync(L.h_flag, L.d_flag, 4, cudaMemcpyDeviceToHost, L.stream)) != cudaSuccess)
+				rc = cuda_fail(who, e);
+			if ((e = cudaStreamSynchronize(L.stream)) != cudaSuccess && rc == DETEXB200_OK)
+				rc = cuda_fail(who, e);
+			if (rc == DETEXB200_OK && *L.h_flag)
+				invalid = true;
+		}
+		if (rc != DETEXB200_OK)
+			return false;
 	}
-	for (int i = 0; i < N_STREAMS; i++)
-		if ((e = cudaStreamSynchronize(c.streams[i])) != cudaSuccess && rc == DETEXB200_OK)
-			rc = cuda_fail(who, e);
-	if (rc != DETEXB200_OK)
-		return false;
-	if ((e = cudaMemcpyAsync(c.h_flag, c.d_flag, 4, cudaMemcpyDeviceToHost, c.streams[0])) != cudaSuccess ||
-	    (e = cudaStreamSynchronize(c.streams[0])) != cudaSuccess) {
-		cuda_fail(who, e);
-		return false;
-	}
-	if (*c.h_flag) {
+	if (invalid) {
 		// Same text as the reference leaves behind for the last failing block (texture.c:63-64).
 		set_error("detexDecompressBlock: Decompress function for format 0x%08X returned error", tf);
 		return false;
@@ -361,28 +703,29 @@ uint8_t *pixel_buffer, uint32_t pf, bool set_message) {
 		return false;
 	}
 	const int bb = block_bytes(tf), out_bytes = 16 * pixel_size(pf);
-	if (!c.reserve(&c.d_in, &c.cap_in, 64) || !c.reserve(&c.d_out, &c.cap_out, 512) || !c.reserve(&c.d_tmp, &c.cap_tmp, 1024))
+	Lane &L = c.lanes[0];
+	if (!L.reserve(&L.d_in, &L.cap_in, 64) || !L.reserve(&L.d_out, &L.cap_out, 512) || !L.reserve(&L.d_tmp, &L.cap_tmp, 1024))
 		return false;
-	cudaStream_t s = c.streams[0];
+	cudaStream_t s = L.stream;
 	uint8_t *hs = (uint8_t *)c.h_small;
 	memcpy(hs, bitstring, bb);
 	cudaError_t e;
-	if ((e = cudaMemsetAsync(c.d_flag, 0, 4, s)) != cudaSuccess ||
-	    (e = cudaMemcpyAsync(c.d_in, hs, bb, cudaMemcpyHostToDevice, s)) != cudaSuccess) {
+	if ((e = cudaMemsetAsync(L.d_flag, 0, 4, s)) != cudaSuccess ||
+	    (e = cudaMemcpyAsync(L.d_in, hs, bb, cudaMemcpyHostToDevice, s)) != cudaSuccess) {
 		cuda_fail("detexDecompressBlock", e);
 		return false;
 	}
-	if (enqueue_decode(tf, c.d_in, 4, 4, 1, 1, c.d_out, pf, DETEXB200_LAYOUT_TILED, mode_mask, flags, c.d_flag, c.d_tmp,
-			(uint32_t *)((uint8_t *)c.d_tmp + 512), s) != DETEXB200_OK)
+	if (enqueue_decode(tf, L.d_in, 4, 4, 1, 1, L.d_out, pf, DETEXB200_LAYOUT_TILED, mode_mask, flags, L.d_flag, L.d_tmp,
+			(uint32_t *)((uint8_t *)L.d_tmp + 512), s) != DETEXB200_OK)
 		return false;
-	if ((e = cudaMemcpyAsync(hs + 64, c.d_out, out_bytes, cudaMemcpyDeviceToHost, s)) != cudaSuccess ||
-	    (e = cudaMemcpyAsync(c.h_flag, c.d_flag, 4, cudaMemcpyDeviceToHost, s)) != cudaSuccess ||
+	if ((e = cudaMemcpyAsync(hs + 64, L.d_out, out_bytes, cudaMemcpyDeviceToHost, s)) != cudaSuccess ||
+	    (e = cudaMemcpyAsync(L.h_flag, L.d_flag, 4, cudaMemcpyDeviceToHost, s)) != cudaSuccess ||
 	    (e = cudaStreamSynchronize(s)) != cudaSuccess) {
 		cuda_fail("detexDecompressBlock", e);
 		return false;
 	}
 	memcpy(pixel_buffer, hs + 64, out_bytes);
-	if (*c.h_flag) {
+	if (*L.h_flag) {
 		if (set_message)
 			set_error("detexDecompressBlock: Decompress function for format 0x%08X returned error", tf);
 		return false;
@@ -421,7 +764,10 @@ void *d_pixels, uint32_t pf, int layout, uint32_t mode_mask, uint32_t flags, uin
 	const int bb = block_bytes(tf), ps = pixel_size(pf), ps_native = pixel_size(native);
 	const size_t slab_budget = 24u << 20;
 	const size_t pixel_region = (slab_budget + (size_t)wib * 64 * ps_native + 1024 * 16 * ps_native + 255) & ~(size_t)255;
-	const size_t map_region = (pixel_region / (16 * ps_native) / 32 + 64) * 4;	// one bit per block of a slab
+	// one bit per block of a slab.  A LINEAR slab holds rows * wib blocks whatever the image width says (width may be
+	// much smaller than wib * 4), so the rows per slab are capped by the bitmap, not only by the pixel budget.
+	const size_t map_blocks = pixel_region / (16 * ps_native);
+	const size_t map_region = (map_blocks / 32 + 64) * 4;
 	cudaError_t e = cudaMallocAsync(&tmp, pixel_region + map_region, s);
 	if (e != cudaSuccess)
 		return cuda_fail("cudaMallocAsync", e);
@@ -429,7 +775,11 @@ void *d_pixels, uint32_t pf, int layout, uint32_t mode_mask, uint32_t flags, uin
 	int rc = DETEXB200_OK;
 	if (layout == DETEXB200_LAYOUT_LINEAR) {
 		const size_t row_bytes = (size_t)width * 4 * ps_native;
-		int rows_per_slab = (int)(slab_budget / (row_bytes ? row_bytes : 1));
+		size_t rows_budget = slab_budget / (row_bytes ? row_bytes : 1);
+		const size_t rows_cap = map_blocks / (size_t)(wib > 0 ? wib : 1);	// >= 4: pixel_region holds four block rows
+		if (rows_budget > rows_cap)
+			rows_budget = rows_cap;
+		int rows_per_slab = rows_budget > (size_t)hib ? hib : (int)rows_budget;
 		if (rows_per_slab < 1)
 			rows_per_slab = 1;
 		for (int r0 = 0; r0 < hib && rc == DETEXB200_OK; r0 += rows_per_slab) {
@@ -538,7 +888,50 @@ int detexb200DeviceCount(void) {
 	return cudaGetDeviceCount(&n) == cudaSuccess ? n : 0;
 }
 
-const char *detexb200Version(void) { return "detex_b200 0.1 (sm_100a; API of hglm/detex v0.1.2)"; }
+#ifndef DETEXB200_BUILD_ID
+#define DETEXB200_BUILD_ID "unknown"
+#endif
+#ifdef DETEXB200_EXPERIMENTS
+#define DETEXB200_EXPERIMENTS_TAG "; +experiments"
+#else
+#define DETEXB200_EXPERIMENTS_TAG ""
+#endif
+// "build <id>": hash of the sources this library was compiled from (detex_b200/build.py); profiles/ncu_traffic.json
+// records it with every ncu figure so that bench.py can tell a stale figure from a current one.
+const char *detexb200Version(void) { return "detex_b200 0.2 (sm_100a; API of hglm/detex v0.1.2; build " DETEXB200_BUILD_ID DETEXB200_EXPERIMENTS_TAG ")"; }
+
+int detexb200SetDevices(int n, const int *device_ids) {
+	int count = 0;
+	if (n < 0 || (n > 0 && device_ids == nullptr) || cudaGetDeviceCount(&count) != cudaSuccess) {
+		set_error("detexb200SetDevices: invalid argument or no CUDA device");
+		return DETEXB200_EINVAL;
+	}
+	std::vector<int> v;
+	for (int i = 0; i < n; i++) {
+		if (device_ids[i] < 0 || device_ids[i] >= count) {
+			set_error("detexb200SetDevices: device ordinal %d out of range (%d devices)", device_ids[i], count);
+			return DETEXB200_EINVAL;
+		}
+		v.push_back(device_ids[i]);
+	}
+	device_set();			// (settle the environment first: an explicit call wins over it)
+	std::lock_guard<std::mutex> g(g_devices_mutex);
+	g_devices = v;
+	return DETEXB200_OK;
+}
+
+int detexb200SetHostThreads(int n) {
+	if (n < 0 || n > 64) {
+		set_error("detexb200SetHostThreads: thread count %d out of range (0 = default, at most 64)", n);
+		return DETEXB200_EINVAL;
+	}
+	device_set();
+	std::lock_guard<std::mutex> g(g_devices_mutex);
+	g_host_threads = n;
+	return DETEXB200_OK;
+}
+
+void detexb200ReleaseThreadResources(void) { g_ctx.release(); }
 
 uint64_t detexb200LaunchCount(void) { return launch_count(); }
 
@@ -604,13 +997,14 @@ bool detexConvertPixels(uint8_t *src, uint32_t n, uint32_t spf, uint8_t *dst, ui
 	if (!c.init())
 		return false;
 	const size_t in_bytes = (size_t)n * pixel_size(spf), out_bytes = (size_t)n * pixel_size(tpf);
-	if (!c.reserve(&c.d_tmp, &c.cap_tmp, in_bytes + 16) || !c.reserve(&c.d_out, &c.cap_out, out_bytes + 16))
+	Lane &L = c.lanes[0];
+	if (!L.reserve(&L.d_tmp, &L.cap_tmp, in_bytes + 16) || !L.reserve(&L.d_out, &L.cap_out, out_bytes + 16))
 		return false;
-	cudaStream_t s = c.streams[0];
+	cudaStream_t s = L.stream;
 	cudaError_t e;
-	if ((e = cudaMemcpyAsync(c.d_tmp, src, in_bytes, cudaMemcpyHostToDevice, s)) != cudaSuccess ||
-	    (e = launch_convert(c.d_tmp, n, spf, c.d_out, tpf, s)) != cudaSuccess ||
-	    (e = cudaMemcpyAsync(dst, c.d_out, out_bytes, cudaMemcpyDeviceToHost, s)) != cudaSuccess ||
+	if ((e = cudaMemcpyAsync(L.d_tmp, src, in_bytes, cudaMemcpyHostToDevice, s)) != cudaSuccess ||
+	    (e = launch_convert(L.d_tmp, n, spf, L.d_out, tpf, s)) != cudaSuccess ||
+	    (e = cudaMemcpyAsync(dst, L.d_out, out_bytes, cudaMemcpyDeviceToHost, s)) != cudaSuccess ||
 	    (e = cudaStreamSynchronize(s)) != cudaSuccess) {
 		cuda_fail("detexConvertPixels", e);
 		return false;

@@ -21,6 +21,15 @@
 #include "common.cuh"
 #include "bptc_tables.cuh"
 
+// Modes 2, 3, 4, 5 and 7 -- the ones with 2-bit colour indices -- decode through per-channel byte tables and PRMT
+// look-ups (four pixels per instruction) instead of sixteen per-pixel interpolations.  Measured on B200 against
+// the per-pixel path (profiles/README.md, round 2: 16.8 M blocks, LINEAR, distribution M 45.2 -> 47.9 G blocks/s,
+// U 36.3 -> 37.9): the default since round 2.  -DDETEXB200_BC7_PERPIXEL builds the per-pixel path for all modes
+// (A/B runs; tests/test_emu_decoders.py keeps both bit-exact).
+#if !defined(DETEXB200_BC7_PERPIXEL) && !defined(DETEXB200_BC7_TABLE2)
+#define DETEXB200_BC7_TABLE2 1
+#endif
+
 namespace detexb200 {
 
 // Shared-memory copy of the packed partition tables (768 bytes).
@@ -288,8 +297,7 @@ __device__ __forceinline__ void bc7_decode_mode(const uint4 &w, const BptcTables
 		d2[0] = a_rb[NS - 1] - a_rb[0];	d2[1] = k_rb[NS - 1] - k_rb[0];	d2[2] = a_ga[NS - 1] - a_ga[0];	d2[3] = k_ga[NS - 1] - k_ga[0];
 	}
 #ifdef DETEXB200_BC7_TABLE2
-	// EXPERIMENT (not the default; prepared for measurement, bit-exactness checked by tests/test_emu_bptc.py
-	// compiled with the macro): modes 3 and 7 -- two subsets, 2-bit indices -- as a byte-table look-up.  A pixel
+	// Modes 3 and 7 -- two subsets, 2-bit indices -- as a byte-table look-up.  A pixel
 	// is one of 2 x 4 colours, so per channel the eight candidates fit two registers and one PRMT per channel
 	// fetches FOUR pixels (selector nibble = index | subset << 2), as the ETC palette engine does; the 4x4 byte
 	// transpose that follows costs less than sixteen per-pixel endpoint selections and interpolations.
@@ -335,7 +343,7 @@ __device__ __forceinline__ void bc7_decode_mode(const uint4 &w, const BptcTables
 	}
 #endif
 #ifdef DETEXB200_BC7_TABLE2
-	// EXPERIMENT, mode 2: three subsets, 2-bit indices, opaque.  Subsets 0 and 1 share one look-up (selector
+	// Mode 2: three subsets, 2-bit indices, opaque.  Subsets 0 and 1 share one look-up (selector
 	// nibble = index | (subset & 1) << 2), subset 2 gets a second one, and a byte mask (0xFF where the pixel is
 	// in subset 2) picks between them.
 	if constexpr (M == 2) {
@@ -379,7 +387,7 @@ __device__ __forceinline__ void bc7_decode_mode(const uint4 &w, const BptcTables
 	// mode 4/5: K_ga split into its green lane (sign-extended) and its alpha lane
 	const uint32_t kg0 = (uint32_t)(int)(int16_t)(k_ga[0] & 0xFFFFu), ka0 = k_ga[0] - kg0;
 #ifdef DETEXB200_BC7_TABLE2
-	// EXPERIMENT, mode 5: one subset, 2-bit colour indices and 2-bit alpha indices.  Four candidates per
+	// Mode 5: one subset, 2-bit colour indices and 2-bit alpha indices.  Four candidates per
 	// channel = one register per channel; R, G, B are fetched with the colour selector, A with the alpha
 	// selector, and the rotation (swap A with R / G / B, :497-508) is folded into the selectors of the last
 	// transposing PRMT.
@@ -415,7 +423,7 @@ __device__ __forceinline__ void bc7_decode_mode(const uint4 &w, const BptcTables
 		}
 		return;
 	}
-	// EXPERIMENT, mode 4: one subset, a 2-bit and a 3-bit index set; the index selection bit says which of
+	// Mode 4: one subset, a 2-bit and a 3-bit index set; the index selection bit says which of
 	// them drives the colour (:380-385).  Eight candidates per channel (two registers; the 2-bit case fills
 	// entries 4-7 with copies of 0-3), their weights picked per block from the 2- or the 3-bit table.
 	if constexpr (M == 4) {

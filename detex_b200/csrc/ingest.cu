@@ -217,6 +217,24 @@ int unit_size(uint32_t format) {
 	return detexFormatIsCompressed(format) ? (int)detexGetCompressedBlockSize(format) : detexGetPixelSize(format);
 }
 
+// Sizes come from an untrusted header: everything is computed in 64 bits and bounded before it is compared with
+// the file or turned into an allocation.  A level is accepted when its dimensions are not negative (the tail of a
+// mip chain legitimately reaches 0 x 0, ktx.c:129-131) and at most MAX_DIM, and its payload lies inside the file.
+constexpr int64_t MAX_DIM = 1 << 20;		// pixels per side (the largest texture any API accepts is 2^15 - 2^16)
+bool level_extent(int width, int height, int block, int unit_bytes, int64_t pos, int64_t file_size,
+int *wib_out, int *hib_out, uint64_t *bytes_out) {
+	if (width < 0 || height < 0 || width > MAX_DIM || height > MAX_DIM || block <= 0 || unit_bytes <= 0 || pos < 0)
+		return false;
+	const uint64_t wib = ((uint64_t)width + block - 1) / block, hib = ((uint64_t)height + block - 1) / block;
+	const uint64_t bytes = wib * hib * (uint64_t)unit_bytes;		// <= 2^40 * 2^6: no overflow
+	if (wib * hib > 0xFFFFFFFFull || bytes > (uint64_t)file_size || (uint64_t)pos > (uint64_t)file_size - bytes)
+		return false;
+	*wib_out = (int)wib;
+	*hib_out = (int)hib;
+	*bytes_out = bytes;
+	return true;
+}
+
 // ktx.c:36-176
 bool parse_ktx(FILE *f, const char *filename, int max_mipmaps, Parsed &p) {
 	const char *who = "detexLoadKTXFileWithMipmaps";
@@ -245,39 +263,39 @@ bool parse_ktx(FILE *f, const char *filename, int max_mipmaps, Parsed &p) {
 	int width = (int)h[9], height = (int)h[10];
 	const int in_file = (int)h[14];
 	const int n_levels = in_file > max_mipmaps ? max_mipmaps : in_file;
-	long pos = 64 + (long)(int)h[15];			// key/value data is skipped
-	if ((int)h[15] > 0 && fseek(f, pos, SEEK_SET) != 0) {
+	if (in_file < 0 || (int)h[15] < 0) {
 		fail("%s: Error reading file %s", who, filename);
 		return false;
 	}
+	int64_t pos = 64 + (int64_t)(int)h[15];			// key/value data is skipped
 	fseek(f, 0, SEEK_END);
-	const long file_size = ftell(f);
-	if ((int)h[15] > 0 && pos > file_size) {
+	const int64_t file_size = ftell(f);
+	if (pos > file_size) {
 		fail("%s: Error reading file %s", who, filename);
 		return false;
 	}
 	for (int i = 0; i < n_levels; i++) {
 		uint32_t image_size;
-		if (pos + 4 > file_size || fseek(f, pos, SEEK_SET) != 0 || fread(&image_size, 1, 4, f) != 4) {
+		if (pos + 4 > file_size || fseek(f, (long)pos, SEEK_SET) != 0 || fread(&image_size, 1, 4, f) != 4) {
 			fail("%s: Error reading file %s", who, filename);
 			return false;
 		}
 		if (other_endian)
 			image_size = swap32(image_size);
-		const int wib = (width + b - 1) / b, hib = (height + b - 1) / b;
-		const int n = hib * wib;
-		if ((int)image_size != n * p.unit_bytes) {
-			fail("%s: Error loading file %s: Image size field of mipmap level %d does not match (%d vs %d)",
-				who, filename, i, (int)image_size, n * p.unit_bytes);
-			return false;
-		}
 		pos += 4;
-		if (pos + (long)n * p.unit_bytes > file_size) {
+		int wib, hib;
+		uint64_t bytes;
+		if (!level_extent(width, height, b, p.unit_bytes, pos, file_size, &wib, &hib, &bytes)) {
 			fail("%s: Error reading file %s", who, filename);
 			return false;
 		}
-		p.levels.push_back({ width, height, wib, hib, (size_t)n * p.unit_bytes, pos });
-		pos += (long)n * p.unit_bytes;
+		if ((uint64_t)image_size != bytes) {
+			fail("%s: Error loading file %s: Image size field of mipmap level %d does not match (%u vs %llu)",
+				who, filename, i, (unsigned)image_size, (unsigned long long)bytes);
+			return false;
+		}
+		p.levels.push_back({ width, height, wib, hib, (size_t)bytes, (long)pos });
+		pos += (int64_t)bytes;
 		width >>= 1;
 		height >>= 1;
 		if (i + 1 < n_levels) {				// mip padding to a multiple of four
@@ -343,15 +361,15 @@ bool parse_dds(FILE *f, const char *filename, int max_mipmaps, Parsed &p) {
 		in_file = (int)u32(24);
 	const int n_levels = in_file > max_mipmaps ? max_mipmaps : in_file;
 	fseek(f, 0, SEEK_END);
-	const long file_size = ftell(f);
+	const int64_t file_size = ftell(f);
 	for (int i = 0; i < n_levels; i++) {
-		const int wib = (width + b - 1) / b, hib = (height + b - 1) / b;
-		const size_t bytes = (size_t)wib * hib * p.unit_bytes;
-		if (pos + (long)bytes > file_size) {
+		int wib, hib;
+		uint64_t bytes;
+		if (!level_extent(width, height, b, p.unit_bytes, pos, file_size, &wib, &hib, &bytes)) {
 			fail("%s: Error reading file %s", who, filename);
 			return false;
 		}
-		p.levels.push_back({ width, height, wib, hib, bytes, pos });
+		p.levels.push_back({ width, height, wib, hib, (size_t)bytes, pos });
 		pos += (long)bytes;
 		width >>= 1;
 		height >>= 1;
@@ -395,27 +413,41 @@ bool load_to_host(const char *filename, Container c, int max_mipmaps, detexTextu
 	if (!open_and_parse(filename, c, max_mipmaps, &f, p))
 		return false;
 	const int n = (int)p.levels.size();
-	detexTexture **textures = (detexTexture **)malloc(sizeof(detexTexture *) * (n > 0 ? n : 1));
-	for (int i = 0; i < n; i++) {
+	const char *who = c == KTX ? "detexLoadKTXFileWithMipmaps" : "detexLoadDDSFileWithMipmaps";
+	detexTexture **textures = (detexTexture **)calloc((size_t)(n > 0 ? n : 1), sizeof(detexTexture *));
+	bool ok = textures != nullptr;
+	const char *what = "Out of memory loading";
+	for (int i = 0; ok && i < n; i++) {
 		const Level &l = p.levels[i];
 		detexTexture *t = (detexTexture *)malloc(sizeof(detexTexture));
+		if (t == nullptr) {
+			ok = false;
+			break;
+		}
+		textures[i] = t;
 		t->format = p.info->format;
 		t->data = (uint8_t *)malloc(l.bytes ? l.bytes : 1);
 		t->width = l.width;
 		t->height = l.height;
 		t->width_in_blocks = l.wib;
 		t->height_in_blocks = l.hib;
-		textures[i] = t;
-		if (!read_at(f, l.offset, t->data, l.bytes)) {
-			for (int j = 0; j <= i; j++) {
+		if (t->data == nullptr)
+			ok = false;
+		else if (!read_at(f, l.offset, t->data, l.bytes)) {
+			ok = false;
+			what = "Error reading";
+		}
+	}
+	if (!ok) {
+		for (int j = 0; textures != nullptr && j < n; j++)
+			if (textures[j] != nullptr) {
 				free(textures[j]->data);
 				free(textures[j]);
 			}
-			free(textures);
-			fclose(f);
-			fail("%s: Error reading file %s", c == KTX ? "detexLoadKTXFileWithMipmaps" : "detexLoadDDSFileWithMipmaps", filename);
-			return false;
-		}
+		free(textures);
+		fclose(f);
+		fail("%s: %s file %s", who, what, filename);
+		return false;
 	}
 	fclose(f);
 	*nu_levels_out = n;
@@ -506,6 +538,11 @@ detexb200DeviceImage *levels_out, int *nu_levels_out, uint32_t *texture_format_o
 	}
 	cudaStream_t s = (cudaStream_t)stream;
 	const int n = (int)p.levels.size();
+	if (n == 0) {		// a file that declares zero mip levels: nothing to hand back (and nothing to free later)
+		fclose(f);
+		fail("detexb200LoadTextureFileToDevice: file %s contains no mipmap level", filename);
+		return DETEXB200_EINVAL;
+	}
 	const int ps = detexGetPixelSize(pf);
 	// one pinned staging buffer, one device buffer for the payloads, one for the pixels (256-byte aligned levels)
 	std::vector<size_t> in_off(n), out_off(n), out_bytes(n);
@@ -522,7 +559,7 @@ detexb200DeviceImage *levels_out, int *nu_levels_out, uint32_t *texture_format_o
 	uint8_t *h_in = nullptr, *d_in = nullptr, *d_out = nullptr;
 	uint32_t *d_flag = nullptr;
 	cudaError_t e;
-	auto bail = [&](const char *what, cudaError_t err) {
+	auto cleanup = [&]() {
 		if (f)
 			fclose(f);
 		if (h_in)
@@ -533,6 +570,9 @@ detexb200DeviceImage *levels_out, int *nu_levels_out, uint32_t *texture_format_o
 			cudaFree(d_out);
 		if (d_flag)
 			cudaFree(d_flag);
+	};
+	auto bail = [&](const char *what, cudaError_t err) {
+		cleanup();
 		fail("%s: CUDA error %d (%s)", what, (int)err, cudaGetErrorString(err));
 		return DETEXB200_ECUDA;
 	};
@@ -544,7 +584,7 @@ detexb200DeviceImage *levels_out, int *nu_levels_out, uint32_t *texture_format_o
 		return bail("cudaMalloc", e);
 	for (int i = 0; i < n; i++)
 		if (!read_at(f, p.levels[i].offset, h_in + in_off[i], p.levels[i].bytes)) {
-			bail("read", cudaSuccess);
+			cleanup();
 			fail("%s: Error reading file %s", c == KTX ? "detexLoadKTXFileWithMipmaps" : "detexLoadDDSFileWithMipmaps", filename);
 			return DETEXB200_EINVAL;
 		}

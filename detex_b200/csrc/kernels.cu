@@ -29,7 +29,9 @@
 #include "decode_s3tc.cuh"
 #include "decode_etc.cuh"
 #include "decode_bptc.cuh"
+#ifdef DETEXB200_EXPERIMENTS
 #include "decode_bptc_palette.cuh"
+#endif
 #include "decode_bptc_float.cuh"
 #include "tone.cuh"
 #include "launch.h"
@@ -1077,6 +1079,9 @@ ToneArgs tone_args) {
 	report_invalid(bad, invalid_flag);
 }
 
+#ifdef DETEXB200_EXPERIMENTS
+// (a measured-and-dropped design, kept out of the default build: -DDETEXB200_EXPERIMENTS compiles it in and
+// DETEXB200_BC7_KERNEL=flow selects it at run time; profiles/README.md, "BC7 palette / dataflow experiment")
 // ---- BC7: mode-sorted, palette-staged, barrier-free dataflow kernel ---------------------------
 // One persistent CTA of 1024 threads per SM works through tiles of 1024 consecutive blocks.  As in
 // decode_sorted_kernel the blocks of a tile are counting-sorted by mode so that a warp decodes 32
@@ -1422,6 +1427,8 @@ int height, int wib, uint32_t mode_mask, uint32_t flags, uint32_t post_op, uint3
 	report_invalid(bad, invalid_flag);
 }
 
+#endif  // DETEXB200_EXPERIMENTS
+
 // ---- host-side launcher ---------------------------------------------------------------------
 static std::atomic<uint64_t> g_launches{0};
 
@@ -1497,6 +1504,7 @@ static void launch_sorted(const uint8_t *src, uint8_t *dst, uint32_t n_blocks, c
 		a.width, a.height, a.wib, a.mode_mask, a.flags, a.post_op, a.invalid, a.invalid_map, tone_args_of(a));
 }
 
+#ifdef DETEXB200_EXPERIMENTS
 // DETEXB200_BC7_KERNEL=flow selects the palette-staged dataflow kernel for BC7 instead of
 // decode_sorted_kernel.  It is bit-exact (tests/test_gpu_parity.py runs the BC7 cases under it too)
 // but measured slower (profiles/README.md, "BC7 palette / dataflow experiment"), so it is not the default.
@@ -1520,6 +1528,8 @@ static void launch_bc7_flow(const uint8_t *src, uint8_t *dst, uint32_t n_blocks,
 		a.width, a.height, a.wib, a.mode_mask, a.flags, a.post_op, a.invalid, a.invalid_map);
 }
 
+#endif  // DETEXB200_EXPERIMENTS
+
 template <int F, int PC>
 static cudaError_t launch_format(const DecodeArgs &a, cudaStream_t stream) {
 	using T = FormatTraits<F>;
@@ -1534,9 +1544,11 @@ static cudaError_t launch_format(const DecodeArgs &a, cudaStream_t stream) {
 		return cudaErrorMisalignedAddress;	// the caller falls back to decode + conversion pass
 	if constexpr (SortTraits<F>::ENABLED) {
 		// multi-mode formats: mode-sorted kernel whenever there is enough work to sort
-		const bool linear_ok = a.layout == LAYOUT_TILED || (a.width % 4 == 0);
+		// (LINEAR fast paths have no column clipping: the image must be exactly wib blocks wide)
+		const bool linear_ok = a.layout == LAYOUT_TILED || (a.width == a.wib * 4);
 		constexpr int TB = SortTraits<F>::TILE_BLOCKS;
 		if (n_blocks >= (uint64_t)TB && aligned_out && linear_ok && !force_unsorted()) {
+#ifdef DETEXB200_EXPERIMENTS
 			if constexpr (F == F_BPTC && (PC == PC_NATIVE || PC == PC_PACK3)) {
 				if (bc7_flow_kernel()) {
 					if (a.layout == LAYOUT_TILED)
@@ -1547,6 +1559,7 @@ static cudaError_t launch_format(const DecodeArgs &a, cudaStream_t stream) {
 					return cudaGetLastError();
 				}
 			}
+#endif
 			// LINEAR rows of 16 bytes or less per block are half sectors when written by lanes in sorted
 			// order: those tiles (BC7, the toned BC6H classes) are staged and copied out in image order
 			// (measured for the toned classes: staged 20.2 G blocks/s, direct 15.3)
@@ -1597,7 +1610,9 @@ static cudaError_t launch_format(const DecodeArgs &a, cudaStream_t stream) {
 		}
 	}
 	else {
-		const bool fast = (a.width % 4 == 0) && aligned_out;
+		// store_linear_rows clips rows only: the fast path needs the image to be exactly wib blocks wide
+		// (a narrower image -- width <= (wib - 1) * 4 is a legal detexTexture -- takes the clipped kernel)
+		const bool fast = (a.width == a.wib * 4) && aligned_out;
 		if (fast) {
 			int tx = 32;
 			while (tx < CTA_THREADS && tx < a.wib)

@@ -105,6 +105,9 @@ def load():
     lib.detexb200DeviceCount.argtypes, lib.detexb200DeviceCount.restype = [], C.c_int
     lib.detexb200Version.argtypes, lib.detexb200Version.restype = [], C.c_char_p
     lib.detexb200LaunchCount.argtypes, lib.detexb200LaunchCount.restype = [], C.c_uint64
+    lib.detexb200SetDevices.argtypes, lib.detexb200SetDevices.restype = [C.c_int, C.POINTER(C.c_int)], C.c_int
+    lib.detexb200SetHostThreads.argtypes, lib.detexb200SetHostThreads.restype = [C.c_int], C.c_int
+    lib.detexb200ReleaseThreadResources.argtypes, lib.detexb200ReleaseThreadResources.restype = [], None
     _lib = lib
     return lib
 
@@ -219,6 +222,28 @@ def hash_device(d_buf, n_bytes, stream=0):
 
 def launch_count():
     return int(load().detexb200LaunchCount())
+
+
+def set_devices(device_ids):
+    """detexb200SetDevices: the GPUs the host-pointer texture calls spread their slabs over
+    (empty list = the calling thread's current device)."""
+    ids = list(device_ids)
+    arr = (C.c_int * max(1, len(ids)))(*ids)
+    _check(load().detexb200SetDevices(len(ids), arr))
+
+
+def set_host_threads(n):
+    _check(load().detexb200SetHostThreads(n))
+
+
+def release_thread_resources():
+    load().detexb200ReleaseThreadResources()
+
+
+def build_id():
+    """The source hash the loaded library was built from (detexb200Version(): "... build <id>...")."""
+    v = load().detexb200Version().decode()
+    return v.split("build ")[1].split(";")[0].split(")")[0].strip() if "build " in v else "unknown"
 
 
 # ---- KTX / DDS ingest straight to device memory (include/detex_b200.h) ----------------------------

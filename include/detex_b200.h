@@ -141,6 +141,28 @@ DETEXB200_API int detexb200LoadTextureFileToDevice(const char *filename, int max
 	uint32_t *texture_format_out, int *all_valid_out, void *stream);
 DETEXB200_API void detexb200FreeDeviceImages(detexb200DeviceImage *levels, int nu_levels);
 
+/*
+ * Which GPUs the host-pointer texture calls of include/detex.h (detexDecompressTextureLinear / ...Tiled,
+ * reference texture.c:77-145) use.  n == 0 (the default): the calling thread's current CUDA device.  n >= 1: every
+ * call cuts the texture into slabs of block rows (LINEAR) or block runs (TILED) and deals them round-robin to the
+ * listed devices, each moving its slabs over its own PCIe link (index-range sharding, no exchange
+ * between devices; results land in the caller's one pixel buffer).  Process-wide; also settable without touching
+ * the host program through the environment: DETEXB200_DEVICES=all | <count> | <ordinal>,<ordinal>,...
+ */
+DETEXB200_API int detexb200SetDevices(int n, const int *device_ids);
+/*
+ * Threads of the copy pool that serves pageable (malloc'd) caller buffers and multi-device calls: each thread
+ * stages one slab at a time through its own pinned bounce buffers.  0 = default (half the hardware threads,
+ * between 4 and 16, at least 3 per device).  Environment: DETEXB200_HOST_THREADS.
+ */
+DETEXB200_API int detexb200SetHostThreads(int n);
+/*
+ * Give the calling thread's streams, device buffers and pinned buffers back to the driver now (they are also
+ * released when the thread exits).  The next call on this thread sets them up again, on whatever CUDA device is
+ * current then.
+ */
+DETEXB200_API void detexb200ReleaseThreadResources(void);
+
 /* Library / device information. */
 DETEXB200_API int detexb200DeviceCount(void);
 DETEXB200_API const char *detexb200Version(void);

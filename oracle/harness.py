@@ -223,6 +223,8 @@ def load_harness():
         h.cpu_harness_fnv1a64.restype = C.c_uint64
         h.cpu_harness_splitmix64.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p]
         h.cpu_harness_splitmix64.restype = None
+        h.cpu_harness_tree_hash.argtypes = [C.c_void_p, C.c_size_t, C.c_int]
+        h.cpu_harness_tree_hash.restype = C.c_uint64
         _cache["harness"] = h
     return _cache["harness"]
 
@@ -243,11 +245,14 @@ def fnv1a64(buf):
     return int(load_harness().cpu_harness_fnv1a64(a.ctypes.data, a.size))
 
 
-def tree_hash(buf, seg=4096):
+def tree_hash(buf, seg=4096, threads=None):
     """CPU statement of detexb200HashDevice (detex_b200/csrc/aux.cu): FNV-1a-64 every
     4096-byte segment, treat the little-endian array of segment hashes as the next buffer,
-    repeat until one hash is left."""
+    repeat until one hash is left.  threads=None: the numpy statement below; threads=N: the same
+    construction in C on N host threads (cpu_harness.c, for multi-gigabyte buffers)."""
     a = np.ascontiguousarray(buf).view(np.uint8).reshape(-1)
+    if threads is not None and seg == 4096:
+        return int(load_harness().cpu_harness_tree_hash(a.ctypes.data, a.size, int(threads)))
     while True:
         n = a.size
         n_seg = max(1, (n + seg - 1) // seg)
@@ -302,9 +307,9 @@ def force_modes(fmt, blocks, modes=None):
     return b.reshape(-1)
 
 
-def cpu_decode(lib, fmt, blocks, width, height, linear=True, pixel_format=None, threads=1):
+def cpu_decode(lib, fmt, blocks, width, height, linear=True, pixel_format=None, threads=1, out=None):
     """Decode with a CPU library through detexDecompressTexture{Linear,Tiled}.
-    Returns (pixels uint8[], ok, seconds)."""
+    Returns (pixels uint8[], ok, seconds).  out: a caller-owned (warm) output buffer to reuse."""
     tf, bs, ps_native = FORMATS[fmt]
     pf = (tf & 0xFFFF) if pixel_format is None else pixel_format
     ps = pixel_size(pf)
@@ -312,7 +317,9 @@ def cpu_decode(lib, fmt, blocks, width, height, linear=True, pixel_format=None, 
     blocks = np.ascontiguousarray(blocks).view(np.uint8).reshape(-1)
     assert blocks.size == wib * hib * bs
     n_out = width * height * ps if linear else wib * hib * 16 * ps
-    out = np.zeros(n_out, dtype=np.uint8)
+    if out is None:
+        out = np.zeros(n_out, dtype=np.uint8)
+    assert out.dtype == np.uint8 and out.size == n_out and out.flags["C_CONTIGUOUS"]
     fn = lib.detexDecompressTextureLinear if linear else lib.detexDecompressTextureTiled
     secs = C.c_double(0)
     ok = load_harness().cpu_harness_decode(C.cast(fn, C.c_void_p), tf, blocks.ctypes.data,

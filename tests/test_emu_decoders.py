@@ -90,12 +90,14 @@ def test_per_block_flags_and_masks(emu, cpu, fmt):
                     assert np.array_equal(tiles[i], o[: 16 * ps]), (fmt, flags, mask, i)
 
 
-def test_bc7_byte_table_experiment_is_bit_exact(tmp_path, cpu):
-    """-DDETEXB200_BC7_TABLE2 (decode_bptc.cuh: modes 2, 3, 4, 5, 7 as PRMT byte-table look-ups; prepared for
-    measurement, not the default build): the same bytes as the checker for every mode, 3 x 32 768 blocks each
-    (all 64 partitions, all anchors, all four rotations occur)."""
-    so = str(tmp_path / "libemu_table2.so")
-    subprocess.run(["g++", "-std=c++17", "-O1", "-fPIC", "-shared", "-DDETEXB200_BC7_TABLE2", "-I", EMU, "-I",
+@pytest.mark.parametrize("variant", ["-DDETEXB200_BC7_TABLE2", "-DDETEXB200_BC7_PERPIXEL"])
+def test_bc7_both_pixel_paths_are_bit_exact(tmp_path, cpu, variant):
+    """decode_bptc.cuh has two ways to turn endpoints + indices into pixels: PRMT byte-table look-ups for modes
+    2, 3, 4, 5, 7 (the default build) and the per-pixel interpolation for every mode (-DDETEXB200_BC7_PERPIXEL,
+    kept for A/B runs): the same bytes as the checker for every mode, 3 x 32 768 blocks each (all 64 partitions,
+    all anchors, all four rotations occur)."""
+    so = str(tmp_path / "libemu_variant.so")
+    subprocess.run(["g++", "-std=c++17", "-O1", "-fPIC", "-shared", variant, "-I", EMU, "-I",
                     os.path.join(ROOT, "detex_b200", "csrc"), "-o", so, os.path.join(EMU, "emu_all.cpp")], check=True)
     lib = C.CDLL(so)
     lib.emu_decode.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]

@@ -352,8 +352,191 @@ def test_bc7_flow_kernel():
     """The alternative BC7 kernel (palette + selectors, barrier-free dataflow; kernels.cu
     decode_bc7_flow_kernel) is selected per process with DETEXB200_BC7_KERNEL=flow: check it in a
     child process (tests/bc7_flow_check.py)."""
+    if b"+experiments" not in D.load().detexb200Version():
+        pytest.skip("library built without -DDETEXB200_EXPERIMENTS (the default): the dataflow kernel is not in it")
     here = os.path.dirname(os.path.abspath(__file__))
     env = dict(os.environ, DETEXB200_BC7_KERNEL="flow")
     r = subprocess.run([sys.executable, os.path.join(here, "bc7_flow_check.py")], env=env, capture_output=True,
                        text=True, timeout=600)
     assert r.returncode == 0 and r.stdout.strip().startswith("OK"), r.stdout[-2000:] + r.stderr[-4000:]
+
+
+# ---- round 2: narrow images, pageable / pinned callers, threads, device sets, configs[4] at full size ----------
+def test_linear_image_narrower_than_its_block_grid(cpu):
+    """width may be anything in ((wib - 1) * 4, wib * 4] for the reference (texture.c:133-136 clips the last
+    block column); a multiple of four below wib * 4 used to take the unclipped fast path and write past the rows
+    (ADVICE r1).  Device API with explicit wib, guard bytes behind the image, every format family."""
+    for fmt in ("BC1", "BPTC", "BPTC_FLOAT", "ETC2", "EAC_R11", "RGTC1"):
+        tf, bs, ps = H.FORMATS[fmt]
+        for wib, hib, width, height in ((8, 8, 29, 32), (8, 8, 30, 30), (300, 20, 1197, 77), (2, 1, 5, 4), (1100, 4, 4397, 16)):
+            n = wib * hib
+            blocks = H.synth_blocks(fmt, n, seed=wib + hib)
+            if fmt.startswith("BPTC"):
+                blocks = H.force_modes(fmt, blocks)
+            # the checker decodes the full block grid; the image is its top-left width x height corner
+            full, _, _ = H.cpu_decode(cpu, fmt, blocks, wib * 4, hib * 4, linear=True)
+            want = full.reshape(hib * 4, wib * 4 * ps)[:height, : width * ps].reshape(-1)
+            d_blocks = torch.from_numpy(blocks.copy()).cuda()
+            d_out = torch.full((width * height * ps + 4096,), 0xA5, dtype=torch.uint8, device="cuda")
+            D.decode_device(fmt, d_blocks.data_ptr(), width, height, d_out.data_ptr(), layout=D.LAYOUT_LINEAR, wib=wib, hib=hib)
+            torch.cuda.synchronize()
+            got = d_out.cpu().numpy()
+            assert np.array_equal(got[: want.size], want), (fmt, wib, hib, width, height)
+            assert (got[want.size:] == 0xA5).all(), ("write past the image", fmt, wib, hib, width, height)
+    # a width that is a multiple of four but SMALLER than the grid (undefined in the reference, legal for
+    # detexb200DecodeDevice's validation): the columns that exist are decoded, nothing else is touched
+    for fmt in ("BC1", "BPTC"):
+        tf, bs, ps = H.FORMATS[fmt]
+        wib, hib, width, height = 1024, 4, 4, 16
+        blocks = H.force_modes(fmt, H.synth_blocks(fmt, wib * hib, seed=2)) if fmt == "BPTC" else H.synth_blocks(fmt, wib * hib, seed=2)
+        full, _, _ = H.cpu_decode(cpu, fmt, blocks, wib * 4, hib * 4, linear=True)
+        want = full.reshape(hib * 4, wib * 4 * ps)[:height, : width * ps].reshape(-1)
+        d_out = torch.full((width * height * ps + 65536,), 0xA5, dtype=torch.uint8, device="cuda")
+        D.decode_device(fmt, torch.from_numpy(blocks.copy()).cuda().data_ptr(), width, height, d_out.data_ptr(),
+                        layout=D.LAYOUT_LINEAR, wib=wib, hib=hib)
+        torch.cuda.synchronize()
+        got = d_out.cpu().numpy()
+        assert np.array_equal(got[: want.size], want) and (got[want.size:] == 0xA5).all(), fmt
+
+
+def _host_call(fmt, blocks, w, h, linear, pf, pinned):
+    """detexDecompressTexture{Linear,Tiled} on pageable (numpy) or pinned (torch) caller buffers."""
+    tf, bs, ps_native = H.FORMATS[fmt]
+    ps = H.pixel_size(pf)
+    wib, hib = (w + 3) // 4, (h + 3) // 4
+    n_out = w * h * ps if linear else wib * hib * 16 * ps
+    if pinned:
+        hb = torch.from_numpy(blocks.copy()).pin_memory()
+        out = torch.zeros(n_out, dtype=torch.uint8).pin_memory()
+        in_ptr, out_ptr = hb.data_ptr(), out.data_ptr()
+    else:
+        hb = blocks.copy()
+        out = np.zeros(n_out, dtype=np.uint8)
+        in_ptr, out_ptr = hb.ctypes.data, out.ctypes.data
+    tex = D.DetexTexture(tf, in_ptr, w, h, wib, hib)
+    fn = D.load().detexDecompressTextureLinear if linear else D.load().detexDecompressTextureTiled
+    ok = fn(C.byref(tex), out_ptr, pf)
+    return (out.numpy() if pinned else out), bool(ok)
+
+
+@pytest.mark.parametrize("pinned", [False, True])
+def test_host_api_pageable_and_pinned_callers(cpu, pinned):
+    """The host-pointer API takes two routes (api.cu): pinned caller buffers are DMA'd directly from the calling
+    thread's lanes; pageable ones (what malloc'ing callers such as detex-convert.c:303-310 pass) go through the copy
+    pool's pinned bounce buffers.  Same bytes either way: several slabs, ragged sizes, both layouts, invalid blocks,
+    fused and two-pass conversions."""
+    PF = H.PIXEL_FORMATS
+    cases = [("BC1", 2048, 2052, None, 0), ("BPTC", 2048, 1030, None, 0), ("BPTC", 1024, 2048, None, 8),
+             ("BPTC_FLOAT", 1024, 1024, None, 14), ("ETC2_EAC", 1532, 1000, None, 0), ("EAC_SIGNED_R11", 4096, 1024, None, 0),
+             ("BC3", 2048, 1024, PF["BGRA8"], 0), ("BC1", 2048, 1024, PF["RGBA16"], 0), ("ETC1", 1024, 2048, PF["RGB8"], 0)]
+    for fmt, w, h, pf, force in cases:
+        tf, bs, _ = H.FORMATS[fmt]
+        pf = (tf & 0xFFFF) if pf is None else pf
+        n = ((w + 3) // 4) * ((h + 3) // 4)
+        blocks = H.synth_blocks(fmt, n, seed=w + h)
+        if force:
+            blocks = H.force_modes(fmt, blocks)
+        for linear in (True, False):
+            want, ok_w, _ = H.cpu_decode(cpu, fmt, blocks, w, h, linear=linear, pixel_format=pf, threads=8)
+            got, ok = _host_call(fmt, blocks, w, h, linear, pf, pinned)
+            assert ok == ok_w, (fmt, w, h, linear, D.detexGetErrorMessage())
+            assert np.array_equal(got, want), (fmt, w, h, linear, pinned)
+
+
+def test_host_api_from_many_threads(cpu):
+    """The reference is re-entrant and lock-free on this path (TLS only: convert.c:870-873, misc.c:75); callers may
+    decode from many threads at once.  Six threads, mixed formats, layouts, sizes on both sides of
+    the copy-pool threshold, pinned and pageable buffers, each checked against the checker; one thread decodes an
+    invalid texture and must see ITS error, the others none."""
+    import threading
+    jobs = [("BC1", 2048, 1024, True, False), ("BPTC", 1024, 1024, True, False), ("BPTC_FLOAT", 512, 1024, False, False),
+            ("ETC2", 256, 256, True, False), ("EAC_RG11", 1024, 512, False, True), ("BC3", 1028, 516, True, True)]
+    prepared = []
+    for fmt, w, h, linear, pinned in jobs:
+        n = ((w + 3) // 4) * ((h + 3) // 4)
+        blocks = H.synth_blocks(fmt, n, seed=len(prepared) + 1)
+        if fmt.startswith("BPTC") and fmt != "BPTC":
+            blocks = H.force_modes(fmt, blocks)
+        want, ok_w, _ = H.cpu_decode(cpu, fmt, blocks, w, h, linear=linear, threads=4)
+        prepared.append((fmt, w, h, linear, pinned, blocks, want, ok_w))
+    errors = []
+
+    def work(k):
+        fmt, w, h, linear, pinned, blocks, want, ok_w = prepared[k]
+        try:
+            for _ in range(4):
+                got, ok = _host_call(fmt, blocks, w, h, linear, H.FORMATS[fmt][0] & 0xFFFF, pinned)
+                msg = D.detexGetErrorMessage()
+                if ok != ok_w or not np.array_equal(got, want):
+                    errors.append((fmt, "pixels or verdict differ"))
+                if not ok and ("0x%08X" % H.FORMATS[fmt][0]) not in msg:
+                    errors.append((fmt, "error text of another thread: " + msg))
+            D.release_thread_resources()
+        except Exception as exc:       # noqa: BLE001
+            errors.append((fmt, repr(exc)))
+
+    threads = [threading.Thread(target=work, args=(k,)) for k in range(len(prepared))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=300)
+    assert not errors, errors
+    assert not prepared[1][7], "the BC7 job is meant to contain invalid blocks (distribution U)"
+
+
+def test_device_set_spreads_one_call_over_gpus(cpu):
+    """detexb200SetDevices (SURVEY.md 8e behind the C ABI): one detexDecompressTextureLinear call, slabs dealt
+    round-robin to the listed devices.  With one GPU the set {0} still takes the pool route; with more, all of them."""
+    n_dev = D.load().detexb200DeviceCount()
+    sets = [[0]] + ([list(range(n_dev))] if n_dev > 1 else []) + ([[1, 0]] if n_dev > 1 else [])
+    try:
+        for devs in sets:
+            D.set_devices(devs)
+            for fmt, w, h, linear, force in (("BC1", 4096, 2048, True, 0), ("BPTC", 2048, 2048, True, 8), ("EAC_RG11", 2048, 1024, False, 0)):
+                n = (w // 4) * (h // 4)
+                blocks = H.synth_blocks(fmt, n, seed=9)
+                if force:
+                    blocks = H.force_modes(fmt, blocks)
+                want, ok_w, _ = H.cpu_decode(cpu, fmt, blocks, w, h, linear=linear, threads=8)
+                for pinned in (True, False):
+                    got, ok = _host_call(fmt, blocks, w, h, linear, H.FORMATS[fmt][0] & 0xFFFF, pinned)
+                    assert ok == ok_w and np.array_equal(got, want), (devs, fmt, pinned)
+        with pytest.raises(D.DetexError):
+            D.set_devices([n_dev])
+    finally:
+        D.set_devices([])
+
+
+def test_config_mixed_tiled_full_size(cpu):
+    """configs[4] at FULL size on one GPU: 33 333 334 ETC2 + 33 333 333 EAC_RG11 + 33 333 333 RGTC2 blocks (seeds 1 / 2 / 3),
+    TILED.  Compared through the hash of hashes (device: detexb200HashDevice; host: the same construction over the
+    checker's output) and byte for byte over the first and last 32 MiB."""
+    threads = os.cpu_count() or 1
+    for fmt, seed, n in (("ETC2", 1, 33_333_334), ("EAC_RG11", 2, 33_333_333), ("RGTC2", 3, 33_333_333)):
+        tf, bs, ps = H.FORMATS[fmt]
+        n_gen = n + (n & 1)                        # the generator works in 16-byte units
+        d_blocks = torch.empty(n_gen * bs, dtype=torch.uint8, device="cuda")
+        D.generate_blocks_device(d_blocks.data_ptr(), n_gen, bs, seed=seed)
+        d_out = torch.empty(n * 16 * ps, dtype=torch.uint8, device="cuda")
+        flag = torch.zeros(1, dtype=torch.int32, device="cuda")
+        D.decode_device(fmt, d_blocks.data_ptr(), 4 * n, 4, d_out.data_ptr(), layout=D.LAYOUT_TILED, wib=n, hib=1,
+                        d_invalid=flag.data_ptr())
+        torch.cuda.synchronize()
+        host_blocks = d_blocks[: n * bs].cpu().numpy()
+        assert np.array_equal(host_blocks[: 1 << 20], H.synth_blocks(fmt, (1 << 20) // bs, seed=seed))
+        # the checker decodes the flat array as rows of 1000 blocks + a ragged tail
+        rows = n // 1000
+        want = np.empty(n * 16 * ps, dtype=np.uint8)
+        body, ok1, _ = H.cpu_decode(cpu, fmt, host_blocks[: rows * 1000 * bs], 4000, 4 * rows, linear=False, threads=threads)
+        want[: body.size] = body
+        ok2 = True
+        if n > rows * 1000:
+            tail, ok2, _ = H.cpu_decode(cpu, fmt, host_blocks[rows * 1000 * bs:], 4 * (n - rows * 1000), 4, linear=False)
+            want[body.size:] = tail
+        del body
+        assert bool(flag.item() == 0) == (ok1 and ok2), fmt
+        assert D.hash_device(d_out.data_ptr(), d_out.numel()) == H.tree_hash(want, threads=threads), fmt
+        m = 32 << 20
+        assert np.array_equal(d_out[:m].cpu().numpy(), want[:m]) and np.array_equal(d_out[-m:].cpu().numpy(), want[-m:]), fmt
+        del d_blocks, d_out, want
+        torch.cuda.empty_cache()

@@ -207,3 +207,66 @@ def test_single_level_entry_points(tmp_path):
         tx = t.contents
         assert (tx.format, tx.width, tx.height, tx.width_in_blocks, tx.height_in_blocks) == (0x0B800334, 24, 24, 6, 6)
         assert bytes(C.cast(tx.data, C.POINTER(C.c_uint8 * len(pay[0]))).contents) == pay[0]
+
+
+def test_crafted_headers_are_rejected_not_trusted(tmp_path):
+    """Sizes in a KTX / DDS header are untrusted input: dimensions whose block count overflows 32-bit
+    arithmetic, negative dimensions and negative level counts must end in an error return -- never in a huge or
+    wrapped allocation, a backwards seek or a crash.  (Only the product is called: the reference computes these
+    sizes in `int` and is not safe to run on such files.)"""
+    lib = _lib()
+    rng = np.random.default_rng(5)
+    dims, pay = _payloads(rng, 32, 32, 8, 4, 1)
+    pk, pd = str(tmp_path / "good.ktx"), str(tmp_path / "good.dds")
+    CF.write_ktx(pk, 0x83F0, 0, 0, 32, 32, 8, 4, pay)
+    CF.write_dds(pd, 32, 32, pay, four_cc=b"DXT1")
+    ktx, dds = open(pk, "rb").read(), open(pd, "rb").read()
+
+    def u32(v):
+        return (v & 0xFFFFFFFF).to_bytes(4, "little")
+
+    def ktx_with(width=None, height=None, levels=None, kv=None, image_size=None):
+        b = bytearray(ktx)
+        for off, v in ((36, width), (40, height), (56, levels), (60, kv)):     # header words 9, 10, 14, 15
+            if v is not None:
+                b[off:off + 4] = u32(v)
+        if image_size is not None:
+            b[64:68] = u32(image_size)
+        return bytes(b)
+
+    def dds_with(width=None, height=None, levels=None):
+        b = bytearray(dds)
+        for off, v in ((16, width), (12, height)):      # dwWidth at 4 + 12, dwHeight at 4 + 8
+            if v is not None:
+                b[off:off + 4] = u32(v)
+        if levels is not None:
+            b[8:12] = u32(int.from_bytes(b[8:12], "little") | 0x20000)
+            b[28:32] = u32(levels)
+        return bytes(b)
+
+    cases = {
+        # wib * hib = 65536 * 65535 wraps negative in int; times 8 bytes it wraps again and can match image_size
+        "wrap.ktx": ktx_with(width=262144, height=262140, image_size=(65536 * 65535 * 8) & 0xFFFFFFFF),
+        "huge.ktx": ktx_with(width=0x7FFFFFFF, height=0x7FFFFFFF, image_size=8),
+        "negw.ktx": ktx_with(width=-32, image_size=len(pay[0])),
+        "negh.ktx": ktx_with(height=-4),
+        "neglevels.ktx": ktx_with(levels=-1),
+        "negkv.ktx": ktx_with(kv=-64),
+        "hugekv.ktx": ktx_with(kv=0x7FFFFFF0),
+        "wrap.dds": dds_with(width=262144, height=262140),
+        "huge.dds": dds_with(width=0x7FFFFFFF, height=0x7FFFFFFF),
+        "negw.dds": dds_with(width=-32),
+        "negh.dds": dds_with(height=-4),
+        "manylevels.dds": dds_with(levels=0x7FFFFFFF),
+    }
+    for name, content in cases.items():
+        path = str(tmp_path / name)
+        open(path, "wb").write(content)
+        got = _load(lib, "detexLoadTextureFileWithMipmaps", path, 16)
+        if name == "neglevels.ktx":
+            assert got == [] or isinstance(got, str), name      # zero levels: nothing loaded, nothing trusted
+        else:
+            assert isinstance(got, str) and got, (name, got if isinstance(got, str) else len(got))
+    # the untouched files still load
+    assert len(_load(lib, "detexLoadTextureFileWithMipmaps", pk, 16)) == 1
+    assert len(_load(lib, "detexLoadTextureFileWithMipmaps", pd, 16)) == 1

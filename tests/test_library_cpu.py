@@ -3,6 +3,7 @@ headers declare, fails loudly without a GPU, and its packed tables match the ora
 import ctypes as C
 import os
 import re
+import subprocess
 
 import numpy as np
 import pytest
@@ -36,6 +37,64 @@ def test_library_exports_every_declared_symbol():
 
 def test_version_string():
     assert b"sm_100a" in D.load().detexb200Version()
+    from detex_b200 import build as B
+    # the build id in the version string is the hash of the sources the library was compiled from
+    assert D.build_id() == B.build_id(), "libdetex_b200.so is older than its sources: rebuild (python -m detex_b200.build)"
+
+
+def test_header_lut_data_symbols_match_the_reference():
+    """The four arrays behind the inline helpers of the reference header (detex.h:933-982: detexClamp0To255,
+    detexDivide0To767By3, ...By7, ...By5) are exported with the reference's contents, so that a host compiled
+    against the reference's own header links against this library alone."""
+    lib = D.load()
+    ref = H.load_reference()
+    for name, n in (("detex_clamp0to255_table", 767), ("detex_division_by_3_table", 768),
+                    ("detex_division_by_7_table", 1792), ("detex_division_by_5_table", 1280)):
+        mine = bytes((C.c_uint8 * n).in_dll(lib, name))
+        if name.startswith("detex_clamp"):
+            assert mine == bytes(min(255, max(0, i - 255)) for i in range(n))
+        else:
+            d = int(name.split("_")[3])
+            assert mine == bytes(i // d for i in range(n))
+        if ref is not None:
+            assert mine == bytes((C.c_uint8 * n).in_dll(ref, name)), name
+
+
+REF_HEADER = "/root/reference/detex.h"
+
+
+@pytest.mark.skipif(not os.path.exists(REF_HEADER), reason="reference header only exists in the build container")
+def test_c_host_built_against_the_reference_header_links_this_library_alone(tmp_path):
+    """A C99 host written against the REFERENCE's detex.h -- using the inline helpers that pull in the LUT data
+    symbols, the texture-level API and the error message -- compiles, links against libdetex_b200.so and nothing
+    else of detex, and runs: without a GPU the decode call fails loudly, the helpers work either way."""
+    src = tmp_path / "host.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <string.h>
+#include "detex.h"
+int main(void) {
+	if (detexClamp0To255(-7) != 0 || detexClamp0To255(300) != 255 || detexClamp0To255(77) != 77) return 2;
+	if (detexDivide0To767By3(767) != 255 || detexDivide0To1791By7(1791) != 255 || detexDivide0To1279By5(1279) != 255) return 3;
+	if (detexDivideMinus895To895By7(-895) != -127 || detexDivideMinus639To639By5(-639) != -127) return 4;
+	uint8_t blocks[2 * 8] = { 0 }, pixels[8 * 4 * 4];
+	detexTexture t = { DETEX_TEXTURE_FORMAT_BC1, blocks, 8, 4, 2, 1 };
+	bool ok = detexDecompressTextureLinear(&t, pixels, DETEX_PIXEL_FORMAT_RGBX8);
+	printf("%d %s\n", (int)ok, ok ? "" : detexGetErrorMessage());
+	return 0;
+}
+''')
+    exe = tmp_path / "host"
+    libdir = os.path.join(ROOT, "detex_b200")
+    subprocess.run(["gcc", "-std=c99", "-D_POSIX_C_SOURCE=200809L", "-I", os.path.dirname(REF_HEADER), str(src), "-o", str(exe),
+                    "-L", libdir, "-l:libdetex_b200.so", "-Wl,-rpath," + libdir], check=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
+    ok, _, msg = r.stdout.strip().partition(" ")
+    if D.load().detexb200DeviceCount() > 0:
+        assert ok == "1"
+    else:
+        assert ok == "0" and "no CPU fallback" in msg
 
 
 def test_header_constants_match_reference_values():

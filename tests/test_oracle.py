@@ -133,3 +133,14 @@ def test_oracle_per_block_flags_and_masks(oracle, fmt):
                 assert r1 == r2, (fmt, flags, mask, i)
                 if r1:
                     assert np.array_equal(o1, o2), (fmt, flags, mask, i)
+
+
+def test_c_tree_hash_equals_the_numpy_statement():
+    """cpu_harness_tree_hash (threaded C, used on multi-gigabyte outputs) against harness.tree_hash (numpy): empty,
+    ragged, exactly one segment, several levels."""
+    rng = np.random.default_rng(11)
+    for n in (0, 1, 4095, 4096, 4097, 3 * 4096 + 5, 512 * 4096, 513 * 4096 + 77, 5_000_000):
+        a = rng.integers(0, 256, n, dtype=np.uint8)
+        want = H.tree_hash(a)
+        for threads in (1, 3, 8):
+            assert H.tree_hash(a, threads=threads) == want, (n, threads)
