@@ -18,6 +18,9 @@
 #include <thread>
 #include <string>
 #include <vector>
+#if defined(__x86_64__)
+#include <emmintrin.h>
+#endif
 
 #include "../../include/detex.h"
 #include "../../include/detex_b200.h"
@@ -61,7 +64,7 @@ inline int block_bytes(uint32_t tf) { return 8 + ((tf & DETEX_TEXTURE_FORMAT_128
 // device it has worked on (pageable caller buffers and multi-device calls, below).
 constexpr int N_STREAMS = 4;
 constexpr size_t SLAB_BYTES = 16u << 20;	// output bytes per slab, pinned single-device path
-constexpr size_t POOL_SLAB_BYTES = 8u << 20;	// ... copy-pool path (more, smaller jobs: smoother tail)
+constexpr size_t POOL_SLAB_BYTES = 4u << 20;	// ... copy-pool path (more, smaller jobs: smoother tail)
 constexpr size_t POOL_MIN_BYTES = 4u << 20;	// smaller textures are not worth a thread hop
 
 std::atomic<bool> g_exiting{false};		// set by an atexit handler: no CUDA calls from destructors after it
@@ -427,6 +430,37 @@ int enqueue_slab(Lane &L, const TexCall &c, const Slab &s, const void *h_src, vo
 // a handful of threads the host copies of some slabs overlap the DMA transfers of others and the PCIe link stays
 // busy.  The same pool spreads ONE call over several GPUs (detexb200SetDevices / DETEXB200_DEVICES): slab k goes
 // to device k mod G, every device moving its slabs over its own PCIe link.
+// Copy a pinned bounce buffer into the caller's (pageable) pixel buffer without reading the destination lines
+// first: plain stores cost a read-for-ownership per line on top of the write, and this copy runs beside the DMA
+// engine's own writes into host memory -- the host memory system, not the PCIe link, is what a pageable call
+// is bound by.  SSE2 streaming stores (baseline x86-64); head and tail through memcpy.
+void stream_copy(void *dst, const void *src, size_t n) {
+#if defined(__x86_64__)
+	uint8_t *d = (uint8_t *)dst;
+	const uint8_t *s = (const uint8_t *)src;
+	if (n < 4096) {
+		memcpy(d, s, n);
+		return;
+	}
+	const size_t head = (size_t)((0 - (uintptr_t)d) & 63u);
+	memcpy(d, s, head);
+	d += head; s += head; n -= head;
+	const size_t lines = n / 64;
+	for (size_t i = 0; i < lines; i++) {
+		const __m128i a = _mm_loadu_si128((const __m128i *)(s + 64 * i)), b = _mm_loadu_si128((const __m128i *)(s + 64 * i + 16));
+		const __m128i c = _mm_loadu_si128((const __m128i *)(s + 64 * i + 32)), e = _mm_loadu_si128((const __m128i *)(s + 64 * i + 48));
+		_mm_stream_si128((__m128i *)(d + 64 * i), a);
+		_mm_stream_si128((__m128i *)(d + 64 * i + 16), b);
+		_mm_stream_si128((__m128i *)(d + 64 * i + 32), c);
+		_mm_stream_si128((__m128i *)(d + 64 * i + 48), e);
+	}
+	_mm_sfence();
+	memcpy(d + 64 * lines, s + 64 * lines, n - 64 * lines);
+#else
+	memcpy(dst, src, n);
+#endif
+}
+
 struct CallState {
 	std::mutex m;
 	std::condition_variable cv;
@@ -492,7 +526,7 @@ private:
 		    (e = cudaEventSynchronize(L.done)) != cudaSuccess)
 			return cuda_fail("slab pipeline", e);
 		if (j.bounce_out)
-			memcpy(c.out + s.out_off, L.h_out, s.out_len);
+			stream_copy(c.out + s.out_off, L.h_out, s.out_len);
 		*invalid = *L.h_flag != 0;
 		return DETEXB200_OK;
 	}
@@ -623,9 +657,10 @@ bool decode_texture_host(const detexTexture *t, uint8_t *pixel_buffer, uint32_t 
 		const std::vector<int> devs = devices.empty() ? std::vector<int>(1, cur) : devices;
 		int want = g_host_threads;
 		if (want <= 0) {
+			// pool threads sleep while their slab is on the link and copy while it is not: one per hardware
+			// thread keeps both the link and the host memory system busy (measured: 8 -> 16 threads on a 16-thread box)
 			const int hw = (int)std::thread::hardware_concurrency();
-			want = hw / 2;
-			want = want < 4 ? 4 : (want > 16 ? 16 : want);
+			want = hw < 4 ? 4 : (hw > 32 ? 32 : hw);
 			if (want < 3 * (int)devs.size())
 				want = 3 * (int)devs.size();
 		}

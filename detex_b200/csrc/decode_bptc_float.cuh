@@ -154,8 +154,35 @@ __device__ __forceinline__ int sext_runtime(uint32_t v, int bits) {
 // pixel i (InterpolateFloat's result, before the final scaling to a half-float pattern).  The native
 // sink below finishes them into FLOAT_RGBX16 / SIGNED_FLOAT_RGBX16 words; tone.cuh has a sink that
 // goes on to 8-bit pixels.
+// Two ways to hand a pixel to a sink:
+//   * integer (FLOAT_PIPE = false): sink(i, v_r, v_g, v_b) with v = InterpolateFloat's 16-bit result;
+//   * float (FLOAT_PIPE = true): sink.emit(i, y_r, y_g, y_b) with y = BIAS + v held in a float whose unit in the last
+//     place is 1 (BIAS = 2^23 unsigned, 1.5 * 2^23 signed), i.e. the integer v sits in the mantissa field.  The
+//     interpolation and the finish then run on the FP32 multiply-add pipe, which this integer-bound decoder leaves
+//     idle: the integer ALU pipe issues a warp instruction every other cycle, the FMA pipe every cycle (ncu, round 2:
+//     ALU pipe 72-77 % busy, FMA 18-23 %).  Every step below is exact -- all operands are integers or integers / 64
+//     below 2^24, sums and fused products included -- so the floors are the only roundings and they are asked for
+//     explicitly (round-down adds against the bias): bit-exact with the integer statement, which
+//     tests/test_emu_decoders.py checks against the oracle on the CPU.
+__device__ __forceinline__ float sat01(float f) {
+#ifdef DETEXB200_HOST_EMU
+	return emu_sat(f);
+#else
+	return __saturatef(f);
+#endif
+}
+
 template <bool SIGNED>
 struct Bc6hHalfSink {
+	// Measured (B200, 4.19 M blocks, G blocks/s LINEAR U / M, integer -> float pipe): signed 19.0 / 18.0 -> 22.4 / 21.1
+	// (the sign-magnitude finish is six integer-pipe instructions per component and three on the FMA pipe, 162 M ->
+	// 146 M warp instructions); unsigned 25.1 / 25.1 -> 23.8 / 24.3 (115 M -> 127 M instructions: the kernel is
+	// issue-bound while it decodes, so the better pipe balance does not pay for the extra instructions).  Hence:
+#ifdef DETEXB200_BC6H_FLOAT_PIPE_ALL
+	static constexpr bool FLOAT_PIPE = true;
+#else
+	static constexpr bool FLOAT_PIPE = SIGNED;
+#endif
 	uint32_t (&px)[32];
 	__device__ __forceinline__ void operator()(int i, int v0, int v1, int v2) const {
 		const int v[3] = { v0, v1, v2 };
@@ -172,6 +199,22 @@ struct Bc6hHalfSink {
 		px[2 * i] = (h[0] & 0xFFFFu) | (h[1] << 16);		// Q10: R | G<<16 | B<<32, X = 0
 		px[2 * i + 1] = h[2] & 0xFFFFu;
 	}
+	// y = BIAS + v  ->  a float whose low 16 mantissa bits are the half-float pattern
+	static __device__ __forceinline__ uint32_t finish(float y) {
+		if (SIGNED) {
+			// sign-magnitude (:577-613): mag = (|v| * 31) >> 5, sign bit when v < 0 and mag != 0, i.e. v <= -2
+			const float v = __fsub_rn(y, 12582912.0f);
+			const float z = __fmaf_rd(fabsf(v), 0.96875f, 8388608.0f);		// 2^23 + floor(|v| * 31 / 32)
+			const float neg = sat01(__fsub_rn(-1.0f, v));				// 1 for v <= -2, 0 for v >= -1
+			return __float_as_uint(__fmaf_rn(neg, 32768.0f, z));
+		}
+		// (v * 31) >> 6 (:616-621): y * 31/64 - 2^23 * 31/64 = v * 31 / 64 exactly, then the floor
+		return __float_as_uint(__fadd_rd(__fmaf_rn(y, 0.484375f, -4063232.0f), 8388608.0f));
+	}
+	__device__ __forceinline__ void emit(int i, float y0, float y1, float y2) const {
+		px[2 * i] = prmt(finish(y0), finish(y1), 0x5410);	// Q10: R | G<<16 | B<<32, X = 0
+		px[2 * i + 1] = finish(y2) & 0xFFFFu;
+	}
 };
 
 template <bool SIGNED, int NS, typename Sink>
@@ -180,7 +223,13 @@ const BptcTables &tab, const Sink &sink) {
 	constexpr int NE = 2 * NS, IB = NS == 1 ? 4 : 3;
 	const uint32_t epmask = epb >= 32 ? 0xFFFFFFFFu : ((1u << epb) - 1u);
 	const int delta_bits[3] = { dr, dg, db };
+#ifdef DETEXB200_BC6H_INT_PIPE
+	constexpr bool FP = false;			// A/B: the integer statement for every sink
+#else
+	constexpr bool FP = Sink::FLOAT_PIPE;
+#endif
 	int a_c[NS][3], k_c[NS][3];		// A = 64*e0 + 32, K = e1 - e0 per subset and component
+	float a_f[NS][3], k_f[NS][3];		// the same divided by 64, as floats (float pipe)
 #pragma unroll
 	for (int c = 0; c < 3; c++) {
 		int e[NE];
@@ -225,8 +274,15 @@ const BptcTables &tab, const Sink &sink) {
 		}
 #pragma unroll
 		for (int s = 0; s < NS; s++) {
-			a_c[s][c] = 64 * e[2 * s] + 32;
-			k_c[s][c] = e[2 * s + 1] - e[2 * s];
+			if constexpr (FP) {
+				const float e0 = __int2float_rn(e[2 * s]), e1 = __int2float_rn(e[2 * s + 1]);	// exact: |e| < 2^17
+				a_f[s][c] = __fadd_rn(e0, 0.5f);				// (64 e0 + 32) / 64
+				k_f[s][c] = __fmul_rn(__fsub_rn(e1, e0), 0.015625f);		// (e1 - e0) / 64
+			}
+			else {
+				a_c[s][c] = 64 * e[2 * s] + 32;
+				k_c[s][c] = e[2 * s + 1] - e[2 * s];
+			}
 		}
 	}
 	// Index stream with the anchor pixels widened to IB bits (:544-564).
@@ -237,6 +293,37 @@ const BptcTables &tab, const Sink &sink) {
 		const uint32_t t = tab.two[raw.partition];
 		subset_bits = t & 0xFFFFu;
 		s = insert_zero_bit(s, (t >> 16) * IB + (IB - 1));
+	}
+	if constexpr (FP) {
+		// endpoint pair of a pixel: X0 + bit * (X1 - X0), interpolation ((64 - w) e0 + w e1 + 32) / 64 = a + w k, floor
+		constexpr float BIAS = SIGNED ? 12582912.0f : 8388608.0f;
+		float da[3] = { 0.0f, 0.0f, 0.0f }, dk[3] = { 0.0f, 0.0f, 0.0f };
+		if constexpr (NS == 2) {
+#pragma unroll
+			for (int c = 0; c < 3; c++) {
+				da[c] = __fsub_rn(a_f[NS - 1][c], a_f[0][c]);
+				dk[c] = __fsub_rn(k_f[NS - 1][c], k_f[0][c]);
+			}
+		}
+#pragma unroll
+		for (int i = 0; i < 16; i++) {
+			const uint32_t wgt = bptc_weight<IB>((uint32_t)(s >> (i * IB)) & ((1u << IB) - 1u));
+			const float wf = __fsub_rn(__uint_as_float(0x4B000000u | wgt), 8388608.0f);	// 2^23 + w - 2^23
+			// 1.0f or 0.0f from the subset bit: an integer multiply-add makes the bit pattern (FMA pipe)
+			const float bit = NS == 2 ? __uint_as_float(mad_u32((subset_bits >> i) & 1u, 0x3F800000u, 0u)) : 0.0f;
+			float y[3];
+#pragma unroll
+			for (int c = 0; c < 3; c++) {
+				float a = a_f[0][c], k = k_f[0][c];
+				if constexpr (NS == 2) {
+					a = __fmaf_rn(bit, da[c], a);
+					k = __fmaf_rn(bit, dk[c], k);
+				}
+				y[c] = __fadd_rd(__fmaf_rn(wf, k, a), BIAS);		// BIAS + floor((a64 + w k64) / 64), :97-108 (Q18)
+			}
+			sink.emit(i, y[0], y[1], y[2]);
+		}
+		return;
 	}
 	// endpoint pair of a pixel: X0 + bit*(X1 - X0) with multiply-adds (FMA pipe), as in the BC7 decoder
 	uint32_t da[3] = { 0u, 0u, 0u }, dk[3] = { 0u, 0u, 0u };

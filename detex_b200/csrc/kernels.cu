@@ -23,7 +23,9 @@
 //   * invalid blocks become zero pixels and raise one flag word (Q16).
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <atomic>
+#include <cuda.h>		// CUtensorMap (the encoder is fetched through cudaGetDriverEntryPoint: no -lcuda)
 
 #include "common.cuh"
 #include "decode_s3tc.cuh"
@@ -741,6 +743,12 @@ template <int F, int PC, bool STAGE, int LAYOUT> constexpr int sort_tile() {
 	if (STAGE)
 		return stages_packed_half3<F, PC>() ? 1024 : 2048;
 #endif
+#ifdef DETEXB200_SORT_256
+	// four CTAs of 256 threads per SM: at most 56 KiB of shared memory each
+	if (STAGE)
+		return stages_packed_half3<F, PC>() ? 256 : 512;
+	return 1024;
+#endif
 	if (STAGE)
 		return stages_packed_half3<F, PC>() ? 512 : 1024;
 	if (F == F_BPTC)
@@ -755,6 +763,10 @@ template <int F, int PC, bool STAGE, int LAYOUT> constexpr int sort_tile() {
 // -> FLOAT_RGB16 LINEAR 15.8 -> 18.1).  Not adopted.
 #ifdef DETEXB200_SORT_1024
 constexpr int SORT_THREADS = 1024, SORT_WARPS = SORT_THREADS / 32, SORT_CTAS = 1;
+#elif defined(DETEXB200_SORT_256)
+// -DDETEXB200_SORT_256: FOUR CTAs of 256 threads per SM (same warps per SM), tiles of 512 (staged) / 1024 blocks: more
+// independent CTAs to run while one waits at a barrier or for its staged tile to drain.
+constexpr int SORT_THREADS = 256, SORT_WARPS = SORT_THREADS / 32, SORT_CTAS = 4;
 #else
 constexpr int SORT_THREADS = 512, SORT_WARPS = SORT_THREADS / 32, SORT_CTAS = 2;
 #endif
@@ -768,10 +780,45 @@ constexpr uint32_t SLOT_EMPTY = 0xFFFFu;		// sorted slot that is bin padding
 //     distribution M where all ids of a group are congruent mod 8 (block i has mode i % 8);
 //   * copy-out reads: consecutive logical chunks (TILED: one or two ids x all c; LINEAR:
 //     consecutive ids / halves of one pixel row).
-template <int TB, int CHUNKS>
+//
+// TMA variant (LINEAR, 16-byte rows): the tile is staged as TB / 64 boxes of 64 consecutive blocks, each box 4 KiB =
+// 4 pixel rows x 8 lines of 128 bytes (a line = one pixel row of eight blocks), and chunk (id & 7) of a line sits at
+// (id & 7) ^ (line & 7) = (id ^ (id >> 3)) & 7 -- which is precisely the layout the hardware's SWIZZLE_128B mode gives a
+// box of {128 bytes, 8 groups of eight blocks, 4 pixel rows}.  The decode writes stay conflict-free as above and
+// one cp.async.bulk.tensor instruction per box replaces the whole copy-out.
+template <int TB, int CHUNKS, bool TMA = false>
 __device__ __forceinline__ uint32_t stage_slot(uint32_t id, uint32_t c) {
+	if (TMA)
+		return (id >> 6) * 256u + c * 64u + ((id & 63u) ^ ((id >> 3) & 7u));
 	const uint32_t fc = CHUNKS == 8 ? (((c & 1u) << 2) | (c >> 1)) : (2u * c);
 	return c * TB + (id ^ (((id >> 3) ^ fc) & 7u));
+}
+
+// ---- TMA store of a staged LINEAR tile ------------------------------------------------------------------------
+// The image is described to the TMA unit as a rank-3 tensor of bytes {128, pitch / 128, height} (strides 128 and
+// pitch): coordinate 1 counts groups of eight blocks along a pixel row.  With wib % 64 == 0 every run of 64
+// consecutive blocks lies inside one block row, so box b of a tile that starts at block t0 is the box {128, 8, 4}
+// at (0, bx / 8, 4 * by) with (by, bx) the block coordinates of block t0 + 64 b: always entirely inside the image
+// (measured on B200, tools/debug/tma_test.cu: a box that sticks out at the high end of a dimension is clipped as
+// documented -- the last block row of an image whose height is not a multiple of four relies on it -- but a
+// negative start coordinate raises an illegal-instruction fault on this store path, so row wrap-around is not left
+// to the hardware).
+__device__ __forceinline__ void fence_proxy_async_smem() {
+	asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap *map, const void *smem_src, int c0, int c1, int c2) {
+	const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem_src);
+	asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];"
+		:: "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(s) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// the shared-memory source of every committed store has been read (the buffer may be overwritten)
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
+// whether a staged LINEAR kernel can hand its tile to the TMA unit: 16-byte rows staged as they are stored
+template <int F, int PC, bool STAGE, int LAYOUT> constexpr bool tma_capable() {
+	return STAGE && LAYOUT == LAYOUT_LINEAR && stage_words<F, PC>() == 16 && !stages_packed_half3<F, PC>() &&
+		!((PC == PC_PACK3 && FormatTraits<F>::OUT_WORDS == 16) || tone_packs3(PC));
 }
 
 template <int F, int PC, bool STAGE, int LAYOUT>
@@ -780,7 +827,7 @@ struct SortedSmem {
 	static constexpr int CHUNKS = stage_words<F, PC>() / 4;		// 16-byte chunks per staged tile
 	uint4 out[STAGE ? TB * CHUNKS : 1];	// staged pixels (stage_slot layout)
 	uint4 raw[2][TB];		// double-buffered compressed tile, filled by cp.async
-	uint16_t id[CAP];		// tile-local block index in each sorted slot
+	uint16_t id[2][CAP];		// tile-local block index in each sorted slot, double-buffered across tiles
 	int count[2][16];		// per-mode histogram, double-buffered across tiles
 	uint8_t bin_lut[256];		// byte 0 of a block -> bin under this launch's mode_mask / flags
 	BptcTables tables;
@@ -809,11 +856,14 @@ __device__ __forceinline__ uint32_t raw_slot(uint32_t id) { return id ^ ((id >> 
 // warp hold two half-warps of different modes (BC6H modes share everything after the bit scatter, so a
 // mixed warp costs about a quarter more) and halves the lanes lost to padding, which matters for the
 // 1024-block tiles of the staged BC6H variants (14 modes: 31 % of the slots are padding at 32).
-template <int F, int LAYOUT, bool STAGE, int PC, int PAD = 32>
+// TMA: the staged LINEAR tile leaves through cp.async.bulk.tensor stores issued by one thread (tmap describes the image,
+// see tma_store_3d above) instead of the cooperative copy-out: no LDS / STG / address arithmetic per block, and one
+// barrier less per tile because the store of tile t is issued at the top of tile t + 1 and runs under its sort.
+template <int F, int LAYOUT, bool STAGE, int PC, int PAD = 32, bool TMA = false>
 __global__ void __launch_bounds__(SORT_THREADS, SORT_CTAS)
 decode_sorted_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, uint32_t n_blocks, int width,
 int height, int wib, uint32_t mode_mask, uint32_t flags, uint32_t post_op, uint32_t *invalid_flag, uint32_t *invalid_map,
-ToneArgs tone_args) {
+ToneArgs tone_args, uint32_t stagger_ns, const __grid_constant__ CUtensorMap tmap) {
 	using T = FormatTraits<F>;
 	using S = SortTraits<F>;
 	using SM = SortedSmem<F, PC, STAGE, LAYOUT>;
@@ -821,19 +871,21 @@ ToneArgs tone_args) {
 	constexpr int OW = T::OUT_WORDS, NB = S::NUM_BINS, TB = SM::TB, PER = TB / SORT_THREADS, CHUNKS = SM::CHUNKS;
 	constexpr int CPR = CHUNKS / 4;			// 16-byte chunks per pixel row of one block
 	static_assert(T::BLOCK_WORDS == 4, "sorted kernel handles 16-byte blocks");
-	static_assert(TB % SORT_THREADS == 0 && NB <= 16 && NB <= SORT_WARPS, "tile / bin limits");
+	static_assert(TB % SORT_THREADS == 0 && NB <= 16, "tile / bin limits");
+	static_assert(!TMA || (tma_capable<F, PC, STAGE, LAYOUT>() && TB % 64 == 0 && TB / 8 <= 256), "TMA store variant");
 	extern __shared__ __align__(16) unsigned char smem_raw[];
-	SM &sm = *reinterpret_cast<SM *>(smem_raw);
+	// (the staged tile is the first member: the hardware swizzle wants it 1024-byte aligned in the shared window)
+	SM &sm = *reinterpret_cast<SM *>(smem_raw + (TMA ? ((0u - (uint32_t)__cvta_generic_to_shared(smem_raw)) & 1023u) : 0u));
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const uint32_t n_tiles = (n_blocks + TB - 1) / TB;
 	if (tid < 32)
 		(&sm.count[0][0])[tid] = 0;
 	bptc_tables_load(sm.tables);
 	// the bin of a block depends on its first byte only (BC7: lowest set bit; BC6H: 2 / 5 mode bits)
-	if (tid < 256) {
+	for (int v = tid; v < 256; v += SORT_THREADS) {
 		uint4 probe;
-		probe.x = (uint32_t)tid; probe.y = probe.z = probe.w = 0u;
-		sm.bin_lut[tid] = (uint8_t)S::bin_of(probe, mode_mask, flags);
+		probe.x = (uint32_t)v; probe.y = probe.z = probe.w = 0u;
+		sm.bin_lut[v] = (uint8_t)S::bin_of(probe, mode_mask, flags);
 	}
 
 	auto issue_tile_load = [&](uint32_t tile, int buf) {
@@ -844,26 +896,31 @@ ToneArgs tone_args) {
 				cp_async_16(&sm.raw[buf][raw_slot(id)], src + (size_t)i * 16);
 		}
 	};
-	bool bad = false;
-	int cur = 0;
-	if (blockIdx.x < n_tiles)
-		issue_tile_load(blockIdx.x, 0);
-	for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, cur ^= 1) {
-		const uint32_t tile0 = tile * TB, n_here = min((uint32_t)TB, n_blocks - tile0);
-		cp_async_commit_and_wait_all();
-		__syncthreads();		// raw[cur] complete; previous copy-out done; count[cur] is zero
-		if (tile + gridDim.x < n_tiles)
-			issue_tile_load(tile + gridDim.x, cur ^ 1);
-		if (tid < 16)
-			sm.count[cur ^ 1][tid] = 0;
-		// ---- sort: classify (first byte through the bin table), histogram
-		int bin[PER], off[PER];
+	// the staged tile that starts at block t0 -> image: one bulk tensor store per box of 64 blocks (thread 0)
+	auto tma_store_tile = [&](uint32_t t0, uint32_t n_in_tile) {
+		uint32_t by = t0 / (uint32_t)wib, bx = t0 - by * (uint32_t)wib;
+		for (uint32_t b = 0; 64u * b < n_in_tile; b++) {
+			tma_store_3d(&tmap, &sm.out[256u * b], 0, (int)(bx >> 3), (int)(4u * by));
+			bx += 64u;
+			if (bx >= (uint32_t)wib) {
+				bx = 0u;
+				by++;
+			}
+		}
+		tma_store_commit();
+	};
+	// ---- sort of one tile, split in two so that the halves can sit on either side of a barrier ----------------------
+	// classify: every thread looks at the blocks IT loaded (its own cp.async copies: no barrier needed, only its own
+	// wait), takes their bin from the first byte, and the warp adds its counts to the tile's histogram.
+	int bin[PER], off[PER];
+	auto classify = [&](uint32_t t, int buf) {
+		const uint32_t n_in_tile = min((uint32_t)TB, n_blocks - t * TB);
 #pragma unroll
 		for (int k = 0; k < PER; k++) {
 			const uint32_t id = k * SORT_THREADS + tid;
 			bin[k] = -1;
-			if (id < n_here)
-				bin[k] = sm.bin_lut[reinterpret_cast<const uint8_t *>(&sm.raw[cur][raw_slot(id)])[0]];
+			if (id < n_in_tile)
+				bin[k] = sm.bin_lut[reinterpret_cast<const uint8_t *>(&sm.raw[buf][raw_slot(id)])[0]];
 		}
 #pragma unroll
 		for (int k = 0; k < PER; k++) {
@@ -871,13 +928,16 @@ ToneArgs tone_args) {
 			const int leader = __ffs((int)peers) - 1;
 			int base = 0;
 			if (lane == leader && bin[k] >= 0)
-				base = atomicAdd(&sm.count[cur][bin[k]], __popc(peers));
+				base = atomicAdd(&sm.count[buf][bin[k]], __popc(peers));
 			base = __shfl_sync(0xFFFFFFFFu, base, leader);
 			off[k] = base + __popc(peers & ((1u << lane) - 1u));
 		}
-		__syncthreads();
-		// padded exclusive scan of the bin counts, redundantly in every warp: lane b <- start[b]
-		const int my_count = lane < NB ? sm.count[cur][lane] : 0;
+	};
+	// scatter (after a barrier: the histogram is complete): padded exclusive scan of the bin counts, redundantly in
+	// every warp (lane b <- start[b]), then the ids of the classified blocks go to their sorted slots.  Returns the
+	// padded total.
+	auto scatter = [&](int buf) -> int {
+		const int my_count = lane < NB ? sm.count[buf][lane] : 0;
 		const int padded = S::PAD_BINS ? ((my_count + (PAD - 1)) & ~(PAD - 1)) : my_count;
 		int start = padded;
 #pragma unroll
@@ -887,30 +947,74 @@ ToneArgs tone_args) {
 				start += t;
 		}
 		start -= padded;		// lane NB holds the padded total
-		const int total = __shfl_sync(0xFFFFFFFFu, start, NB);
 		// the padding slots at the end of every bin get the sentinel (one warp per bin); the occupied
-		// slots are written by the scatter, so the array needs no clearing pass
-		if (S::PAD_BINS && warp < NB) {
-			const int c = __shfl_sync(0xFFFFFFFFu, my_count, warp), st = __shfl_sync(0xFFFFFFFFu, start, warp);
-			if (lane < ((-c) & (PAD - 1)))
-				sm.id[st + c + lane] = (uint16_t)SLOT_EMPTY;
+		// slots are written below, so the array needs no clearing pass
+		if (S::PAD_BINS) {
+#pragma unroll
+			for (int b = warp; b < NB; b += SORT_WARPS) {
+				const int c = __shfl_sync(0xFFFFFFFFu, my_count, b), st = __shfl_sync(0xFFFFFFFFu, start, b);
+				if (lane < ((-c) & (PAD - 1)))
+					sm.id[buf][st + c + lane] = (uint16_t)SLOT_EMPTY;
+			}
 		}
 #pragma unroll
 		for (int k = 0; k < PER; k++) {
 			const int st = __shfl_sync(0xFFFFFFFFu, start, bin[k] & 31);
 			if (bin[k] >= 0)
-				sm.id[st + off[k]] = (uint16_t)(k * SORT_THREADS + tid);
+				sm.id[buf][st + off[k]] = (uint16_t)(k * SORT_THREADS + tid);
 		}
-		__syncthreads();
+		return __shfl_sync(0xFFFFFFFFu, start, NB);
+	};
+
+	// ---- software pipeline over the tiles of this CTA (two barriers per tile) --------------------------------------
+	//   B1 | decode(t): sorted groups -> pixels (stored, or parked in the stage)
+	//      | classify(t+1): own blocks of the next tile (its cp.async data was requested one iteration ago) -> histogram
+	//   B2 | thread 0: TMA store of the staged tile t      | cp.async of tile t+2 into the buffer decode(t) just left
+	//      | scatter(t+1) -> sorted ids of the next tile   | (no TMA: cooperative copy-out of the stage)
+	//      | thread 0: wait until the TMA unit has read the stage
+	// The latency-bound steps of the sort (shared atomics, shuffles, dependent shared loads) of tile t+1 share their
+	// barrier intervals with the arithmetic of tile t instead of having two intervals of their own.
+	bool bad = false;
+	uint32_t tile = blockIdx.x;
+	if (tile >= n_tiles)
+		return;			// (uniform over the CTA; the launcher never starts more CTAs than tiles)
+	// Start-up stagger.  All CTAs start together and every tile costs about the same, so without it the whole chip
+	// alternates between a phase in which every CTA decodes (the memory system idles) and a phase in which every CTA
+	// drains its tile (the SMs idle at the barrier behind the drain): ncu showed 35 % of all warp samples at that one
+	// barrier.  CTA i therefore sleeps frac(i * golden ratio) of roughly one tile period before its first tile; the
+	// phases stay spread because the tiles are uniform.
+	if (stagger_ns != 0u) {
+		const uint32_t frac = (blockIdx.x * 0x9E3779B9u) >> 16;		// 16-bit fraction, low discrepancy in blockIdx.x
+		uint32_t ns = (frac * stagger_ns) >> 16;
+		while (ns > 0u) {
+			const uint32_t step = ns > 500000u ? 500000u : ns;
+			__nanosleep(step);
+			ns -= step;
+		}
+	}
+	issue_tile_load(tile, 0);
+	cp_async_commit_and_wait_all();
+	__syncthreads();		// tables, bin table, zeroed histograms; (everyone's copies of the first tile)
+	classify(tile, 0);
+	if (tile + gridDim.x < n_tiles)
+		issue_tile_load(tile + gridDim.x, 1);
+	asm volatile("cp.async.commit_group;" ::: "memory");
+	__syncthreads();		// histogram of the first tile complete
+	int total = scatter(0);
+	for (int cur = 0;; cur ^= 1) {
+		const uint32_t tile0 = tile * TB, n_here = min((uint32_t)TB, n_blocks - tile0);
+		const uint32_t next = tile + gridDim.x;
+		const bool has_next = next < n_tiles;
+		__syncthreads();	// B1: id[cur] scattered, raw[cur] landed (classified one iteration ago), stage free
 		// ---- decode: groups of 32 same-mode blocks; padding slots hold the 0xFFFF sentinel.
 		// The next group's ids are fetched before the current group is decoded.
 		int g = warp * 32;
 		// (with PAD < 32 the last group may end inside the warp: slots from total on are not initialised)
-		uint32_t id_next = g + (PAD < 32 ? lane : 0) < total ? sm.id[g + lane] : SLOT_EMPTY;
+		uint32_t id_next = g + (PAD < 32 ? lane : 0) < total ? sm.id[cur][g + lane] : SLOT_EMPTY;
 		for (; g < total; g += SORT_WARPS * 32) {
 			const uint32_t id = id_next;
 			const int g_next = g + SORT_WARPS * 32;
-			id_next = g_next + (PAD < 32 ? lane : 0) < total ? sm.id[g_next + lane] : SLOT_EMPTY;
+			id_next = g_next + (PAD < 32 ? lane : 0) < total ? sm.id[cur][g_next + lane] : SLOT_EMPTY;
 			const bool live = id != SLOT_EMPTY;
 			if (live) {
 				const uint4 w = sm.raw[cur][raw_slot(id)];
@@ -929,7 +1033,7 @@ ToneArgs tone_args) {
 					tone_tile<PC>(px, t, post_op, ctx, ok);
 #pragma unroll
 					for (int c = 0; c < 4; c++)
-						sm.out[stage_slot<TB, 4>(id, c)] = make_uint4(t[4 * c], t[4 * c + 1], t[4 * c + 2], t[4 * c + 3]);
+						sm.out[stage_slot<TB, 4, TMA>(id, c)] = make_uint4(t[4 * c], t[4 * c + 1], t[4 * c + 2], t[4 * c + 3]);
 				}
 				else if constexpr (STAGE && stages_packed_half3<F, PC>()) {
 					apply_post_op<OW>(px, post_op);
@@ -944,7 +1048,7 @@ ToneArgs tone_args) {
 					apply_post_op<OW>(px, post_op);
 #pragma unroll
 					for (int c = 0; c < CHUNKS; c++)
-						sm.out[stage_slot<TB, CHUNKS>(id, c)] = make_uint4(px[4 * c], px[4 * c + 1], px[4 * c + 2], px[4 * c + 3]);
+						sm.out[stage_slot<TB, CHUNKS, TMA>(id, c)] = make_uint4(px[4 * c], px[4 * c + 1], px[4 * c + 2], px[4 * c + 3]);
 				}
 				else {
 					emit<PC>(px, post_op, ctx, ok, [&](auto &w) {
@@ -972,109 +1076,133 @@ ToneArgs tone_args) {
 				}
 			}
 		}
-		if constexpr (!STAGE)
-			continue;		// direct stores: the barrier at the loop top is enough
-		__syncthreads();
-		// ---- store
-		constexpr bool PACK_ROWS = (PC == PC_PACK3 && OW == 16) || tone_packs3(PC);	// RGBX8 stage -> RGB8 rows
-		static_assert(!STAGE || PC == PC_NATIVE || (is_tone_class(PC) && LAYOUT == LAYOUT_LINEAR) ||
-			PACK_ROWS || (stages_packed_half3<F, PC>() && LAYOUT == LAYOUT_LINEAR),
-			"staged copy-out repacks RGB8 rows only");
-		if constexpr (stages_packed_half3<F, PC>() && LAYOUT == LAYOUT_LINEAR) {
-			// 24-byte rows out of packed 96-byte tiles, in 8-byte pieces: piece q = id * 3 + j of pixel row r
-			// lies at byte 24 r + 8 j of its tile and at row_base + 8 q of the image row, so a warp's 32
-			// pieces are 256 contiguous bytes of the image
-			const size_t pitch = (size_t)width * 6;
-			const uint32_t by0 = tile0 / (uint32_t)wib, bx0 = tile0 - by0 * (uint32_t)wib;	// uniform
-			uint8_t *const row0 = dst + (size_t)by0 * 4 * pitch;
-			const uint8_t *const stage_bytes = reinterpret_cast<const uint8_t *>(sm.out);
-#pragma unroll
-			for (int k = 0; k < TB * 3 / SORT_THREADS; k++) {
-				const uint32_t q = k * SORT_THREADS + tid, id = q / 3u, j = q - id * 3u;
-				if (id < n_here) {
-					uint32_t bx = bx0 + id, by = by0;
-					while (bx >= (uint32_t)wib) {	// tiles may wrap over block rows
-						bx -= (uint32_t)wib;
-						by++;
-					}
-					uint8_t *out = row0 + (size_t)(by - by0) * 4 * pitch + bx * 24u + j * 8u;
-					const int rows = height - (int)by * 4;	// >= 4 except in a clipped last block row
-#pragma unroll
-					for (int r = 0; r < 4; r++) {
-						if (r < rows) {
-							const uint32_t byte = 24u * r + 8u * j;
-							const uint2 v = *reinterpret_cast<const uint2 *>(stage_bytes +
-								(size_t)stage_slot<TB, 6>(id, byte >> 4) * 16 + (byte & 8u));
-							st_stream_v2(out, v.x, v.y);
+		if (has_next) {
+			asm volatile("cp.async.wait_group 0;" ::: "memory");	// my copies of the next tile have landed
+			classify(next, cur ^ 1);
+		}
+		if constexpr (TMA)
+			fence_proxy_async_smem();	// my writes to the staged tile -> visible to the TMA unit
+		__syncthreads();	// B2: tile decoded (stage complete); histogram of the next tile complete; raw[cur] free
+		if constexpr (TMA) {
+			if (tid == 0)
+				tma_store_tile(tile0, n_here);
+		}
+		if (has_next && next + gridDim.x < n_tiles)
+			issue_tile_load(next + gridDim.x, cur);
+		asm volatile("cp.async.commit_group;" ::: "memory");
+		if (tid < 16)
+			sm.count[cur][tid] = 0;		// (consumed by scatter one iteration ago; next used after B1)
+		if constexpr (STAGE && !TMA) {
+			// ---- store
+			constexpr bool PACK_ROWS = (PC == PC_PACK3 && OW == 16) || tone_packs3(PC);	// RGBX8 stage -> RGB8 rows
+			static_assert(!STAGE || PC == PC_NATIVE || (is_tone_class(PC) && LAYOUT == LAYOUT_LINEAR) ||
+				PACK_ROWS || (stages_packed_half3<F, PC>() && LAYOUT == LAYOUT_LINEAR),
+				"staged copy-out repacks RGB8 rows only");
+			if constexpr (stages_packed_half3<F, PC>() && LAYOUT == LAYOUT_LINEAR) {
+				// 24-byte rows out of packed 96-byte tiles, in 8-byte pieces: piece q = id * 3 + j of pixel row r
+				// lies at byte 24 r + 8 j of its tile and at row_base + 8 q of the image row, so a warp's 32
+				// pieces are 256 contiguous bytes of the image
+				const size_t pitch = (size_t)width * 6;
+				const uint32_t by0 = tile0 / (uint32_t)wib, bx0 = tile0 - by0 * (uint32_t)wib;	// uniform
+				uint8_t *const row0 = dst + (size_t)by0 * 4 * pitch;
+				const uint8_t *const stage_bytes = reinterpret_cast<const uint8_t *>(sm.out);
+	#pragma unroll
+				for (int k = 0; k < TB * 3 / SORT_THREADS; k++) {
+					const uint32_t q = k * SORT_THREADS + tid, id = q / 3u, j = q - id * 3u;
+					if (id < n_here) {
+						uint32_t bx = bx0 + id, by = by0;
+						while (bx >= (uint32_t)wib) {	// tiles may wrap over block rows
+							bx -= (uint32_t)wib;
+							by++;
 						}
-						out += pitch;
-					}
-				}
-			}
-		}
-		else if constexpr (LAYOUT == LAYOUT_TILED && PACK_ROWS) {
-			// 48-byte RGB8 tiles out of staged RGBX8 tiles: thread <-> block in image order, three 128-bit
-			// stores per tile; a warp completes 1536 contiguous bytes with three back-to-back instructions
-			uint8_t *out = dst + (size_t)tile0 * 48;
-#pragma unroll
-			for (int k = 0; k < TB / SORT_THREADS; k++) {
-				const uint32_t id = k * SORT_THREADS + tid;
-				if (id < n_here) {
-					uint32_t t[16], q[12];
-#pragma unroll
-					for (int r = 0; r < 4; r++) {
-						const uint4 v = sm.out[stage_slot<TB, CHUNKS>(id, r)];
-						t[4 * r] = v.x; t[4 * r + 1] = v.y; t[4 * r + 2] = v.z; t[4 * r + 3] = v.w;
-					}
-					repack<PC_PACK3, 16>(t, q);
-					uint8_t *o = out + (size_t)id * 48;
-#pragma unroll
-					for (int c = 0; c < 3; c++)
-						st_stream_v4(o + 16 * c, q[4 * c], q[4 * c + 1], q[4 * c + 2], q[4 * c + 3]);
-				}
-			}
-		}
-		else if (LAYOUT == LAYOUT_TILED) {
-			uint8_t *out = dst + (size_t)tile0 * (CHUNKS * 16);
-			for (uint32_t q = tid; q < n_here * CHUNKS; q += SORT_THREADS) {
-				const uint4 v = sm.out[stage_slot<TB, CHUNKS>(q / CHUNKS, q % CHUNKS)];
-				st_stream_v4(out + (size_t)q * 16, v.x, v.y, v.z, v.w);
-			}
-		}
-		else {
-			constexpr int ROW_BYTES = post_words<OW, PC>();	// bytes of one stored pixel row of one block
-			const size_t pitch = (size_t)width * (ROW_BYTES / 4);
-			const uint32_t by0 = tile0 / (uint32_t)wib, bx0 = tile0 - by0 * (uint32_t)wib;	// uniform
-			uint8_t *const row0 = dst + (size_t)by0 * 4 * pitch;
-			// thread t owns row positions p = t, t+512, ... (p = id*CPR + half) for all 4 pixel rows
-#pragma unroll
-			for (int j = 0; j < TB * CPR / SORT_THREADS; j++) {
-				const uint32_t p = j * SORT_THREADS + tid, id = p / CPR, half = p % CPR;
-				if (id < n_here) {
-					uint32_t bx = bx0 + id, by = by0;
-					while (bx >= (uint32_t)wib) {	// tiles may wrap over block rows (0-1 turns unless wib < TB)
-						bx -= (uint32_t)wib;
-						by++;
-					}
-					uint8_t *out = row0 + (size_t)(by - by0) * 4 * pitch + bx * (uint32_t)ROW_BYTES + half * 16;
-					const int rows = height - (int)by * 4;	// >= 4 except in a clipped last block row
-#pragma unroll
-					for (int r = 0; r < 4; r++) {
-						if (r < rows) {
-							const uint4 v = sm.out[stage_slot<TB, CHUNKS>(id, r * CPR + half)];
-							if constexpr (PACK_ROWS) {		// four RGBX8 pixels -> 12 bytes
-								st_stream_u32(out, prmt(v.x, v.y, 0x4210));
-								st_stream_u32(out + 4, prmt(v.y, v.z, 0x5421));
-								st_stream_u32(out + 8, prmt(v.z, v.w, 0x6542));
+						uint8_t *out = row0 + (size_t)(by - by0) * 4 * pitch + bx * 24u + j * 8u;
+						const int rows = height - (int)by * 4;	// >= 4 except in a clipped last block row
+	#pragma unroll
+						for (int r = 0; r < 4; r++) {
+							if (r < rows) {
+								const uint32_t byte = 24u * r + 8u * j;
+								const uint2 v = *reinterpret_cast<const uint2 *>(stage_bytes +
+									(size_t)stage_slot<TB, 6>(id, byte >> 4) * 16 + (byte & 8u));
+								st_stream_v2(out, v.x, v.y);
 							}
-							else
-								st_stream_v4(out, v.x, v.y, v.z, v.w);
+							out += pitch;
 						}
-						out += pitch;
+					}
+				}
+			}
+			else if constexpr (LAYOUT == LAYOUT_TILED && PACK_ROWS) {
+				// 48-byte RGB8 tiles out of staged RGBX8 tiles: thread <-> block in image order, three 128-bit
+				// stores per tile; a warp completes 1536 contiguous bytes with three back-to-back instructions
+				uint8_t *out = dst + (size_t)tile0 * 48;
+	#pragma unroll
+				for (int k = 0; k < TB / SORT_THREADS; k++) {
+					const uint32_t id = k * SORT_THREADS + tid;
+					if (id < n_here) {
+						uint32_t t[16], q[12];
+	#pragma unroll
+						for (int r = 0; r < 4; r++) {
+							const uint4 v = sm.out[stage_slot<TB, CHUNKS>(id, r)];
+							t[4 * r] = v.x; t[4 * r + 1] = v.y; t[4 * r + 2] = v.z; t[4 * r + 3] = v.w;
+						}
+						repack<PC_PACK3, 16>(t, q);
+						uint8_t *o = out + (size_t)id * 48;
+	#pragma unroll
+						for (int c = 0; c < 3; c++)
+							st_stream_v4(o + 16 * c, q[4 * c], q[4 * c + 1], q[4 * c + 2], q[4 * c + 3]);
+					}
+				}
+			}
+			else if (LAYOUT == LAYOUT_TILED) {
+				uint8_t *out = dst + (size_t)tile0 * (CHUNKS * 16);
+				for (uint32_t q = tid; q < n_here * CHUNKS; q += SORT_THREADS) {
+					const uint4 v = sm.out[stage_slot<TB, CHUNKS>(q / CHUNKS, q % CHUNKS)];
+					st_stream_v4(out + (size_t)q * 16, v.x, v.y, v.z, v.w);
+				}
+			}
+			else {
+				constexpr int ROW_BYTES = post_words<OW, PC>();	// bytes of one stored pixel row of one block
+				const size_t pitch = (size_t)width * (ROW_BYTES / 4);
+				const uint32_t by0 = tile0 / (uint32_t)wib, bx0 = tile0 - by0 * (uint32_t)wib;	// uniform
+				uint8_t *const row0 = dst + (size_t)by0 * 4 * pitch;
+				// thread t owns row positions p = t, t+512, ... (p = id*CPR + half) for all 4 pixel rows
+	#pragma unroll
+				for (int j = 0; j < TB * CPR / SORT_THREADS; j++) {
+					const uint32_t p = j * SORT_THREADS + tid, id = p / CPR, half = p % CPR;
+					if (id < n_here) {
+						uint32_t bx = bx0 + id, by = by0;
+						while (bx >= (uint32_t)wib) {	// tiles may wrap over block rows (0-1 turns unless wib < TB)
+							bx -= (uint32_t)wib;
+							by++;
+						}
+						uint8_t *out = row0 + (size_t)(by - by0) * 4 * pitch + bx * (uint32_t)ROW_BYTES + half * 16;
+						const int rows = height - (int)by * 4;	// >= 4 except in a clipped last block row
+	#pragma unroll
+						for (int r = 0; r < 4; r++) {
+							if (r < rows) {
+								const uint4 v = sm.out[stage_slot<TB, CHUNKS>(id, r * CPR + half)];
+								if constexpr (PACK_ROWS) {		// four RGBX8 pixels -> 12 bytes
+									st_stream_u32(out, prmt(v.x, v.y, 0x4210));
+									st_stream_u32(out + 4, prmt(v.y, v.z, 0x5421));
+									st_stream_u32(out + 8, prmt(v.z, v.w, 0x6542));
+								}
+								else
+									st_stream_v4(out, v.x, v.y, v.z, v.w);
+							}
+							out += pitch;
+						}
 					}
 				}
 			}
 		}
+		if (has_next)
+			total = scatter(cur ^ 1);
+		if constexpr (TMA) {
+			if (tid == 0)
+				tma_store_wait_read();	// the stage may be overwritten; shared memory outlives the reads
+		}
+		if (!has_next)
+			break;
+		tile = next;
 	}
 	report_invalid(bad, invalid_flag);
 }
@@ -1486,10 +1614,54 @@ static ToneArgs tone_args_of(const DecodeArgs &a) {
 	return t;
 }
 
-template <int F, int LAYOUT, bool STAGE, int PC, int PAD = 32>
-static void launch_sorted(const uint8_t *src, uint8_t *dst, uint32_t n_blocks, const DecodeArgs &a, cudaStream_t stream) {
+// Tensor map of a LINEAR image for tma_store_3d: bytes {128, pitch / 128, height}, box {128, 8, 4}, SWIZZLE_128B.
+// cuTensorMapEncodeTiled is a driver-API function; it is fetched through the runtime so that the library keeps
+// linking against cudart only.  Returns false when the driver entry point is missing or refuses the shape (the
+// caller then launches the cooperative copy-out variant).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+	const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+	static const EncodeTiledFn fn = [] {
+		void *p = nullptr;
+		cudaDriverEntryPointQueryResult q;
+		if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+		    q != cudaDriverEntryPointSuccess) {
+			(void)cudaGetLastError();
+			p = nullptr;
+		}
+		return (EncodeTiledFn)p;
+	}();
+	return fn;
+}
+// DETEXB200_TMA_STORE=0 in the environment selects the cooperative copy-out of the staged LINEAR kernels (A/B runs)
+static bool tma_store_enabled() {
+	static const bool v = [] { const char *e = getenv("DETEXB200_TMA_STORE"); return !(e && e[0] == '0'); }();
+	return v;
+}
+static bool make_linear_tensor_map(CUtensorMap *map, void *dst, size_t pitch, int height) {
+	const EncodeTiledFn encode = encode_tiled_fn();
+	if (encode == nullptr || pitch % 1024 != 0 || height < 1 || (((uintptr_t)dst) & 15u) != 0)
+		return false;
+	const cuuint64_t dims[3] = { 128, (cuuint64_t)(pitch / 128), (cuuint64_t)height };
+	const cuuint64_t strides[2] = { 128, (cuuint64_t)pitch };		// bytes, dimensions 1 and 2
+	const cuuint32_t box[3] = { 128, 8, 4 };			// 64 blocks x 4 pixel rows
+	const cuuint32_t elem[3] = { 1, 1, 1 };
+	return encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, dst, dims, strides, box, elem, CU_TENSOR_MAP_INTERLEAVE_NONE,
+		CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// Start-up stagger of the persistent sorted kernels (see the kernel): about one tile period.  DETEXB200_STAGGER_NS
+// overrides it (0 switches it off; A/B runs).
+static uint32_t stagger_ns() {
+	static const uint32_t v = [] { const char *e = getenv("DETEXB200_STAGGER_NS"); return e ? (uint32_t)atoi(e) : 0u; }();
+	return v;
+}
+
+template <int F, int LAYOUT, bool STAGE, int PC, int PAD, bool TMA>
+static void launch_sorted_variant(const uint8_t *src, uint8_t *dst, uint32_t n_blocks, const DecodeArgs &a, cudaStream_t stream,
+const CUtensorMap &tmap) {
 	using SM = SortedSmem<F, PC, STAGE, LAYOUT>;
-	const size_t smem = sizeof(SM);
+	const size_t smem = sizeof(SM) + (TMA ? 1024 : 0);		// + alignment slack for the swizzled stage
 	const uint64_t tiles = ((uint64_t)n_blocks + SM::TB - 1) / SM::TB;
 	const uint64_t resident = (uint64_t)sm_count() * SORT_CTAS;		// persistent: two CTAs per SM
 	const unsigned grid = (unsigned)(tiles < resident ? tiles : resident);
@@ -1497,11 +1669,31 @@ static void launch_sorted(const uint8_t *src, uint8_t *dst, uint32_t n_blocks, c
 	int dev = 0;
 	cudaGetDevice(&dev);
 	if (!configured[dev & 63].load()) {
-		cudaFuncSetAttribute(decode_sorted_kernel<F, LAYOUT, STAGE, PC, PAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		cudaFuncSetAttribute(decode_sorted_kernel<F, LAYOUT, STAGE, PC, PAD, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 		configured[dev & 63].store(true);
 	}
-	decode_sorted_kernel<F, LAYOUT, STAGE, PC, PAD><<<grid, SORT_THREADS, smem, stream>>>(src, dst, n_blocks,
-		a.width, a.height, a.wib, a.mode_mask, a.flags, a.post_op, a.invalid, a.invalid_map, tone_args_of(a));
+	decode_sorted_kernel<F, LAYOUT, STAGE, PC, PAD, TMA><<<grid, SORT_THREADS, smem, stream>>>(src, dst, n_blocks,
+		a.width, a.height, a.wib, a.mode_mask, a.flags, a.post_op, a.invalid, a.invalid_map, tone_args_of(a),
+		tiles > 2 * resident ? stagger_ns() : 0u, tmap);
+}
+
+// One instantiation of the sorted kernel: opt in to > 48 KiB of dynamic shared memory once per
+// device, then launch.  Staged LINEAR tiles of 16-byte rows leave through the TMA unit when the image allows it
+// (whole boxes of 64 blocks per block row, 16-byte aligned base).
+template <int F, int LAYOUT, bool STAGE, int PC, int PAD = 32>
+static void launch_sorted(const uint8_t *src, uint8_t *dst, uint32_t n_blocks, const DecodeArgs &a, cudaStream_t stream) {
+	CUtensorMap tmap;
+	if constexpr (tma_capable<F, PC, STAGE, LAYOUT>()) {
+		constexpr int ROW_BYTES = 16;
+		// whole boxes of 64 blocks per block row (pixel rows beyond the image height are clipped by the hardware)
+		if (tma_store_enabled() && a.wib % 64 == 0 && a.height > 4 * (a.hib - 1) &&
+		    make_linear_tensor_map(&tmap, dst, (size_t)a.wib * ROW_BYTES, a.height)) {
+			launch_sorted_variant<F, LAYOUT, STAGE, PC, PAD, true>(src, dst, n_blocks, a, stream, tmap);
+			return;
+		}
+	}
+	memset(&tmap, 0, sizeof(tmap));
+	launch_sorted_variant<F, LAYOUT, STAGE, PC, PAD, false>(src, dst, n_blocks, a, stream, tmap);
 }
 
 #ifdef DETEXB200_EXPERIMENTS

@@ -152,8 +152,8 @@ DETEXB200_API void detexb200FreeDeviceImages(detexb200DeviceImage *levels, int n
 DETEXB200_API int detexb200SetDevices(int n, const int *device_ids);
 /*
  * Threads of the copy pool that serves pageable (malloc'd) caller buffers and multi-device calls: each thread
- * stages one slab at a time through its own pinned bounce buffers.  0 = default (half the hardware threads,
- * between 4 and 16, at least 3 per device).  Environment: DETEXB200_HOST_THREADS.
+ * stages one slab at a time through its own pinned bounce buffers.  0 = default (one per hardware thread,
+ * between 4 and 32, at least 3 per device).  Environment: DETEXB200_HOST_THREADS.
  */
 DETEXB200_API int detexb200SetHostThreads(int n);
 /*

@@ -77,6 +77,9 @@ static inline float __fsub_rn(float a, float b) { volatile float x = a, y = b; r
 static inline float __fsub_rd(float a, float b) { volatile float x = a, y = b; return emu_rounded(FE_DOWNWARD, [&] { return x - y; }); }
 static inline float __fdiv_rd(float a, float b) { volatile float x = a, y = b; return emu_rounded(FE_DOWNWARD, [&] { return x / y; }); }
 static inline float __fmaf_rd(float a, float b, float c) { volatile float x = a, y = b, z = c; return emu_rounded(FE_DOWNWARD, [&] { return fmaf(x, y, z); }); }
+static inline float __fadd_rn(float a, float b) { volatile float x = a, y = b; return emu_rounded(FE_TONEAREST, [&] { return x + y; }); }
+static inline float __fmaf_rn(float a, float b, float c) { volatile float x = a, y = b, z = c; return emu_rounded(FE_TONEAREST, [&] { return fmaf(x, y, z); }); }
+static inline float __int2float_rn(int v) { return (float)v; }
 /* the .sat modifier of mul.f32: clamp to [0, 1], NaN -> +0 */
 static inline float emu_sat(float f) { return f != f ? 0.0f : (f < 0.0f ? 0.0f : (f > 1.0f ? 1.0f : f)); }
 
