@@ -440,6 +440,26 @@ class Bench:
         modes = [(shift + k) % n_modes for k in range(n_modes)]
         return H.force_modes(fmt, hb, modes)
 
+    def host_copy_gbs(self):
+        """GB/s of plain host copies, one 64 MiB buffer per thread, all host threads at once (rank 0's share of the box
+        when several ranks run): the ceiling of any path that has to copy the pixels once on the host"""
+        threads = max(1, self.cores // self.world)
+        src = [np.ones(64 << 20, dtype=np.uint8) for _ in range(threads)]
+        dst = [np.empty(64 << 20, dtype=np.uint8) for _ in range(threads)]
+
+        def work(i):
+            for _ in range(3):
+                np.copyto(dst[i], src[i])
+        for i in range(threads):        # touch the pages
+            dst[i][:] = 0
+        ts = [threading.Thread(target=work, args=(i,)) for i in range(threads)]
+        t0 = time.perf_counter()
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+        return threads * 3 * (64 << 20) / (time.perf_counter() - t0) / 1e9
+
     # ---- end-to-end legs: reference-facing API, host buffers, copies inside the timed region ---------------------
     def e2e(self, parts, steps):
         torch, D, lib = self.torch, self.D, self.lib
@@ -484,6 +504,7 @@ class Bench:
             return self.reduce_max(time.perf_counter() - t0)
 
         job_blocks = self.reduce_sum(sum(p["n"] for p in parts))
+        host_copy = self.host_copy_gbs()
         res = {}
         views = {}
         for kind in ("pinned", "pageable"):
@@ -522,7 +543,12 @@ class Bench:
                "pageable": {"value": res["pageable"]["value"], "ms_per_step": res["pageable"]["ms_per_step"],
                             "buffers": "malloc'd (numpy) block and pixel arrays, warm pages; the library stages them "
                                        "through the pinned bounce buffers of its copy pool",
-                            "frac_of_pinned": res["pageable"]["value"] / res["pinned"]["value"]},
+                            "frac_of_pinned": res["pageable"]["value"] / res["pinned"]["value"],
+                            "gbs_out": d2h / (res["pageable"]["ms_per_step"] / 1e3) / 1e9,
+                            "host_copy_ceiling_gbs": host_copy,
+                            "bound": "host memory: every pixel is written by the DMA engine into a pinned bounce buffer and copied "
+                                     "once more by the pool's threads; host_copy_ceiling_gbs is what plain multi-threaded memcpy "
+                                     "reaches on this box with all cores and no DMA beside it"},
                "pcie_ceiling": {"value": ceiling, "ms_per_step": 1e3 * t_copy / steps,
                                 "gbs_d2h": d2h * steps / t_copy / 1e9,
                                 "how": "cudaMemcpyAsync of the same bytes, pinned, H2D and D2H on two streams, same box, all ranks at once"},

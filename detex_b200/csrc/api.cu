@@ -149,6 +149,7 @@ struct Context {
 	bool ready = false, failed = false;
 	int device = -1;			// the context (lanes) belongs to this device
 	Lane lanes[N_STREAMS];
+	std::map<int, std::vector<Lane>> rings;	// pool path: per device, the lanes whose slabs are in flight
 	void *h_small = nullptr;		// pinned scratch for single-block calls (512 bytes)
 
 	bool init() {
@@ -196,6 +197,13 @@ struct Context {
 		const bool switched = cudaGetDevice(&cur) == cudaSuccess && cur != device && cudaSetDevice(device) == cudaSuccess;
 		for (int i = 0; i < N_STREAMS; i++)
 			lanes[i].release();
+		for (auto &r : rings) {
+			if (cudaSetDevice(r.first) == cudaSuccess)
+				for (Lane &L : r.second)
+					L.release();
+		}
+		rings.clear();
+		cudaSetDevice(device);
 		cudaFreeHost(h_small);
 		h_small = nullptr;
 		if (switched)
@@ -461,6 +469,12 @@ void stream_copy(void *dst, const void *src, size_t n) {
 #endif
 }
 
+// tuning knobs of the pool path (environment, read once; see device_set())
+size_t g_pool_slab_bytes = POOL_SLAB_BYTES;	// DETEXB200_POOL_SLAB_KB
+bool g_pool_stream_copy = true;		// DETEXB200_POOL_COPY=memcpy selects plain memcpy out of the bounce buffers
+int g_pool_ring = 48;			// DETEXB200_POOL_RING: lanes (slabs in flight) per device and calling thread.  Measured on a
+					// 16-core box (BC1 8192^2, pageable): 8 -> 24 -> 48 lanes = 12.5 -> 28.6 -> 34.7 GB/s of pixels
+
 struct CallState {
 	std::mutex m;
 	std::condition_variable cv;
@@ -469,12 +483,18 @@ struct CallState {
 	bool invalid = false;
 	std::string error;
 };
+// A slab goes through the pool twice: SUBMIT (copy the blocks into the lane's pinned buffer, enqueue H2D -> kernel ->
+// D2H into the lane's pinned buffer, record the lane's event) and FINISH (wait for the event, copy the pixels into the
+// caller's buffer, hand the lane back).  No thread sits idle while its slab is on the link: as many slabs as the
+// caller's ring has lanes are in flight, and the pool's threads spend their time copying.
 struct Job {
+	enum Kind { SUBMIT, FINISH } kind;
 	const TexCall *call;
 	const Slab *slab;
+	Lane *lane;
+	bool *lane_busy;
 	int device;
 	bool bounce_in, bounce_out;
-	size_t max_in, max_out, max_tmp;
 	CallState *state;
 };
 
@@ -500,15 +520,13 @@ private:
 	std::deque<Job> q_;
 	size_t threads_ = 0;
 
-	static int run(const Job &j, std::map<int, Lane> &lanes, bool *invalid) {
+	static int run_submit(const Job &j) {
 		const TexCall &c = *j.call;
 		const Slab &s = *j.slab;
+		Lane &L = *j.lane;
 		cudaError_t e;
 		if ((e = cudaSetDevice(j.device)) != cudaSuccess)
 			return cuda_fail("cudaSetDevice", e);
-		Lane &L = lanes[j.device];
-		if (!L.init() || !reserve_lane(L, c, j.max_in, j.max_out, j.max_tmp, j.bounce_in, j.bounce_out))
-			return DETEXB200_ECUDA;
 		set_hdr_parameters(c.gamma, c.range_min, c.range_max);
 		if ((e = cudaMemsetAsync(L.d_flag, 0, 4, L.stream)) != cudaSuccess)
 			return cuda_fail("cudaMemsetAsync", e);
@@ -522,17 +540,28 @@ private:
 		if (rc != DETEXB200_OK)
 			return rc;
 		if ((e = cudaMemcpyAsync(L.h_flag, L.d_flag, 4, cudaMemcpyDeviceToHost, L.stream)) != cudaSuccess ||
-		    (e = cudaEventRecord(L.done, L.stream)) != cudaSuccess ||
-		    (e = cudaEventSynchronize(L.done)) != cudaSuccess)
+		    (e = cudaEventRecord(L.done, L.stream)) != cudaSuccess)
 			return cuda_fail("slab pipeline", e);
-		if (j.bounce_out)
-			stream_copy(c.out + s.out_off, L.h_out, s.out_len);
+		return DETEXB200_OK;
+	}
+	static int run_finish(const Job &j, bool *invalid) {
+		const TexCall &c = *j.call;
+		const Slab &s = *j.slab;
+		Lane &L = *j.lane;
+		cudaError_t e;
+		if ((e = cudaEventSynchronize(L.done)) != cudaSuccess)
+			return cuda_fail("slab pipeline", e);
+		if (j.bounce_out) {
+			if (g_pool_stream_copy)
+				stream_copy(c.out + s.out_off, L.h_out, s.out_len);
+			else
+				memcpy(c.out + s.out_off, L.h_out, s.out_len);
+		}
 		*invalid = *L.h_flag != 0;
 		return DETEXB200_OK;
 	}
 
 	void worker() {
-		std::map<int, Lane> lanes;		// this thread's lane on every device it has served
 		for (;;) {
 			Job j;
 			{
@@ -542,7 +571,18 @@ private:
 				q_.pop_front();
 			}
 			bool invalid = false;
-			const int rc = run(j, lanes, &invalid);
+			int rc;
+			if (j.kind == Job::SUBMIT) {
+				rc = run_submit(j);
+				if (rc == DETEXB200_OK) {		// second trip: behind the jobs already queued
+					Job f = j;
+					f.kind = Job::FINISH;
+					submit(f);
+					continue;
+				}
+			}
+			else
+				rc = run_finish(j, &invalid);
 			CallState &st = *j.state;
 			std::lock_guard<std::mutex> g(st.m);
 			if (rc != DETEXB200_OK && st.rc == DETEXB200_OK) {
@@ -550,8 +590,9 @@ private:
 				st.error = g_error;
 			}
 			st.invalid = st.invalid || invalid;
-			if (--st.pending == 0)
-				st.cv.notify_all();
+			*j.lane_busy = false;
+			st.pending--;
+			st.cv.notify_all();		// the caller waits for free lanes and for the last slab
 		}
 	}
 };
@@ -573,6 +614,14 @@ std::vector<int> device_set() {
 		g_devices_from_env = true;
 		if (const char *t = getenv("DETEXB200_HOST_THREADS"))
 			g_host_threads = atoi(t);
+		if (const char *t = getenv("DETEXB200_POOL_SLAB_KB"))
+			if (atoi(t) >= 64)
+				g_pool_slab_bytes = (size_t)atoi(t) << 10;
+		if (const char *t = getenv("DETEXB200_POOL_COPY"))
+			g_pool_stream_copy = t[0] != 'm';
+		if (const char *t = getenv("DETEXB200_POOL_RING"))
+			if (atoi(t) >= 2 && atoi(t) <= 256)
+				g_pool_ring = atoi(t);
 		const char *e = getenv("DETEXB200_DEVICES");
 		if (e && *e && g_devices.empty()) {
 			int n = 0;
@@ -642,7 +691,7 @@ bool decode_texture_host(const detexTexture *t, uint8_t *pixel_buffer, uint32_t 
 	const std::vector<int> devices = device_set();
 	const bool pinned_in = host_pointer_is_pinned(t->data), pinned_out = host_pointer_is_pinned(pixel_buffer);
 	const bool use_pool = in_bytes + out_bytes >= POOL_MIN_BYTES && (!devices.empty() || !pinned_in || !pinned_out);
-	const std::vector<Slab> slabs = plan_slabs(t, layout, call.bb, call.ps, use_pool ? POOL_SLAB_BYTES : SLAB_BYTES);
+	const std::vector<Slab> slabs = plan_slabs(t, layout, call.bb, call.ps, use_pool ? g_pool_slab_bytes : SLAB_BYTES);
 	size_t max_in = 0, max_out = 0, max_tmp = 0;
 	for (const Slab &s : slabs) {
 		max_in = s.in_len > max_in ? s.in_len : max_in;
@@ -657,33 +706,59 @@ bool decode_texture_host(const detexTexture *t, uint8_t *pixel_buffer, uint32_t 
 		const std::vector<int> devs = devices.empty() ? std::vector<int>(1, cur) : devices;
 		int want = g_host_threads;
 		if (want <= 0) {
-			// pool threads sleep while their slab is on the link and copy while it is not: one per hardware
-			// thread keeps both the link and the host memory system busy (measured: 8 -> 16 threads on a 16-thread box)
+			// the pool's threads copy (blocks in, pixels out) and enqueue; one per hardware thread keeps the host
+			// memory system busy, which is what a pageable call is bound by
 			const int hw = (int)std::thread::hardware_concurrency();
 			want = hw < 4 ? 4 : (hw > 32 ? 32 : hw);
-			if (want < 3 * (int)devs.size())
-				want = 3 * (int)devs.size();
 		}
 		if (want > 64)
 			want = 64;
 		pool().ensure(want);
-		CallState st;
-		st.pending = (int)slabs.size();
-		for (size_t k = 0; k < slabs.size(); k++) {
-			Job j;
-			j.call = &call;
-			j.slab = &slabs[k];
-			j.device = devs[k % devs.size()];
-			j.bounce_in = !pinned_in;
-			j.bounce_out = !pinned_out;
-			j.max_in = max_in;
-			j.max_out = max_out;
-			j.max_tmp = max_tmp;
-			j.state = &st;
-			pool().submit(j);
+		// the caller's ring of lanes on every device of the set: streams, device buffers, pinned bounce buffers
+		const size_t per_dev = (slabs.size() + devs.size() - 1) / devs.size();
+		const size_t ring = per_dev < (size_t)g_pool_ring ? per_dev : (size_t)g_pool_ring;
+		std::vector<std::vector<char>> busy(devs.size(), std::vector<char>(ring, 0));
+		bool ok = true;
+		for (size_t d = 0; d < devs.size() && ok; d++) {
+			if (cudaSetDevice(devs[d]) != cudaSuccess) {
+				set_error("%s: cannot select CUDA device %d", who, devs[d]);
+				ok = false;
+				break;
+			}
+			std::vector<Lane> &r = c.rings[devs[d]];
+			if (r.size() < ring)
+				r.resize(ring);
+			for (size_t i = 0; i < ring && ok; i++)
+				ok = r[i].init() && reserve_lane(r[i], call, max_in, max_out, max_tmp, !pinned_in, !pinned_out);
 		}
-		std::unique_lock<std::mutex> g(st.m);
-		st.cv.wait(g, [&] { return st.pending == 0; });
+		cudaSetDevice(cur);
+		if (!ok)
+			return false;
+		CallState st;
+		{
+			std::unique_lock<std::mutex> g(st.m);
+			for (size_t k = 0; k < slabs.size(); k++) {
+				const size_t d = k % devs.size(), i = (k / devs.size()) % ring;
+				char *flag = &busy[d][i];
+				st.cv.wait(g, [&] { return !*flag; });		// the lane's previous slab has been copied out
+				if (st.rc != DETEXB200_OK)
+					break;
+				*flag = 1;
+				st.pending++;
+				Job j;
+				j.kind = Job::SUBMIT;
+				j.call = &call;
+				j.slab = &slabs[k];
+				j.lane = &c.rings[devs[d]][i];
+				j.lane_busy = reinterpret_cast<bool *>(flag);
+				j.device = devs[d];
+				j.bounce_in = !pinned_in;
+				j.bounce_out = !pinned_out;
+				j.state = &st;
+				pool().submit(j);
+			}
+			st.cv.wait(g, [&] { return st.pending == 0; });
+		}
 		if (st.rc != DETEXB200_OK) {
 			g_error = st.error;
 			return false;

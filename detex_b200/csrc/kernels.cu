@@ -311,7 +311,10 @@ __device__ __forceinline__ void report_invalid(bool any_bad_in_thread, uint32_t 
 // planar block and would execute the planar instruction stream for one or two active lanes.
 // Instead a lane that meets a planar block only queues the block's index in shared memory; after
 // a CTA barrier the queued blocks are decoded together, 32 per warp pass.
-constexpr int DEFER_ITERS = 8;		// blocks per thread between two drains of the queue
+#ifndef DETEXB200_DEFER_ITERS
+#define DETEXB200_DEFER_ITERS 8
+#endif
+constexpr int DEFER_ITERS = DETEXB200_DEFER_ITERS;	// blocks per thread between two drains of the queue
 template <int F> struct DeferTraits { static constexpr bool ENABLED = false; };
 struct DeferEtc2 {
 	static constexpr bool ENABLED = true;
@@ -434,6 +437,15 @@ uint32_t mode_mask, uint32_t flags, uint32_t post_op, uint32_t *invalid_flag, ui
 	// a warp takes TI consecutive tiles per pass, all of their loads issued before the first decode
 	constexpr int TI = TiledTune<F>::ITERS;
 	const uint32_t n_groups = (n_tiles + TI - 1) / TI;
+	// deferral formats (TI == 1, a rolled pass loop): the block of the NEXT pass is requested before this pass is
+	// decoded, so that its HBM latency hides behind the decode (see decode_linear_kernel)
+	using BlockT = typename BlockReg<BW>::type;
+	BlockT blk_next{};
+	if constexpr (D::ENABLED) {
+		const uint32_t i0 = ((uint32_t)blockIdx.x * CTA_WARPS + warp) * 32u + lane;
+		if (blockIdx.x * CTA_WARPS < n_groups && (blockIdx.x * CTA_WARPS + warp) < n_tiles && i0 < n_blocks)
+			blk_next = BlockReg<BW>::load(src + (size_t)i0 * (BW * 4));
+	}
 	for (uint32_t tile_base = blockIdx.x * CTA_WARPS; tile_base < n_groups; tile_base += gridDim.x * CTA_WARPS, it++) {
 #pragma unroll
 		for (int k = 0; k < TI; k++) {
@@ -442,8 +454,16 @@ uint32_t mode_mask, uint32_t flags, uint32_t post_op, uint32_t *invalid_flag, ui
 			const bool active = tile < n_tiles && i < n_blocks;
 			uint32_t px[OW];
 			bool ok = true, rare = false;
+			BlockT blk = blk_next;
+			if constexpr (D::ENABLED) {
+				static_assert(!D::ENABLED || TI == 1, "the prefetch assumes one tile per pass");
+				const uint32_t tile_n = tile + gridDim.x * CTA_WARPS, i_n = tile_n * 32u + lane;
+				if (tile_base + gridDim.x * CTA_WARPS < n_groups && tile_n < n_tiles && i_n < n_blocks)
+					blk_next = BlockReg<BW>::load(src + (size_t)i_n * (BW * 4));
+			}
 			if (active) {
-				const auto blk = BlockReg<BW>::load(src + (size_t)i * (BW * 4));
+				if constexpr (!D::ENABLED)
+					blk = BlockReg<BW>::load(src + (size_t)i * (BW * 4));
 				if constexpr (D::ENABLED)
 					rare = D::is_rare(blk);
 				if (!rare)
@@ -577,11 +597,29 @@ ToneArgs tone_args) {
 	constexpr int ITERS = LinearTune<F>::ITERS;
 	const int rows_per_group = ITERS * blockDim.y;
 	for (int g = blockIdx.y; g * rows_per_group < hib; g += gridDim.y) {
+		// Formats with a deferral queue run DEFER_ITERS strips per barrier interval in a rolled loop (their decoders are
+		// too large to unroll eight times); the next strip's block is requested before the current one is decoded, or
+		// every iteration would start by waiting out the full HBM latency of its one load (ncu, round 2: one third of
+		// all warp samples of the ETC2 kernels sat on the first use of the loaded block).
+		using BlockT = typename BlockReg<BW>::type;
+		BlockT blk_next{};
+		if constexpr (D::ENABLED) {
+			const int by0 = g * rows_per_group + threadIdx.y;
+			if (bx < wib && by0 < hib)
+				blk_next = BlockReg<BW>::load(src + ((size_t)by0 * wib + bx) * (BW * 4));
+		}
 #pragma unroll(D::ENABLED ? 1 : ITERS)
 		for (int k = 0; k < ITERS; k++) {
 			const int by = g * rows_per_group + k * blockDim.y + threadIdx.y;
+			BlockT blk = blk_next;
+			if constexpr (D::ENABLED) {
+				const int by_n = by + blockDim.y;
+				if (k + 1 < ITERS && bx < wib && by_n < hib)
+					blk_next = BlockReg<BW>::load(src + ((size_t)by_n * wib + bx) * (BW * 4));
+			}
 			if (bx < wib && by < hib) {
-				const auto blk = BlockReg<BW>::load(src + ((size_t)by * wib + bx) * (BW * 4));
+				if constexpr (!D::ENABLED)
+					blk = BlockReg<BW>::load(src + ((size_t)by * wib + bx) * (BW * 4));
 				bool rare = false;
 				if constexpr (D::ENABLED)
 					rare = D::is_rare(blk);
@@ -738,17 +776,28 @@ template <int F, int PC> constexpr int stage_words() {
 //     1024, 29.0 at 3072 -- the further apart in time the halves are written, the worse: stays at 1024;
 //   BC6H, 2048 -> 3072: TILED +3-9 % and LINEAR -4 ... -13 % at 8.4 M blocks, +-2 % at 4.2 M: stays at 2048
 //     (SortTraits::TILE_BLOCKS).
-template <int F, int PC, bool STAGE, int LAYOUT> constexpr int sort_tile() {
+// Threads per CTA (1024 threads = 32 warps per SM in every configuration, 64 registers each).  BC7: four CTAs of 256
+// threads -- more independent CTAs to run while one sits at a barrier or waits for its staged tile to drain; measured
+// against two CTAs of 512 (round 2, 16.8 M blocks, M LINEAR / TILED 48.7 / 48.9 -> 51.7 / 51.4 G blocks/s, U LINEAR
+// 38.5 -> 40.1; 4.2 M blocks: M 45.7 / 43.7 -> 48.7 / 48.0).  BC6H loses 6-13 % that way (its 15 bins want the larger
+// tiles that only 512-thread CTAs have the shared memory for) and keeps two CTAs of 512.
+// -DDETEXB200_SORT_1024 builds the round-1 experiment "ONE CTA of 1024 threads per SM, staged tiles of 2048 blocks":
+// measured slower then (BC7 LINEAR M 41.8 -> 36.9), kept for A/B runs.
+template <int F> constexpr int sort_threads() {
 #ifdef DETEXB200_SORT_1024
-	if (STAGE)
-		return stages_packed_half3<F, PC>() ? 1024 : 2048;
-#endif
-#ifdef DETEXB200_SORT_256
-	// four CTAs of 256 threads per SM: at most 56 KiB of shared memory each
-	if (STAGE)
-		return stages_packed_half3<F, PC>() ? 256 : 512;
 	return 1024;
+#elif defined(DETEXB200_SORT_512)
+	return 512;
+#else
+	return F == F_BPTC ? 256 : 512;
 #endif
+}
+template <int F, int PC, bool STAGE, int LAYOUT> constexpr int sort_tile() {
+	constexpr int THREADS = sort_threads<F>();
+	if (THREADS == 1024 && STAGE)
+		return stages_packed_half3<F, PC>() ? 1024 : 2048;
+	if (THREADS == 256)		// at most 56 KiB of shared memory per CTA
+		return STAGE ? (stages_packed_half3<F, PC>() ? 256 : 512) : 1024;
 	if (STAGE)
 		return stages_packed_half3<F, PC>() ? 512 : 1024;
 	if (F == F_BPTC)
@@ -756,20 +805,6 @@ template <int F, int PC, bool STAGE, int LAYOUT> constexpr int sort_tile() {
 	return SortTraits<F>::TILE_BLOCKS;
 }
 
-// -DDETEXB200_SORT_1024 builds the experiment "ONE CTA of 1024 threads per SM, staged tiles of 2048 blocks
-// (1024 for the packed half tiles)": half the padded bins per block, but no second CTA to fill the SM while
-// one sits at a barrier.  Measured (G blocks/s, 512 x 2 -> 1024 x 1): BC7 LINEAR M 41.8 -> 36.9, U 34.0 ->
-// 32.9, BC7 TILED M 42.5 -> 36.5; only the staged BC6H variants gain (-> RGBX8 LINEAR 20.2 -> 21.0,
-// -> FLOAT_RGB16 LINEAR 15.8 -> 18.1).  Not adopted.
-#ifdef DETEXB200_SORT_1024
-constexpr int SORT_THREADS = 1024, SORT_WARPS = SORT_THREADS / 32, SORT_CTAS = 1;
-#elif defined(DETEXB200_SORT_256)
-// -DDETEXB200_SORT_256: FOUR CTAs of 256 threads per SM (same warps per SM), tiles of 512 (staged) / 1024 blocks: more
-// independent CTAs to run while one waits at a barrier or for its staged tile to drain.
-constexpr int SORT_THREADS = 256, SORT_WARPS = SORT_THREADS / 32, SORT_CTAS = 4;
-#else
-constexpr int SORT_THREADS = 512, SORT_WARPS = SORT_THREADS / 32, SORT_CTAS = 2;
-#endif
 constexpr uint32_t SLOT_EMPTY = 0xFFFFu;		// sorted slot that is bin padding
 
 // Physical 16-byte slot of chunk c of the block with tile-local index id in the staging buffer:
@@ -860,7 +895,7 @@ __device__ __forceinline__ uint32_t raw_slot(uint32_t id) { return id ^ ((id >> 
 // see tma_store_3d above) instead of the cooperative copy-out: no LDS / STG / address arithmetic per block, and one
 // barrier less per tile because the store of tile t is issued at the top of tile t + 1 and runs under its sort.
 template <int F, int LAYOUT, bool STAGE, int PC, int PAD = 32, bool TMA = false>
-__global__ void __launch_bounds__(SORT_THREADS, SORT_CTAS)
+__global__ void __launch_bounds__(sort_threads<F>(), 1024 / sort_threads<F>())
 decode_sorted_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, uint32_t n_blocks, int width,
 int height, int wib, uint32_t mode_mask, uint32_t flags, uint32_t post_op, uint32_t *invalid_flag, uint32_t *invalid_map,
 ToneArgs tone_args, uint32_t stagger_ns, const __grid_constant__ CUtensorMap tmap) {
@@ -868,6 +903,7 @@ ToneArgs tone_args, uint32_t stagger_ns, const __grid_constant__ CUtensorMap tma
 	using S = SortTraits<F>;
 	using SM = SortedSmem<F, PC, STAGE, LAYOUT>;
 	const EmitCtx<PC> ctx(tone_args);
+	constexpr int SORT_THREADS = sort_threads<F>(), SORT_WARPS = SORT_THREADS / 32;
 	constexpr int OW = T::OUT_WORDS, NB = S::NUM_BINS, TB = SM::TB, PER = TB / SORT_THREADS, CHUNKS = SM::CHUNKS;
 	constexpr int CPR = CHUNKS / 4;			// 16-byte chunks per pixel row of one block
 	static_assert(T::BLOCK_WORDS == 4, "sorted kernel handles 16-byte blocks");
@@ -1206,6 +1242,291 @@ ToneArgs tone_args, uint32_t stagger_ns, const __grid_constant__ CUtensorMap tma
 	}
 	report_invalid(bad, invalid_flag);
 }
+
+#ifdef DETEXB200_EXPERIMENTS
+// ---- mode-sorted kernel, second structure: one sorter warp, ticketed groups, one barrier per tile ---------------
+// EXPERIMENT (round 2), measured slower than decode_sorted_kernel and therefore only in -DDETEXB200_EXPERIMENTS builds,
+// selected at run time with DETEXB200_SORT_KERNEL=stream: BC7 16.8 M blocks M LINEAR 30.7 vs 47.9 G blocks/s, TILED 38.2 vs
+// 48.6 (U TILED 45.2 vs 48.2); bit-exact (the GPU parity tests pass under it).  Why it loses: the sort is ~12 % of the
+// decode's instructions whoever executes it, and ONE warp gets one eighth of its scheduler's issue slots while the
+// seven decoding warps beside it are busy -- the sorter becomes the critical path and the decoders wait for it at the
+// tile barrier (ncu: 44-56 % of all warp samples at that barrier).  The idea behind it:
+// What ncu showed for decode_sorted_kernel on BC7 (distribution M, round 2): the decode itself -- two thirds of the
+// instructions -- takes a quarter of the warp samples; the counting sort (shared atomics, shuffles, dependent shared
+// loads: latency-bound, executed by ALL warps between barriers of its own), the loop head and the barriers take the
+// rest.  Here the sort of a tile is the job of ONE warp, which needs no atomics and no CTA barrier for it, and it runs
+// while the other warps decode the previous tile:
+//   * the sorter warp requests tile t+1 (cp.async), and streams through it 32 blocks at a time: match the bins of the
+//     32 blocks, append them to the open group of their bin (a running count per bin), open a new group whenever a bin
+//     reaches a multiple of 32.  Groups of 32 same-mode ids come out in one pass, no histogram / prefix / scatter; the
+//     open groups left at the end of the tile stay partly filled (the rest of their slots holds the sentinel);
+//   * every warp -- the sorter too, once it is done -- draws groups of tile t from a ticket counter (drawn one group
+//     ahead, so the atomic's latency is hidden) and decodes them;
+//   * ONE __syncthreads per tile hands tile t+1 to the decoders and the buffers of tile t back to the sorter;
+//   * staged LINEAR output (BC7, toned BC6H): thread 0 of the sorter warp hands the staged tile t-1 to the TMA unit
+//     right after the barrier and waits until it has been read; the decoders meet it on a named barrier before their
+//     FIRST write to the stage -- i.e. after a whole group has been decoded into registers, which covers the drain.
+constexpr int STREAM_THREADS = 512, STREAM_WARPS = STREAM_THREADS / 32, STREAM_CTAS = 2;
+template <int F, int PC, bool STAGE, int LAYOUT> constexpr int stream_tile() {
+	if (STAGE)
+		return 1024;
+	return F == F_BPTC ? 3072 : 2048;
+}
+template <int F, int PC, bool STAGE, int LAYOUT>
+struct StreamSmem {
+	static constexpr int TB = stream_tile<F, PC, STAGE, LAYOUT>(), NB = SortTraits<F>::NUM_BINS;
+	static constexpr int MAX_GROUPS = TB / 32 + NB;
+	uint4 out[STAGE ? TB * 4 : 1];		// staged pixels (stage_slot<.., TMA> layout), first: 1024-byte aligned
+	uint4 raw[2][TB];			// double-buffered compressed tile, filled by cp.async
+	uint16_t ids[2][MAX_GROUPS * 32];	// groups of 32 tile-local block indices (sentinel = unused slot)
+	int n_groups[2];
+	int ticket[2];
+	int delta[8][16];			// sorter: blocks per bin in each chunk of the current batch
+	int gmap[16][16];			// sorter: group number of group q of a bin's stream, at [bin][q % 16]
+	uint8_t bin_lut[256];
+	BptcTables tables;
+};
+
+template <int F, int LAYOUT, bool STAGE, int PC>
+__global__ void __launch_bounds__(STREAM_THREADS, STREAM_CTAS)
+decode_stream_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, uint32_t n_blocks, int width,
+int height, int wib, uint32_t mode_mask, uint32_t flags, uint32_t post_op, uint32_t *invalid_flag, uint32_t *invalid_map,
+ToneArgs tone_args, const __grid_constant__ CUtensorMap tmap) {
+	using T = FormatTraits<F>;
+	using S = SortTraits<F>;
+	using SM = StreamSmem<F, PC, STAGE, LAYOUT>;
+	const EmitCtx<PC> ctx(tone_args);
+	constexpr int OW = T::OUT_WORDS, NB = S::NUM_BINS, TB = SM::TB;
+	constexpr bool TMA = STAGE;
+	static_assert(T::BLOCK_WORDS == 4 && NB <= 15 && TB % 64 == 0, "16-byte blocks, at most 15 bins");
+	static_assert(!STAGE || tma_capable<F, PC, true, LAYOUT>(), "the only staged output of this kernel is the TMA one");
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	SM &sm = *reinterpret_cast<SM *>(smem_raw + ((0u - (uint32_t)__cvta_generic_to_shared(smem_raw)) & 1023u));
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const bool sorter = warp == STREAM_WARPS - 1;
+	const unsigned lt_mask = (1u << lane) - 1u;
+	const uint32_t n_tiles = (n_blocks + TB - 1) / TB;
+	uint32_t tile = blockIdx.x;
+	if (tile >= n_tiles)
+		return;
+	bptc_tables_load(sm.tables);
+	for (int v = tid; v < 256; v += STREAM_THREADS) {
+		uint4 probe;
+		probe.x = (uint32_t)v; probe.y = probe.z = probe.w = 0u;
+		sm.bin_lut[v] = (uint8_t)S::bin_of(probe, mode_mask, flags);
+	}
+	if (tid < 2) {
+		sm.n_groups[tid] = 0;
+		sm.ticket[tid] = 0;
+	}
+	__syncthreads();
+
+	// ---- sorter warp ---------------------------------------------------------------------------------------------
+	auto request_tile = [&](uint32_t t, int buf) {		// (whole warp) cp.async of tile t into raw[buf]
+		const uint32_t n_in_tile = min((uint32_t)TB, n_blocks - t * TB);
+		for (uint32_t id = lane; id < n_in_tile; id += 32)
+			cp_async_16(&sm.raw[buf][raw_slot(id)], src + ((size_t)t * TB + id) * 16);
+		asm volatile("cp.async.commit_group;" ::: "memory");
+	};
+	// (whole warp) raw[buf] -> ids[buf], n_groups[buf].  Eight chunks of 32 blocks are in flight together so that the
+	// shared-memory and shuffle latencies of a chunk overlap those of its neighbours: per batch there are six
+	// warp-wide dependent steps instead of four per chunk.  Lane b < 16 keeps the running count of bin b in a register.
+	auto sort_tile_into = [&](uint32_t t, int buf) {
+		const uint32_t n_in_tile = min((uint32_t)TB, n_blocks - t * TB);
+		uint32_t *ids32 = reinterpret_cast<uint32_t *>(sm.ids[buf]);
+		for (int i = lane; i < SM::MAX_GROUPS * 16; i += 32)
+			ids32[i] = 0xFFFFFFFFu;
+		int my_cnt = 0, n_groups = 0;
+		asm volatile("cp.async.wait_group 0;" ::: "memory");
+		__syncwarp();
+		constexpr int BATCH = 8;
+		for (uint32_t c0 = 0; c0 * 32 < n_in_tile; c0 += BATCH) {
+			int bin[BATCH], rank[BATCH], pos[BATCH];
+			reinterpret_cast<uint4 *>(&sm.delta[0][0])[lane] = make_uint4(0u, 0u, 0u, 0u);	// 8 x 16 counts
+#pragma unroll
+			for (int k = 0; k < BATCH; k++) {
+				const uint32_t id = (c0 + k) * 32 + lane;
+				bin[k] = 15;				// lanes beyond the tile: a bin of their own, never emitted
+				if (id < n_in_tile)
+					bin[k] = sm.bin_lut[reinterpret_cast<const uint8_t *>(&sm.raw[buf][raw_slot(id)])[0]];
+			}
+			__syncwarp();
+#pragma unroll
+			for (int k = 0; k < BATCH; k++) {
+				const unsigned peers = __match_any_sync(0xFFFFFFFFu, bin[k]);
+				rank[k] = __popc(peers & lt_mask);
+				if (rank[k] == 0)
+					sm.delta[k][bin[k]] = __popc(peers);	// blocks of this bin in chunk k
+			}
+			__syncwarp();
+			// lane b: count of bin b before each chunk of the batch
+#pragma unroll
+			for (int k = 0; k < BATCH; k++) {
+				pos[k] = my_cnt;
+				my_cnt += sm.delta[k][lane & 15];
+			}
+			unsigned openers[BATCH];
+#pragma unroll
+			for (int k = 0; k < BATCH; k++) {
+				pos[k] = __shfl_sync(0xFFFFFFFFu, pos[k], bin[k]) + rank[k];	// position of the block in its bin's stream
+				openers[k] = __ballot_sync(0xFFFFFFFFu, bin[k] != 15 && (pos[k] & 31) == 0);
+			}
+#pragma unroll
+			for (int k = 0; k < BATCH; k++) {
+				if ((openers[k] >> lane) & 1u)		// first block of a new group of its bin
+					sm.gmap[bin[k]][(pos[k] >> 5) & 15] = n_groups + __popc(openers[k] & lt_mask);
+				n_groups += __popc(openers[k]);
+			}
+			__syncwarp();
+#pragma unroll
+			for (int k = 0; k < BATCH; k++)
+				if (bin[k] != 15)
+					sm.ids[buf][sm.gmap[bin[k]][(pos[k] >> 5) & 15] * 32 + (pos[k] & 31)] = (uint16_t)((c0 + k) * 32 + lane);
+			__syncwarp();
+		}
+		if (lane == 0) {
+			sm.n_groups[buf] = n_groups;
+			sm.ticket[buf] = 0;
+		}
+	};
+	// the staged tile that starts at block t0 -> image: one bulk tensor store per box of 64 blocks (one thread)
+	auto tma_store_tile = [&](uint32_t t0, uint32_t n_in_tile) {
+		uint32_t by = t0 / (uint32_t)wib, bx = t0 - by * (uint32_t)wib;
+		for (uint32_t b = 0; 64u * b < n_in_tile; b++) {
+			tma_store_3d(&tmap, &sm.out[256u * b], 0, (int)(bx >> 3), (int)(4u * by));
+			bx += 64u;
+			if (bx >= (uint32_t)wib) {
+				bx = 0u;
+				by++;
+			}
+		}
+		tma_store_commit();
+	};
+
+	if (sorter) {
+		request_tile(tile, 0);
+		sort_tile_into(tile, 0);
+	}
+	bool bad = false;
+	for (int it = 0;; it++) {
+		const int cur = it & 1;
+		const uint32_t tile0 = tile * TB;
+		const uint32_t next = tile + gridDim.x;
+		const bool has_next = next < n_tiles;
+		__syncthreads();	// tile `tile` is sorted (ids[cur], n_groups[cur]); everything of the previous tile is done
+		bool stage_open = !(TMA && it > 0);	// may this thread write to the stage yet?
+		if (sorter) {
+			if constexpr (TMA) {
+				if (it > 0 && lane == 0)
+					tma_store_tile(tile0 - gridDim.x * TB, TB);	// (only the last tile of the texture can be partial)
+			}
+			if (has_next)
+				request_tile(next, cur ^ 1);
+			if constexpr (TMA) {
+				if (it > 0) {
+					if (lane == 0)
+						tma_store_wait_read();
+					__syncwarp();
+					asm volatile("bar.arrive 1, %0;" :: "n"(STREAM_THREADS) : "memory");	// the stage is free
+					stage_open = true;
+				}
+			}
+			if (has_next)
+				sort_tile_into(next, cur ^ 1);
+		}
+		// ---- decode: groups drawn from the ticket, one ahead
+		const int n_groups = *(volatile int *)&sm.n_groups[cur];
+		int g_next = 0;
+		if (lane == 0)
+			g_next = atomicAdd(&sm.ticket[cur], 1);
+		g_next = __shfl_sync(0xFFFFFFFFu, g_next, 0);
+		uint32_t id_next = g_next < n_groups ? sm.ids[cur][g_next * 32 + lane] : SLOT_EMPTY;
+		while (g_next < n_groups) {
+			const uint32_t id = id_next;
+			if (lane == 0)
+				g_next = atomicAdd(&sm.ticket[cur], 1);
+			g_next = __shfl_sync(0xFFFFFFFFu, g_next, 0);
+			id_next = g_next < n_groups ? sm.ids[cur][g_next * 32 + lane] : SLOT_EMPTY;
+			const bool live = id != SLOT_EMPTY;
+			uint32_t px[OW];
+			bool ok = true;
+			const uint4 w = sm.raw[cur][raw_slot(live ? id : 0u)];
+			if (live) {
+				ok = decode_px<F, PC>(w, mode_mask, flags, &sm.tables, ctx, px);
+				if (!ok) {
+					bad = true;
+					mark_invalid(invalid_map, tile0 + id);
+#pragma unroll
+					for (int k = 0; k < OW; k++)
+						px[k] = invalid_fill(post_op);
+				}
+			}
+			if constexpr (TMA) {
+				if (!stage_open) {		// (uniform over the warp) the staged previous tile has been read
+					asm volatile("bar.sync 1, %0;" :: "n"(STREAM_THREADS) : "memory");
+					stage_open = true;
+				}
+			}
+			if (live) {
+				if constexpr (STAGE && is_tone_class(PC)) {
+					uint32_t t[16];
+					tone_tile<PC>(px, t, post_op, ctx, ok);
+#pragma unroll
+					for (int c = 0; c < 4; c++)
+						sm.out[stage_slot<TB, 4, true>(id, c)] = make_uint4(t[4 * c], t[4 * c + 1], t[4 * c + 2], t[4 * c + 3]);
+				}
+				else if constexpr (STAGE) {
+					apply_post_op<OW>(px, post_op);
+#pragma unroll
+					for (int c = 0; c < 4; c++)
+						sm.out[stage_slot<TB, 4, true>(id, c)] = make_uint4(px[4 * c], px[4 * c + 1], px[4 * c + 2], px[4 * c + 3]);
+				}
+				else {
+					emit<PC>(px, post_op, ctx, ok, [&](auto &q) {
+						constexpr int OWO = post_words<OW, PC>(), CH = OWO / 4;
+						if (LAYOUT == LAYOUT_TILED) {
+							uint8_t *out = dst + (size_t)(tile0 + id) * (OWO * 4);
+							if (CH % 2 == 0 && (((uintptr_t)dst) & 31u) == 0) {
+#pragma unroll
+								for (int c = 0; c + 1 < CH; c += 2)
+									st_stream_v8(out + 16 * c, q[4 * c], q[4 * c + 1], q[4 * c + 2], q[4 * c + 3],
+										q[4 * c + 4], q[4 * c + 5], q[4 * c + 6], q[4 * c + 7]);
+							}
+							else {
+#pragma unroll
+								for (int c = 0; c < CH; c++)
+									st_stream_v4(out + 16 * c, q[4 * c], q[4 * c + 1], q[4 * c + 2], q[4 * c + 3]);
+							}
+						}
+						else {
+							const uint32_t i = tile0 + id;
+							const uint32_t by = i / (uint32_t)wib, bx = i - by * (uint32_t)wib;
+							store_linear_rows(dst, (size_t)width * (OWO / 4), (int)bx, (int)by, height, q);
+						}
+					});
+				}
+			}
+		}
+		if constexpr (TMA) {
+			if (!stage_open)		// a warp that drew no group still owes the named barrier its arrival
+				asm volatile("bar.arrive 1, %0;" :: "n"(STREAM_THREADS) : "memory");
+			fence_proxy_async_smem();	// my writes to the staged tile -> visible to the TMA unit
+		}
+		if (!has_next)
+			break;
+		tile = next;
+	}
+	if constexpr (TMA) {
+		__syncthreads();		// the last tile is staged
+		if (tid == 0) {
+			tma_store_tile(tile * TB, min((uint32_t)TB, n_blocks - tile * TB));
+			tma_store_wait_read();
+		}
+	}
+	report_invalid(bad, invalid_flag);
+}
+
+#endif  // DETEXB200_EXPERIMENTS
 
 #ifdef DETEXB200_EXPERIMENTS
 // (a measured-and-dropped design, kept out of the default build: -DDETEXB200_EXPERIMENTS compiles it in and
@@ -1663,7 +1984,8 @@ const CUtensorMap &tmap) {
 	using SM = SortedSmem<F, PC, STAGE, LAYOUT>;
 	const size_t smem = sizeof(SM) + (TMA ? 1024 : 0);		// + alignment slack for the swizzled stage
 	const uint64_t tiles = ((uint64_t)n_blocks + SM::TB - 1) / SM::TB;
-	const uint64_t resident = (uint64_t)sm_count() * SORT_CTAS;		// persistent: two CTAs per SM
+	constexpr int SORT_THREADS = sort_threads<F>();
+	const uint64_t resident = (uint64_t)sm_count() * (1024 / SORT_THREADS);	// persistent: 1024 threads per SM
 	const unsigned grid = (unsigned)(tiles < resident ? tiles : resident);
 	static std::atomic<bool> configured[64];
 	int dev = 0;
@@ -1680,19 +2002,65 @@ const CUtensorMap &tmap) {
 // One instantiation of the sorted kernel: opt in to > 48 KiB of dynamic shared memory once per
 // device, then launch.  Staged LINEAR tiles of 16-byte rows leave through the TMA unit when the image allows it
 // (whole boxes of 64 blocks per block row, 16-byte aligned base).
+#ifdef DETEXB200_EXPERIMENTS
+// DETEXB200_SORT_KERNEL=stream selects decode_stream_kernel where it can run (experiment builds only).
+static bool stream_kernel_enabled() {
+	static const bool v = [] { const char *e = getenv("DETEXB200_SORT_KERNEL"); return e && e[0] == 's'; }();
+	return v;
+}
+
+template <int F, int LAYOUT, bool STAGE, int PC>
+static void launch_stream(const uint8_t *src, uint8_t *dst, uint32_t n_blocks, const DecodeArgs &a, cudaStream_t stream,
+const CUtensorMap &tmap) {
+	using SM = StreamSmem<F, PC, STAGE, LAYOUT>;
+	const size_t smem = sizeof(SM) + 1024;		// + slack to align the struct (the swizzled stage) to 1024 bytes
+	const uint64_t tiles = ((uint64_t)n_blocks + SM::TB - 1) / SM::TB;
+	const uint64_t resident = (uint64_t)sm_count() * STREAM_CTAS;		// persistent: two CTAs per SM
+	const unsigned grid = (unsigned)(tiles < resident ? tiles : resident);
+	static std::atomic<bool> configured[64];
+	int dev = 0;
+	cudaGetDevice(&dev);
+	if (!configured[dev & 63].load()) {
+		cudaFuncSetAttribute(decode_stream_kernel<F, LAYOUT, STAGE, PC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		configured[dev & 63].store(true);
+	}
+	decode_stream_kernel<F, LAYOUT, STAGE, PC><<<grid, STREAM_THREADS, smem, stream>>>(src, dst, n_blocks,
+		a.width, a.height, a.wib, a.mode_mask, a.flags, a.post_op, a.invalid, a.invalid_map, tone_args_of(a), tmap);
+}
+
+#endif  // DETEXB200_EXPERIMENTS
+
+// One instantiation of the sorted kernel: opt in to > 48 KiB of dynamic shared memory once per device, then launch.
+// Staged LINEAR tiles of 16-byte rows leave through the TMA unit when the image allows it (whole boxes of 64 blocks per
+// block row, 16-byte aligned base); otherwise, and for the tiles that are repacked on the way out, the CTA copies them out.
 template <int F, int LAYOUT, bool STAGE, int PC, int PAD = 32>
 static void launch_sorted(const uint8_t *src, uint8_t *dst, uint32_t n_blocks, const DecodeArgs &a, cudaStream_t stream) {
 	CUtensorMap tmap;
+	memset(&tmap, 0, sizeof(tmap));
+#ifdef DETEXB200_EXPERIMENTS
+	if constexpr (!STAGE) {
+		if (stream_kernel_enabled()) {
+			launch_stream<F, LAYOUT, false, PC>(src, dst, n_blocks, a, stream, tmap);
+			return;
+		}
+	}
+#endif
 	if constexpr (tma_capable<F, PC, STAGE, LAYOUT>()) {
 		constexpr int ROW_BYTES = 16;
 		// whole boxes of 64 blocks per block row (pixel rows beyond the image height are clipped by the hardware)
 		if (tma_store_enabled() && a.wib % 64 == 0 && a.height > 4 * (a.hib - 1) &&
 		    make_linear_tensor_map(&tmap, dst, (size_t)a.wib * ROW_BYTES, a.height)) {
+#ifdef DETEXB200_EXPERIMENTS
+			if (stream_kernel_enabled()) {
+				launch_stream<F, LAYOUT, true, PC>(src, dst, n_blocks, a, stream, tmap);
+				return;
+			}
+#endif
 			launch_sorted_variant<F, LAYOUT, STAGE, PC, PAD, true>(src, dst, n_blocks, a, stream, tmap);
 			return;
 		}
+		memset(&tmap, 0, sizeof(tmap));
 	}
-	memset(&tmap, 0, sizeof(tmap));
 	launch_sorted_variant<F, LAYOUT, STAGE, PC, PAD, false>(src, dst, n_blocks, a, stream, tmap);
 }
 
@@ -1764,6 +2132,16 @@ static cudaError_t launch_format(const DecodeArgs &a, cudaStream_t stream) {
 			else if (a.layout == LAYOUT_TILED)
 				launch_sorted<F, LAYOUT_TILED, ST, PC_NATIVE, sort_pad<F, PC_NATIVE, ST>()>(src, dst, (uint32_t)n_blocks, a, stream);
 			else {
+				// A/B: DETEXB200_BC7_LINEAR_DIRECT=1 stores BC7's 16-byte rows straight from the decoding lanes
+				// (half sectors, merged in L2) instead of staging the tile
+				static const bool bc7_direct = [] { const char *e = getenv("DETEXB200_BC7_LINEAR_DIRECT"); return e && e[0] == '1'; }();
+				if constexpr (F == F_BPTC && PC == PC_NATIVE) {
+					if (bc7_direct) {
+						launch_sorted<F, LAYOUT_LINEAR, false, PC, 32>(src, dst, (uint32_t)n_blocks, a, stream);
+						count_launch();
+						return cudaGetLastError();
+					}
+				}
 				constexpr bool STL = ST || is_tone_class(PC) || stages_packed_half3<F, PC>();
 				static const bool stage_half3 = [] { const char *e = getenv("DETEXB200_HALF3_STAGE"); return !(e && e[0] == '0'); }();
 				if constexpr (stages_packed_half3<F, PC>()) {
