@@ -267,6 +267,8 @@ class Bench:
         self.peak, self.peak_src = measured_peak()
         self.build = D.build_id()
         self.cores = os.cpu_count() or 1
+        if world > 1:       # the ranks share the host cores: each library instance gets its share of copy threads
+            D.set_host_threads(max(4, self.cores // world))
 
     # ---- device-resident inputs of one workload: rotating buffer sets totalling >> L2 (126 MB) -------------------
     def build_parts(self, wl):

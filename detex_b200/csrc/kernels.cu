@@ -1043,13 +1043,18 @@ ToneArgs tone_args, uint32_t stagger_ns, const __grid_constant__ CUtensorMap tma
 		const bool has_next = next < n_tiles;
 		__syncthreads();	// B1: id[cur] scattered, raw[cur] landed (classified one iteration ago), stage free
 		// ---- decode: groups of 32 same-mode blocks; padding slots hold the 0xFFFF sentinel.
-		// The next group's ids are fetched before the current group is decoded.
-		int g = warp * 32;
+		// The next group's ids are fetched before the current group is decoded.  Groups are dealt round-robin to the
+		// warps; drawing them from a shared ticket counter instead (heaviest bins first, the ticket drawn one group
+		// ahead) was measured in both rounds and lost both times (round 2: BC7 M LINEAR 51.2 -> 48.8 G blocks/s, signed
+		// BC6H 20.5 -> 18.7): with a ticket all warps of the CTA work through the same mode at the same time.
+		// (Also measured and dropped in round 2: dealing odd rounds in reverse warp order so that no warp collects the most
+		// expensive group of every round -- no gain for BC7, -3 % for BC6H M.)
+		int g_next = warp * 32;
 		// (with PAD < 32 the last group may end inside the warp: slots from total on are not initialised)
-		uint32_t id_next = g + (PAD < 32 ? lane : 0) < total ? sm.id[cur][g + lane] : SLOT_EMPTY;
-		for (; g < total; g += SORT_WARPS * 32) {
+		uint32_t id_next = g_next + (PAD < 32 ? lane : 0) < total ? sm.id[cur][g_next + lane] : SLOT_EMPTY;
+		while (g_next < total) {
 			const uint32_t id = id_next;
-			const int g_next = g + SORT_WARPS * 32;
+			g_next += SORT_WARPS * 32;
 			id_next = g_next + (PAD < 32 ? lane : 0) < total ? sm.id[cur][g_next + lane] : SLOT_EMPTY;
 			const bool live = id != SLOT_EMPTY;
 			if (live) {
