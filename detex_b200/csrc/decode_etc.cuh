@@ -65,14 +65,20 @@ __device__ __forceinline__ void etc_add_clamp(uint32_t rb, uint32_t ga, int m, u
 
 // mode: ETC_INDIVIDUAL / ETC_DIFFERENTIAL / ETC_T / ETC_H.  punch: non-opaque punch-through
 // block (modifier 0 for selectors 0 and 2, selector 2 -> transparent black, Q13).
-template <bool ALPHA>
+// KIND narrows the modes the caller can pass, at compile time: ETC_KIND_ANY all four, ETC_KIND_SIMPLE individual /
+// differential only (the T / H halves of every select fold away: the ETC1 decoder, and the main pass of the ETC2-family
+// texture kernels, which queue T, H and planar blocks for a deferred pass), ETC_KIND_TH T / H only (the deferred pass).
+enum EtcKind : int { ETC_KIND_ANY = 0, ETC_KIND_SIMPLE = 1, ETC_KIND_TH = 2 };
+template <bool ALPHA, int KIND = ETC_KIND_ANY>
 __device__ __forceinline__ void etc_palette_pixels(uint32_t w0, uint32_t idx, uint32_t mode, bool punch, uint32_t (&px)[16]) {
 	// Opaque to the optimiser: a caller that knows the mode on one of its paths (e.g. "differential
 	// bit clear -> individual") would otherwise get a specialised clone of this whole function on
 	// that path, and warps holding both kinds of block would execute both clones.
 	asm volatile("" : "+r"(mode));
 	const uint32_t b0 = w0 & 0xFFu, b1 = (w0 >> 8) & 0xFFu, b2 = (w0 >> 16) & 0xFFu, b3 = w0 >> 24;
-	const bool is_t = mode == ETC_T, is_h = mode == ETC_H, is_th = is_t || is_h;
+	const bool is_t = KIND != ETC_KIND_SIMPLE && mode == ETC_T;
+	const bool is_h = KIND != ETC_KIND_SIMPLE && (KIND == ETC_KIND_TH ? !is_t : mode == ETC_H);
+	const bool is_th = KIND == ETC_KIND_TH || (KIND != ETC_KIND_SIMPLE && (is_t || is_h));
 	// Everything below is straight-line code: both variants of every mode-dependent quantity are
 	// computed and one is picked with a select, so a warp with mixed modes runs it exactly once.
 	// (With if/else on the mode the compiler clones the whole pixel loop per branch and a mixed
@@ -84,7 +90,7 @@ __device__ __forceinline__ void etc_palette_pixels(uint32_t w0, uint32_t idx, ui
 	// true result is in [0,248]), so carries between bytes cancel and the word is exact.
 	const uint32_t v1 = w & 0xF8F8F8u, d3 = w & 0x070707u;
 	const uint32_t v2 = v1 + (d3 << 3) - ((d3 & 0x040404u) << 4);
-	const bool differential = mode == ETC_DIFFERENTIAL;
+	const bool differential = KIND != ETC_KIND_TH && mode == ETC_DIFFERENTIAL;
 	const uint32_t base0 = differential ? (v1 | ((v1 >> 5) & 0x070707u)) : ((w & 0xF0F0F0u) | ((w >> 4) & 0x0F0F0Fu));
 	const uint32_t base1 = differential ? (v2 | ((v2 >> 5) & 0x070707u)) : ((w & 0x0F0F0Fu) * 17u);
 	// -- T / H base colours (4-bit channels replicated to 8 bits) and distance
@@ -200,14 +206,16 @@ __device__ __forceinline__ bool decode_etc1(const uint2 blk, uint32_t mode_mask,
 	bool ok = mode_mask & (differential ? ETC_DIFFERENTIAL : ETC_INDIVIDUAL);
 	if (differential)
 		ok = ok && etc2_mode(blk.x) == ETC_DIFFERENTIAL;
-	etc_palette_pixels<false>(blk.x, bswap32(blk.y), differential ? (uint32_t)ETC_DIFFERENTIAL : (uint32_t)ETC_INDIVIDUAL, false, px);
+	etc_palette_pixels<false, ETC_KIND_SIMPLE>(blk.x, bswap32(blk.y), differential ? (uint32_t)ETC_DIFFERENTIAL : (uint32_t)ETC_INDIVIDUAL, false, px);
 	return ok;
 }
 
-// Which of the two code paths of an ETC2-family decoder gets compiled in: the texture kernels
-// decode palette-mode blocks in their main pass and the (rare) planar blocks in a deferred
-// pass, so each pass only carries the code it can reach.
-enum EtcPaths : int { ETC_PATHS_ALL = 0, ETC_PATHS_NO_PLANAR = 1, ETC_PATHS_PLANAR_ONLY = 2 };
+// Which code paths of an ETC2-family decoder get compiled in.  The texture kernels decode the individual / differential
+// blocks (the ETC1 subset: 91 % of uniformly random blocks) in their main pass and queue the T, H and planar blocks for
+// a deferred pass, so each pass only carries the code it can reach: ETC_PATHS_SIMPLE / ETC_PATHS_RARE.  (Round 1 deferred
+// planar only -- ETC_PATHS_NO_PLANAR / ETC_PATHS_PLANAR_ONLY -- and its main pass computed both the sub-block and the
+// T / H variant of every palette quantity for every block: ETC2 ran at 52 G blocks/s where ETC1 ran at 76.)
+enum EtcPaths : int { ETC_PATHS_ALL = 0, ETC_PATHS_NO_PLANAR = 1, ETC_PATHS_PLANAR_ONLY = 2, ETC_PATHS_SIMPLE = 3, ETC_PATHS_RARE = 4 };
 
 // ETC2 -> RGBX8.  decompress-etc.c:321-367.
 template <int PATHS = ETC_PATHS_ALL>
@@ -216,7 +224,15 @@ __device__ __forceinline__ bool decode_etc2(const uint2 blk, uint32_t mode_mask,
 	const bool differential_bit = (blk.x >> 24) & 2u;
 	const uint32_t mode_if_diff = etc2_mode(blk.x);
 	const uint32_t mode = differential_bit ? mode_if_diff : (uint32_t)ETC_INDIVIDUAL;
-	if (PATHS != ETC_PATHS_NO_PLANAR && (PATHS == ETC_PATHS_PLANAR_ONLY || mode == ETC_PLANAR))
+	if constexpr (PATHS == ETC_PATHS_SIMPLE)
+		etc_palette_pixels<false, ETC_KIND_SIMPLE>(blk.x, idx, mode, false, px);
+	else if constexpr (PATHS == ETC_PATHS_RARE) {
+		if (mode == ETC_PLANAR)
+			etc2_planar(blk.x, blk.y, px);
+		else
+			etc_palette_pixels<false, ETC_KIND_TH>(blk.x, idx, mode, false, px);
+	}
+	else if (PATHS != ETC_PATHS_NO_PLANAR && (PATHS == ETC_PATHS_PLANAR_ONLY || mode == ETC_PLANAR))
 		etc2_planar(blk.x, blk.y, px);
 	else if (PATHS != ETC_PATHS_PLANAR_ONLY)
 		etc_palette_pixels<false>(blk.x, idx, mode, false, px);
@@ -233,7 +249,17 @@ uint32_t (&px)[16]) {
 	const uint32_t mode = etc2_mode(blk.x);
 	bool ok = (mode_mask & mode) != 0u;
 	ok = ok && !(opaque && (flags & FLAG_NON_OPAQUE_ONLY)) && !(!opaque && (flags & FLAG_OPAQUE_ONLY));
-	if (PATHS != ETC_PATHS_NO_PLANAR && (PATHS == ETC_PATHS_PLANAR_ONLY || mode == ETC_PLANAR)) {
+	if constexpr (PATHS == ETC_PATHS_SIMPLE)
+		etc_palette_pixels<true, ETC_KIND_SIMPLE>(blk.x, idx, mode, !opaque, px);	// (always differential in this format)
+	else if constexpr (PATHS == ETC_PATHS_RARE) {
+		if (mode == ETC_PLANAR) {
+			ok = ok && !(flags & FLAG_NON_OPAQUE_ONLY);		// :695-697
+			etc2_planar(blk.x, blk.y, px);
+		}
+		else
+			etc_palette_pixels<true, ETC_KIND_TH>(blk.x, idx, mode, !opaque, px);
+	}
+	else if (PATHS != ETC_PATHS_NO_PLANAR && (PATHS == ETC_PATHS_PLANAR_ONLY || mode == ETC_PLANAR)) {
 		ok = ok && !(flags & FLAG_NON_OPAQUE_ONLY);		// :695-697
 		etc2_planar(blk.x, blk.y, px);
 	}

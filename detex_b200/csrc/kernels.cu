@@ -306,31 +306,53 @@ __device__ __forceinline__ void report_invalid(bool any_bad_in_thread, uint32_t 
 }
 
 // ---- rare-mode deferral ------------------------------------------------------------------------
-// ETC2's planar mode is rare (2.7 % of uniformly random blocks) but runs completely different
-// code from the four palette modes; with one block per lane almost every warp contains a
-// planar block and would execute the planar instruction stream for one or two active lanes.
-// Instead a lane that meets a planar block only queues the block's index in shared memory; after
-// a CTA barrier the queued blocks are decoded together, 32 per warp pass.
+// The ETC2 family has five modes.  Individual and differential (the ETC1 subset) are 91 % of uniformly random blocks and
+// share one short code path; T, H (paint colours and a distance) and planar (a bilinear ramp) are rare and run
+// different code.  With one block per lane almost every warp contains a rare block, and a decoder that can meet all
+// five modes either diverges or -- as round 1's unified palette engine did -- computes both variants of everything
+// for every block.  Instead a lane that meets a T / H / planar block only queues the block's index in shared memory;
+// after a CTA barrier the queued blocks are decoded together, 32 per warp pass (ETC_PATHS_RARE), and the main pass
+// carries the individual / differential code only (ETC_PATHS_SIMPLE).
 #ifndef DETEXB200_DEFER_ITERS
 #define DETEXB200_DEFER_ITERS 8
 #endif
 constexpr int DEFER_ITERS = DETEXB200_DEFER_ITERS;	// blocks per thread between two drains of the queue
+// Which blocks are deferred depends on the layout.  TILED: T, H and planar (measured, round 2, 33.5 M blocks: ETC2 67.9 ->
+// 74.7 G blocks/s, punch-through 62.9 -> 65.2, ETC2_EAC 53.0 -> 57.6).  LINEAR: planar only, as in round 1 -- there the
+// deferred pass writes a block's four 16-byte row segments long after its row neighbours were written, the main pass
+// leaves 9 % of its 512-byte warp rows with holes, and the drain (three barriers, one latency-bound block per thread)
+// grows with the number of deferred blocks: ETC2 LINEAR 57.5 -> 39.9 with T / H deferred, DRAM reads doubled by the
+// partial-sector fills (ncu).  -DDETEXB200_DEFER_PLANAR_ONLY / -DDETEXB200_DEFER_TH_LINEAR force one split for both.
+template <int LAYOUT> constexpr bool defer_th() {
+#ifdef DETEXB200_DEFER_PLANAR_ONLY
+	return false;
+#elif defined(DETEXB200_DEFER_TH_LINEAR)
+	return true;
+#else
+	return LAYOUT == LAYOUT_TILED;
+#endif
+}
+template <int LAYOUT> constexpr int etc_main_paths() { return defer_th<LAYOUT>() ? ETC_PATHS_SIMPLE : ETC_PATHS_NO_PLANAR; }
+template <int LAYOUT> constexpr int etc_deferred_paths() { return defer_th<LAYOUT>() ? ETC_PATHS_RARE : ETC_PATHS_PLANAR_ONLY; }
 template <int F> struct DeferTraits { static constexpr bool ENABLED = false; };
 struct DeferEtc2 {
 	static constexpr bool ENABLED = true;
-	// word holding bytes 0..3 of the colour block; ETC2: planar needs the differential bit set
-	static __device__ __forceinline__ bool planar(uint32_t w0, bool needs_diff_bit) {
-		return (!needs_diff_bit || ((w0 >> 24) & 2u)) && etc2_mode(w0) == ETC_PLANAR;
+	// word holding bytes 0..3 of the colour block; ETC2: the rare modes need the differential bit set
+	template <int LAYOUT>
+	static __device__ __forceinline__ bool rare(uint32_t w0, bool needs_diff_bit) {
+		const uint32_t mode = etc2_mode(w0);
+		const bool hit = defer_th<LAYOUT>() ? mode != ETC_DIFFERENTIAL : mode == ETC_PLANAR;
+		return (!needs_diff_bit || ((w0 >> 24) & 2u)) && hit;
 	}
 };
 template <> struct DeferTraits<F_ETC2> : DeferEtc2 {
-	static __device__ __forceinline__ bool is_rare(const uint2 &b) { return planar(b.x, true); }
+	template <int LAYOUT> static __device__ __forceinline__ bool is_rare(const uint2 &b) { return rare<LAYOUT>(b.x, true); }
 };
 template <> struct DeferTraits<F_ETC2_PUNCHTHROUGH> : DeferEtc2 {
-	static __device__ __forceinline__ bool is_rare(const uint2 &b) { return planar(b.x, false); }
+	template <int LAYOUT> static __device__ __forceinline__ bool is_rare(const uint2 &b) { return rare<LAYOUT>(b.x, false); }
 };
 template <> struct DeferTraits<F_ETC2_EAC> : DeferEtc2 {
-	static __device__ __forceinline__ bool is_rare(const uint4 &b) { return planar(b.z, true); }
+	template <int LAYOUT> static __device__ __forceinline__ bool is_rare(const uint4 &b) { return rare<LAYOUT>(b.z, true); }
 };
 
 // Measured tuning of the LINEAR kernel (profiles/README.md, "LINEAR kernel tuning"): block rows
@@ -465,9 +487,9 @@ uint32_t mode_mask, uint32_t flags, uint32_t post_op, uint32_t *invalid_flag, ui
 				if constexpr (!D::ENABLED)
 					blk = BlockReg<BW>::load(src + (size_t)i * (BW * 4));
 				if constexpr (D::ENABLED)
-					rare = D::is_rare(blk);
+					rare = D::template is_rare<LAYOUT_TILED>(blk);
 				if (!rare)
-					ok = decode_px<F, PC, D::ENABLED ? ETC_PATHS_NO_PLANAR : ETC_PATHS_ALL>(blk, mode_mask, flags, &tables, ctx, px);
+					ok = decode_px<F, PC, D::ENABLED ? etc_main_paths<LAYOUT_TILED>() : ETC_PATHS_ALL>(blk, mode_mask, flags, &tables, ctx, px);
 			}
 			if (!ok) {
 				bad = true;
@@ -541,7 +563,7 @@ uint32_t mode_mask, uint32_t flags, uint32_t post_op, uint32_t *invalid_flag, ui
 				const uint32_t j = queue[e];
 				const auto blk = BlockReg<BW>::load(src + (size_t)j * (BW * 4));
 				uint32_t qx[OW];
-				if (!decode_block<F, ETC_PATHS_PLANAR_ONLY>(blk, mode_mask, flags, &tables, qx)) {
+				if (!decode_block<F, etc_deferred_paths<LAYOUT_TILED>()>(blk, mode_mask, flags, &tables, qx)) {
 					bad = true;
 					mark_invalid(invalid_map, j);
 #pragma unroll
@@ -622,12 +644,12 @@ ToneArgs tone_args) {
 					blk = BlockReg<BW>::load(src + ((size_t)by * wib + bx) * (BW * 4));
 				bool rare = false;
 				if constexpr (D::ENABLED)
-					rare = D::is_rare(blk);
+					rare = D::template is_rare<LAYOUT_LINEAR>(blk);
 				if (rare)
 					queue[atomicAdd(&queue_n, 1)] = (uint32_t)by * (uint32_t)wib + (uint32_t)bx;
 				else {
 					uint32_t px[OW];
-					const bool ok = decode_px<F, PC, D::ENABLED ? ETC_PATHS_NO_PLANAR : ETC_PATHS_ALL>(blk, mode_mask, flags, &tables, ctx, px);
+					const bool ok = decode_px<F, PC, D::ENABLED ? etc_main_paths<LAYOUT_LINEAR>() : ETC_PATHS_ALL>(blk, mode_mask, flags, &tables, ctx, px);
 					if (!ok) {
 						bad = true;
 						mark_invalid(invalid_map, (uint32_t)by * (uint32_t)wib + (uint32_t)bx);
@@ -648,7 +670,7 @@ ToneArgs tone_args) {
 				const int qy = (int)(j / (uint32_t)wib), qx_ = (int)(j - (uint32_t)qy * (uint32_t)wib);
 				const auto blk = BlockReg<BW>::load(src + (size_t)j * (BW * 4));
 				uint32_t qp[OW];
-				if (!decode_block<F, ETC_PATHS_PLANAR_ONLY>(blk, mode_mask, flags, &tables, qp)) {
+				if (!decode_block<F, etc_deferred_paths<LAYOUT_LINEAR>()>(blk, mode_mask, flags, &tables, qp)) {
 					bad = true;
 					mark_invalid(invalid_map, j);
 #pragma unroll
