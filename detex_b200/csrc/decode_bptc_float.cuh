@@ -215,6 +215,18 @@ struct Bc6hHalfSink {
 		px[2 * i] = prmt(finish(y0), finish(y1), 0x5410);	// Q10: R | G<<16 | B<<32, X = 0
 		px[2 * i + 1] = finish(y2) & 0xFFFFu;
 	}
+	// unsigned, integer pipe: t = 4 * (interpolation sum), i.e. the 16-bit value v = (sum >> 6) is bytes 1-2 of t;
+	// (v * 31) >> 6 = (v * 124) >> 8 = bytes 1-2 of v * 124 (< 2^23)
+#ifdef DETEXB200_BC6H_NO_SCALED
+	static constexpr bool TAKES_SCALED = false;
+#else
+	static constexpr bool TAKES_SCALED = !SIGNED;
+#endif
+	__device__ __forceinline__ void emit_scaled(int i, uint32_t t0, uint32_t t1, uint32_t t2) const {
+		const uint32_t p0 = prmt(t0, 0u, 0x4421) * 124u, p1 = prmt(t1, 0u, 0x4421) * 124u, p2 = prmt(t2, 0u, 0x4421) * 124u;
+		px[2 * i] = prmt(p0, p1, 0x6521);			// Q10: R | G<<16 | B<<32, X = 0
+		px[2 * i + 1] = prmt(p2, 0u, 0x4421);
+	}
 };
 
 template <bool SIGNED, int NS, typename Sink>
@@ -334,6 +346,11 @@ const BptcTables &tab, const Sink &sink) {
 			dk[c] = (uint32_t)(k_c[NS - 1][c] - k_c[0][c]);
 		}
 	}
+	// Unsigned format, sinks that can take it: everything is carried scaled by 4, so that the two ">> 6" of the
+	// reference (InterpolateFloat :97-108, the finish :616-621) become ">> 8" -- byte extractions that ride on the
+	// PRMT which assembles the pixel anyway, instead of a shift each on the integer ALU pipe.
+	constexpr bool SCALED = !SIGNED && Sink::TAKES_SCALED;
+	constexpr int SC = SCALED ? 4 : 1;
 #pragma unroll
 	for (int i = 0; i < 16; i++) {
 		const uint32_t bit = NS == 2 ? ((subset_bits >> i) & 1u) : 0u;
@@ -341,14 +358,20 @@ const BptcTables &tab, const Sink &sink) {
 		int v[3];
 #pragma unroll
 		for (int c = 0; c < 3; c++) {
-			int a = a_c[0][c], k = k_c[0][c];
+			int a = a_c[0][c] * SC, k = k_c[0][c] * SC;
 			if constexpr (NS == 2) {
-				a = (int)mad_u32(bit, da[c], (uint32_t)a);
-				k = (int)mad_u32(bit, dk[c], (uint32_t)k);
+				a = (int)mad_u32(bit, da[c] * SC, (uint32_t)a);
+				k = (int)mad_u32(bit, dk[c] * SC, (uint32_t)k);
 			}
-			v[c] = (a + wgt * k) >> 6;			// InterpolateFloat, :97-108 (Q18)
+			if constexpr (SCALED)
+				v[c] = a + wgt * k;			// 4 * (a + w k) < 2^25: the interpolated value is bytes 1-2
+			else
+				v[c] = (a + wgt * k) >> 6;		// InterpolateFloat, :97-108 (Q18)
 		}
-		sink(i, v[0], v[1], v[2]);
+		if constexpr (SCALED)
+			sink.emit_scaled(i, (uint32_t)v[0], (uint32_t)v[1], (uint32_t)v[2]);
+		else
+			sink(i, v[0], v[1], v[2]);
 	}
 }
 

@@ -142,8 +142,9 @@ __device__ __forceinline__ uint32_t tone8_of_zero(const Tone &t) {
 // low 13 bits cleared.
 template <int N, int MODE>
 struct Bc6hTone8Sink {
-	static constexpr bool FLOAT_PIPE = false;
+	static constexpr bool FLOAT_PIPE = false, TAKES_SCALED = false;
 	__device__ __forceinline__ void emit(int, float, float, float) const {}
+	__device__ __forceinline__ void emit_scaled(int, uint32_t, uint32_t, uint32_t) const {}
 	uint32_t (&q)[N];		// the first 16 words receive the pixels
 	const Tone &tone;
 	__device__ __forceinline__ void operator()(int i, int v0, int v1, int v2) const {
@@ -162,8 +163,9 @@ __device__ __forceinline__ uint32_t tone16_of_zero(const Tone &t) {
 }
 template <int MODE>
 struct Bc6hTone16Sink {
-	static constexpr bool FLOAT_PIPE = false;
+	static constexpr bool FLOAT_PIPE = false, TAKES_SCALED = false;
 	__device__ __forceinline__ void emit(int, float, float, float) const {}
+	__device__ __forceinline__ void emit_scaled(int, uint32_t, uint32_t, uint32_t) const {}
 	uint32_t (&q)[32];
 	const Tone &tone;
 	uint32_t x16;
