@@ -639,7 +639,10 @@ std::vector<int> device_set() {
 					const long d = strtol(p, &end, 10);
 					if (end == p)
 						break;
-					if (d >= 0 && d < n)
+					bool seen = false;
+					for (int v : g_devices)
+						seen = seen || v == (int)d;
+					if (d >= 0 && d < n && !seen)		// (every device once: a lane ring belongs to one device)
 						g_devices.push_back((int)d);
 					p = *end == ',' ? end + 1 : end;
 				}
@@ -760,6 +763,12 @@ bool decode_texture_host(const detexTexture *t, uint8_t *pixel_buffer, uint32_t 
 			st.cv.wait(g, [&] { return st.pending == 0; });
 		}
 		if (st.rc != DETEXB200_OK) {
+			// a failed slab may have left work behind on its lane: nothing of this call may still be running (and
+			// writing into the caller's buffers) once it has returned
+			for (size_t d = 0; d < devs.size(); d++)
+				for (size_t i = 0; i < ring; i++)
+					cudaStreamSynchronize(c.rings[devs[d]][i].stream);
+			(void)cudaGetLastError();
 			g_error = st.error;
 			return false;
 		}
@@ -1022,6 +1031,11 @@ int detexb200SetDevices(int n, const int *device_ids) {
 			set_error("detexb200SetDevices: device ordinal %d out of range (%d devices)", device_ids[i], count);
 			return DETEXB200_EINVAL;
 		}
+		for (int seen : v)
+			if (seen == device_ids[i]) {
+				set_error("detexb200SetDevices: device ordinal %d listed twice", device_ids[i]);
+				return DETEXB200_EINVAL;
+			}
 		v.push_back(device_ids[i]);
 	}
 	device_set();			// (settle the environment first: an explicit call wins over it)

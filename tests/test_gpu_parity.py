@@ -503,6 +503,8 @@ def test_device_set_spreads_one_call_over_gpus(cpu):
                     assert ok == ok_w and np.array_equal(got, want), (devs, fmt, pinned)
         with pytest.raises(D.DetexError):
             D.set_devices([n_dev])
+        with pytest.raises(D.DetexError):
+            D.set_devices([0, 0])
     finally:
         D.set_devices([])
 

@@ -1,5 +1,5 @@
 # 8-GPU call: the default bench at N = 4 and N = 8 (all legs, per-rank parity), the reference arm, and ONE
-# detexDecompressTextureLinear call spread over 1 / 2 / 4 / 8 GPUs.   gpurun --gpus 8 --timeout 1200 -- "bash tools/r2_run_n8.sh"
+# detexDecompressTextureLinear call spread over 1 / 2 / 4 / 8 GPUs.   gpurun --gpus 8 --timeout 1200 -- "bash tools/evidence_n8.sh"
 O=gpurun_out/n8
 mkdir -p gpurun_out/n8
 nvidia-smi --query-gpu=index,name --format=csv > $O/gpus.txt; nproc > $O/nproc.txt

@@ -8,6 +8,7 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $O
 nproc > $O/nproc.txt
 python -c "import detex_b200 as D; print(D.load().detexb200Version().decode())" > $O/version.txt
 timeout 1500 python -m pytest tests -m gpu -q 2>&1 | tail -8 > $O/pytest_gpu.log; tail -3 $O/pytest_gpu.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $O/smoke.log 2>&1; tail -2 $O/smoke.log
 cap() {   # name, traffic key ("" = none), kernel regex, skip, command...
 	local name=$1 key=$2 rx=$3 skip=$4; shift 4
 	timeout 600 ncu --set full --clock-control none --import-source on -k regex:$rx -s $skip -c 1 -f -o gpurun_out/final/ncu_$name "$@" > $O/ncu_$name.log 2>&1
