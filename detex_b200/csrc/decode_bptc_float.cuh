@@ -229,19 +229,13 @@ struct Bc6hHalfSink {
 	}
 };
 
-template <bool SIGNED, int NS, typename Sink>
-__device__ __forceinline__ void bc6h_finish(const uint4 &w, const Bc6hRaw &raw, int epb, int dr, int dg, int db,
-const BptcTables &tab, const Sink &sink) {
-	constexpr int NE = 2 * NS, IB = NS == 1 ? 4 : 3;
+// Delta decode and unquantisation of the endpoints: e[c][k] = unquantised value of endpoint k, component c
+// (16 bits: 0 .. 0xFFFF, signed formats -0x8000 .. 0x7FFF).
+template <bool SIGNED, int NS>
+__device__ __forceinline__ void bc6h_unquantized(const Bc6hRaw &raw, int epb, int dr, int dg, int db, int (&out)[3][2 * NS]) {
+	constexpr int NE = 2 * NS;
 	const uint32_t epmask = epb >= 32 ? 0xFFFFFFFFu : ((1u << epb) - 1u);
 	const int delta_bits[3] = { dr, dg, db };
-#ifdef DETEXB200_BC6H_INT_PIPE
-	constexpr bool FP = false;			// A/B: the integer statement for every sink
-#else
-	constexpr bool FP = Sink::FLOAT_PIPE;
-#endif
-	int a_c[NS][3], k_c[NS][3];		// A = 64*e0 + 32, K = e1 - e0 per subset and component
-	float a_f[NS][3], k_f[NS][3];		// the same divided by 64, as floats (float pipe)
 #pragma unroll
 	for (int c = 0; c < 3; c++) {
 		int e[NE];
@@ -282,30 +276,38 @@ const BptcTables &tab, const Sink &sink) {
 				if (epb >= 16)
 					unq = x;
 			}
-			e[k] = unq;
+			out[c][k] = unq;
 		}
+	}
+}
+
+// Interpolation constants of a block from its unquantised endpoints: A = 64*e0 + 32, K = e1 - e0 per subset and
+// component (integer pipe), or the same divided by 64 as floats (float pipe).
+template <int NS, bool FP>
+struct Bc6hLines {
+	int a_c[NS][3], k_c[NS][3];
+	float a_f[NS][3], k_f[NS][3];
+	__device__ __forceinline__ void set(const int (&e)[3][2 * NS]) {
 #pragma unroll
-		for (int s = 0; s < NS; s++) {
-			if constexpr (FP) {
-				const float e0 = __int2float_rn(e[2 * s]), e1 = __int2float_rn(e[2 * s + 1]);	// exact: |e| < 2^17
-				a_f[s][c] = __fadd_rn(e0, 0.5f);				// (64 e0 + 32) / 64
-				k_f[s][c] = __fmul_rn(__fsub_rn(e1, e0), 0.015625f);		// (e1 - e0) / 64
+		for (int c = 0; c < 3; c++)
+#pragma unroll
+			for (int s = 0; s < NS; s++) {
+				if constexpr (FP) {
+					const float e0 = __int2float_rn(e[c][2 * s]), e1 = __int2float_rn(e[c][2 * s + 1]);	// exact: |e| < 2^17
+					a_f[s][c] = __fadd_rn(e0, 0.5f);				// (64 e0 + 32) / 64
+					k_f[s][c] = __fmul_rn(__fsub_rn(e1, e0), 0.015625f);		// (e1 - e0) / 64
+				}
+				else {
+					a_c[s][c] = 64 * e[c][2 * s] + 32;
+					k_c[s][c] = e[c][2 * s + 1] - e[c][2 * s];
+				}
 			}
-			else {
-				a_c[s][c] = 64 * e[2 * s] + 32;
-				k_c[s][c] = e[2 * s + 1] - e[2 * s];
-			}
-		}
 	}
-	// Index stream with the anchor pixels widened to IB bits (:544-564).
-	const uint2 sw = window64<NS == 1 ? 65 : 82>(w);
-	uint64_t s = insert_zero_bit(((uint64_t)sw.y << 32) | sw.x, IB - 1);
-	uint32_t subset_bits = 0u;
-	if constexpr (NS == 2) {
-		const uint32_t t = tab.two[raw.partition];
-		subset_bits = t & 0xFFFFu;
-		s = insert_zero_bit(s, (t >> 16) * IB + (IB - 1));
-	}
+};
+
+// The 16 pixels of a block: weight(i) = interpolation weight of pixel i, subset_bits bit i = subset of pixel i (NS = 2).
+template <bool SIGNED, int NS, bool FP, typename Sink, typename Weight>
+__device__ __forceinline__ void bc6h_pixel_loop(const Bc6hLines<NS, FP> &ln, uint32_t subset_bits, const Sink &sink, Weight &&weight) {
 	if constexpr (FP) {
 		// endpoint pair of a pixel: X0 + bit * (X1 - X0), interpolation ((64 - w) e0 + w e1 + 32) / 64 = a + w k, floor
 		constexpr float BIAS = SIGNED ? 12582912.0f : 8388608.0f;
@@ -313,20 +315,20 @@ const BptcTables &tab, const Sink &sink) {
 		if constexpr (NS == 2) {
 #pragma unroll
 			for (int c = 0; c < 3; c++) {
-				da[c] = __fsub_rn(a_f[NS - 1][c], a_f[0][c]);
-				dk[c] = __fsub_rn(k_f[NS - 1][c], k_f[0][c]);
+				da[c] = __fsub_rn(ln.a_f[NS - 1][c], ln.a_f[0][c]);
+				dk[c] = __fsub_rn(ln.k_f[NS - 1][c], ln.k_f[0][c]);
 			}
 		}
 #pragma unroll
 		for (int i = 0; i < 16; i++) {
-			const uint32_t wgt = bptc_weight<IB>((uint32_t)(s >> (i * IB)) & ((1u << IB) - 1u));
+			const uint32_t wgt = weight(i);
 			const float wf = __fsub_rn(__uint_as_float(0x4B000000u | wgt), 8388608.0f);	// 2^23 + w - 2^23
 			// 1.0f or 0.0f from the subset bit: an integer multiply-add makes the bit pattern (FMA pipe)
 			const float bit = NS == 2 ? __uint_as_float(mad_u32((subset_bits >> i) & 1u, 0x3F800000u, 0u)) : 0.0f;
 			float y[3];
 #pragma unroll
 			for (int c = 0; c < 3; c++) {
-				float a = a_f[0][c], k = k_f[0][c];
+				float a = ln.a_f[0][c], k = ln.k_f[0][c];
 				if constexpr (NS == 2) {
 					a = __fmaf_rn(bit, da[c], a);
 					k = __fmaf_rn(bit, dk[c], k);
@@ -337,42 +339,82 @@ const BptcTables &tab, const Sink &sink) {
 		}
 		return;
 	}
-	// endpoint pair of a pixel: X0 + bit*(X1 - X0) with multiply-adds (FMA pipe), as in the BC7 decoder
-	uint32_t da[3] = { 0u, 0u, 0u }, dk[3] = { 0u, 0u, 0u };
-	if constexpr (NS == 2) {
+	else {
+		// endpoint pair of a pixel: X0 + bit*(X1 - X0) with multiply-adds (FMA pipe), as in the BC7 decoder
+		uint32_t da[3] = { 0u, 0u, 0u }, dk[3] = { 0u, 0u, 0u };
+		if constexpr (NS == 2) {
 #pragma unroll
-		for (int c = 0; c < 3; c++) {
-			da[c] = (uint32_t)(a_c[NS - 1][c] - a_c[0][c]);
-			dk[c] = (uint32_t)(k_c[NS - 1][c] - k_c[0][c]);
+			for (int c = 0; c < 3; c++) {
+				da[c] = (uint32_t)(ln.a_c[NS - 1][c] - ln.a_c[0][c]);
+				dk[c] = (uint32_t)(ln.k_c[NS - 1][c] - ln.k_c[0][c]);
+			}
 		}
-	}
-	// Unsigned format, sinks that can take it: everything is carried scaled by 4, so that the two ">> 6" of the
-	// reference (InterpolateFloat :97-108, the finish :616-621) become ">> 8" -- byte extractions that ride on the
-	// PRMT which assembles the pixel anyway, instead of a shift each on the integer ALU pipe.
-	constexpr bool SCALED = !SIGNED && Sink::TAKES_SCALED;
-	constexpr int SC = SCALED ? 4 : 1;
+		// Unsigned format, sinks that can take it: everything is carried scaled by 4, so that the two ">> 6" of the
+		// reference (InterpolateFloat :97-108, the finish :616-621) become ">> 8" -- byte extractions that ride on the
+		// PRMT which assembles the pixel anyway, instead of a shift each on the integer ALU pipe.
+		constexpr bool SCALED = !SIGNED && Sink::TAKES_SCALED;
+		constexpr int SC = SCALED ? 4 : 1;
 #pragma unroll
-	for (int i = 0; i < 16; i++) {
-		const uint32_t bit = NS == 2 ? ((subset_bits >> i) & 1u) : 0u;
-		const int wgt = (int)bptc_weight<IB>((uint32_t)(s >> (i * IB)) & ((1u << IB) - 1u));
-		int v[3];
+		for (int i = 0; i < 16; i++) {
+			const uint32_t bit = NS == 2 ? ((subset_bits >> i) & 1u) : 0u;
+			const int wgt = (int)weight(i);
+			int v[3];
 #pragma unroll
-		for (int c = 0; c < 3; c++) {
-			int a = a_c[0][c] * SC, k = k_c[0][c] * SC;
-			if constexpr (NS == 2) {
-				a = (int)mad_u32(bit, da[c] * SC, (uint32_t)a);
-				k = (int)mad_u32(bit, dk[c] * SC, (uint32_t)k);
+			for (int c = 0; c < 3; c++) {
+				int a = ln.a_c[0][c] * SC, k = ln.k_c[0][c] * SC;
+				if constexpr (NS == 2) {
+					a = (int)mad_u32(bit, da[c] * SC, (uint32_t)a);
+					k = (int)mad_u32(bit, dk[c] * SC, (uint32_t)k);
+				}
+				if constexpr (SCALED)
+					v[c] = a + wgt * k;			// 4 * (a + w k) < 2^25: the interpolated value is bytes 1-2
+				else
+					v[c] = (a + wgt * k) >> 6;		// InterpolateFloat, :97-108 (Q18)
 			}
 			if constexpr (SCALED)
-				v[c] = a + wgt * k;			// 4 * (a + w k) < 2^25: the interpolated value is bytes 1-2
+				sink.emit_scaled(i, (uint32_t)v[0], (uint32_t)v[1], (uint32_t)v[2]);
 			else
-				v[c] = (a + wgt * k) >> 6;		// InterpolateFloat, :97-108 (Q18)
+				sink(i, v[0], v[1], v[2]);
 		}
-		if constexpr (SCALED)
-			sink.emit_scaled(i, (uint32_t)v[0], (uint32_t)v[1], (uint32_t)v[2]);
-		else
-			sink(i, v[0], v[1], v[2]);
 	}
+}
+
+// Index stream of a block with the anchor pixels widened to IB bits (:544-564) and the subset bit of every pixel.
+template <int NS>
+__device__ __forceinline__ uint64_t bc6h_index_stream(const uint4 &w, uint32_t partition, const BptcTables &tab, uint32_t &subset_bits) {
+	constexpr int IB = NS == 1 ? 4 : 3;
+	const uint2 sw = window64<NS == 1 ? 65 : 82>(w);
+	uint64_t s = insert_zero_bit(((uint64_t)sw.y << 32) | sw.x, IB - 1);
+	subset_bits = 0u;
+	if constexpr (NS == 2) {
+		const uint32_t t = tab.two[partition];
+		subset_bits = t & 0xFFFFu;
+		s = insert_zero_bit(s, (t >> 16) * IB + (IB - 1));
+	}
+	return s;
+}
+
+template <typename Sink> constexpr bool bc6h_float_pipe() {
+#ifdef DETEXB200_BC6H_INT_PIPE
+	return false;			// A/B: the integer statement for every sink
+#else
+	return Sink::FLOAT_PIPE;
+#endif
+}
+
+template <bool SIGNED, int NS, typename Sink>
+__device__ __forceinline__ void bc6h_finish(const uint4 &w, const Bc6hRaw &raw, int epb, int dr, int dg, int db,
+const BptcTables &tab, const Sink &sink) {
+	constexpr int IB = NS == 1 ? 4 : 3;
+	constexpr bool FP = bc6h_float_pipe<Sink>();
+	int e[3][2 * NS];
+	bc6h_unquantized<SIGNED, NS>(raw, epb, dr, dg, db, e);
+	Bc6hLines<NS, FP> ln;
+	ln.set(e);
+	uint32_t subset_bits;
+	const uint64_t s = bc6h_index_stream<NS>(w, raw.partition, tab, subset_bits);
+	bc6h_pixel_loop<SIGNED, NS, FP>(ln, subset_bits, sink,
+		[&](int i) { return bptc_weight<IB>((uint32_t)(s >> (i * IB)) & ((1u << IB) - 1u)); });
 }
 
 // 5-bit mode code -> detex mode number, -1 for the reserved codes (Q8,
@@ -404,6 +446,88 @@ __device__ __forceinline__ bool decode_bptc_float_to(const uint4 blk, uint32_t m
 	else
 		bc6h_finish<SIGNED, 2>(blk, raw, info.epb, info.dr, info.dg, info.db, tab, sink);
 	return (mode_mask >> mode) & 1u;		// :121
+}
+
+// ---- the decoder in two halves ---------------------------------------------------------------------------------
+// bc6h_prepare: everything that depends on the mode (bit scatter, delta decode, unquantisation, index widths) ->
+// a 48-byte record that looks the same for all 14 modes; bc6h_pixels: record -> 16 pixels, one instruction stream
+// for every block.  The mode-sorted kernels run the first half on groups of same-mode blocks and the second half
+// in image order (kernels.cu, SPLIT), so that a warp's stores are consecutive blocks of the image.
+//   q0 = { (e0 | e1 << 16) of subset 0 for r, g, b;  subset bit of every pixel | valid << 16 }
+//   q1 = { the same of subset 1 (one-subset modes: a copy of subset 0);  0 }
+//   q2 = the interpolation weight of every pixel, one byte each
+struct Bc6hPrepared {
+	uint4 q0, q1, q2;
+};
+
+template <bool SIGNED, int NS>
+__device__ __forceinline__ void bc6h_prepare_tail(const uint4 &w, const Bc6hRaw &raw, const Bc6hModeInfo &info,
+const BptcTables &tab, Bc6hPrepared &p) {
+	constexpr int IB = NS == 1 ? 4 : 3;
+	int e[3][2 * NS];
+	bc6h_unquantized<SIGNED, NS>(raw, info.epb, info.dr, info.dg, info.db, e);
+	uint32_t subset_bits;
+	const uint64_t s = bc6h_index_stream<NS>(w, raw.partition, tab, subset_bits);
+	p.q0 = make_uint4(prmt((uint32_t)e[0][0], (uint32_t)e[0][1], 0x5410), prmt((uint32_t)e[1][0], (uint32_t)e[1][1], 0x5410),
+		prmt((uint32_t)e[2][0], (uint32_t)e[2][1], 0x5410), subset_bits);
+	if constexpr (NS == 2)
+		p.q1 = make_uint4(prmt((uint32_t)e[0][2], (uint32_t)e[0][3], 0x5410), prmt((uint32_t)e[1][2], (uint32_t)e[1][3], 0x5410),
+			prmt((uint32_t)e[2][2], (uint32_t)e[2][3], 0x5410), 0u);
+	else
+		p.q1 = make_uint4(p.q0.x, p.q0.y, p.q0.z, 0u);
+	uint32_t wq[4];
+#pragma unroll
+	for (int j = 0; j < 4; j++) {
+		uint32_t b[4];
+#pragma unroll
+		for (int k = 0; k < 4; k++)
+			b[k] = bptc_weight<IB>((uint32_t)(s >> ((4 * j + k) * IB)) & ((1u << IB) - 1u));
+		wq[j] = prmt(prmt(b[0], b[1], 0x0040), prmt(b[2], b[3], 0x0040), 0x5410);
+	}
+	p.q2 = make_uint4(wq[0], wq[1], wq[2], wq[3]);
+}
+
+// Returns whether the block is valid; the record carries the same flag (bit 16 of q0.w).
+template <bool SIGNED>
+__device__ __forceinline__ bool bc6h_prepare(const uint4 blk, uint32_t mode_mask, const BptcTables &tab, Bc6hPrepared &p) {
+	const int mode = bc6h_mode(blk.x);
+	Bc6hRaw raw;
+	Bc6hModeInfo info = bc6h_mode_info(0);
+	p.q0 = p.q1 = p.q2 = make_uint4(0u, 0u, 0u, 0u);
+	switch (mode) {
+#define BC6H_CASE(M) case M: bc6h_scatter<M>(blk, raw); info = bc6h_mode_info(M); break;
+	BC6H_CASE(0) BC6H_CASE(1) BC6H_CASE(2) BC6H_CASE(3) BC6H_CASE(4) BC6H_CASE(5) BC6H_CASE(6)
+	BC6H_CASE(7) BC6H_CASE(8) BC6H_CASE(9) BC6H_CASE(10) BC6H_CASE(11) BC6H_CASE(12) BC6H_CASE(13)
+#undef BC6H_CASE
+	default: return false;
+	}
+	if (mode >= 10)
+		bc6h_prepare_tail<SIGNED, 1>(blk, raw, info, tab, p);
+	else
+		bc6h_prepare_tail<SIGNED, 2>(blk, raw, info, tab, p);
+	const bool ok = (mode_mask >> mode) & 1u;		// :121
+	p.q0.w |= ok ? 0x10000u : 0u;
+	return ok;
+}
+
+__device__ __forceinline__ bool bc6h_prepared_valid(const Bc6hPrepared &p) { return (p.q0.w >> 16) & 1u; }
+
+template <bool SIGNED, typename Sink>
+__device__ __forceinline__ void bc6h_pixels(const Bc6hPrepared &p, const Sink &sink) {
+	constexpr bool FP = bc6h_float_pipe<Sink>();
+	const uint32_t pair[2][3] = { { p.q0.x, p.q0.y, p.q0.z }, { p.q1.x, p.q1.y, p.q1.z } };
+	int e[3][4];
+#pragma unroll
+	for (int c = 0; c < 3; c++)
+#pragma unroll
+		for (int s = 0; s < 2; s++) {
+			e[c][2 * s] = SIGNED ? (int)(int16_t)(pair[s][c] & 0xFFFFu) : (int)(pair[s][c] & 0xFFFFu);
+			e[c][2 * s + 1] = SIGNED ? ((int)pair[s][c] >> 16) : (int)(pair[s][c] >> 16);
+		}
+	Bc6hLines<2, FP> ln;
+	ln.set(e);
+	const uint32_t wq[4] = { p.q2.x, p.q2.y, p.q2.z, p.q2.w };
+	bc6h_pixel_loop<SIGNED, 2, FP>(ln, p.q0.w & 0xFFFFu, sink, [&](int i) { return prmt(wq[i >> 2], 0u, 0x4440u | (uint32_t)(i & 3)); });
 }
 
 template <bool SIGNED>

@@ -239,6 +239,17 @@ uint32_t mode_mask, uint32_t flags, const BptcTables *tab, const EmitCtx<PC> &ct
 		return decode_block<F, PATHS>(blk, mode_mask, flags, tab, px);
 }
 
+// The second half of the split BC6H decoder (bc6h_prepare -> record -> here) for the class.
+template <int F, int PC>
+__device__ __forceinline__ void pixels_px(const Bc6hPrepared &p, const EmitCtx<PC> &ctx, uint32_t (&px)[32]) {
+	if constexpr (is_tone_class(PC))
+		bc6h_pixels<false>(p, Bc6hTone8Sink<32, tone_mode(PC)>{ px, ctx.tone });
+	else if constexpr (is_tone16_class(PC))
+		bc6h_pixels<false>(p, Bc6hTone16Sink<tone_mode(PC)>{ px, ctx.tone, tone16_of_zero<tone_mode(PC)>(ctx.tone) });
+	else
+		bc6h_pixels<F == F_BPTC_SIGNED_FLOAT>(p, Bc6hHalfSink<F == F_BPTC_SIGNED_FLOAT>{ px });
+}
+
 // post_op, then hand the words that go to memory to store(words): the decoded array itself for
 // the native class, a repacked one otherwise.  ok: the block was valid (its pixels are already
 // filled with invalid_fill() otherwise).
@@ -814,8 +825,10 @@ template <int F> constexpr int sort_threads() {
 	return F == F_BPTC ? 256 : 512;
 #endif
 }
-template <int F, int PC, bool STAGE, int LAYOUT> constexpr int sort_tile() {
+template <int F, int PC, bool STAGE, int LAYOUT, bool SPLIT = false> constexpr int sort_tile() {
 	constexpr int THREADS = sort_threads<F>();
+	if (SPLIT)		// 48-byte records instead of staged pixels: two blocks per thread
+		return 2 * THREADS;
 	if (THREADS == 1024 && STAGE)
 		return stages_packed_half3<F, PC>() ? 1024 : 2048;
 	if (THREADS == 256)		// at most 56 KiB of shared memory per CTA
@@ -874,15 +887,19 @@ __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.b
 
 // whether a staged LINEAR kernel can hand its tile to the TMA unit: 16-byte rows staged as they are stored
 template <int F, int PC, bool STAGE, int LAYOUT> constexpr bool tma_capable() {
+	if (STAGE && LAYOUT == LAYOUT_LINEAR && stages_packed_half3<F, PC>())
+		return true;		// 24-byte rows: boxes of {192, 8, 4} bytes, no swizzle (the inner extent exceeds 128 bytes)
 	return STAGE && LAYOUT == LAYOUT_LINEAR && stage_words<F, PC>() == 16 && !stages_packed_half3<F, PC>() &&
 		!((PC == PC_PACK3 && FormatTraits<F>::OUT_WORDS == 16) || tone_packs3(PC));
 }
+// bytes of one stored pixel row of one block in a TMA-stored stage
+template <int F, int PC> constexpr int tma_row_bytes() { return stages_packed_half3<F, PC>() ? 24 : 16; }
 
-template <int F, int PC, bool STAGE, int LAYOUT>
+template <int F, int PC, bool STAGE, int LAYOUT, bool SPLIT = false>
 struct SortedSmem {
-	static constexpr int TB = sort_tile<F, PC, STAGE, LAYOUT>(), NB = SortTraits<F>::NUM_BINS, CAP = TB + NB * 32;
+	static constexpr int TB = sort_tile<F, PC, STAGE, LAYOUT, SPLIT>(), NB = SortTraits<F>::NUM_BINS, CAP = TB + NB * 32;
 	static constexpr int CHUNKS = stage_words<F, PC>() / 4;		// 16-byte chunks per staged tile
-	uint4 out[STAGE ? TB * CHUNKS : 1];	// staged pixels (stage_slot layout)
+	uint4 out[SPLIT ? TB * 3 : (STAGE ? TB * CHUNKS : 1)];	// staged pixels (stage_slot layout); SPLIT: prepared blocks, three planes
 	uint4 raw[2][TB];		// double-buffered compressed tile, filled by cp.async
 	uint16_t id[2][CAP];		// tile-local block index in each sorted slot, double-buffered across tiles
 	int count[2][16];		// per-mode histogram, double-buffered across tiles
@@ -916,17 +933,24 @@ __device__ __forceinline__ uint32_t raw_slot(uint32_t id) { return id ^ ((id >> 
 // TMA: the staged LINEAR tile leaves through cp.async.bulk.tensor stores issued by one thread (tmap describes the image,
 // see tma_store_3d above) instead of the cooperative copy-out: no LDS / STG / address arithmetic per block, and one
 // barrier less per tile because the store of tile t is issued at the top of tile t + 1 and runs under its sort.
-template <int F, int LAYOUT, bool STAGE, int PC, int PAD = 32, bool TMA = false>
+// SPLIT (BC6H): the decode step only PREPARES the blocks of a group -- the mode-dependent half of the decoder, down to a
+// 48-byte record that looks the same for every mode (decode_bptc_float.cuh) -- and parks the records in shared memory;
+// after the second barrier every thread takes blocks in IMAGE order, runs the mode-independent half (interpolation,
+// finish, output conversion: most of the work) and stores the pixels itself.  No lane idles in padded bins during that
+// half, the lanes of a warp hold consecutive blocks of the image (a LINEAR row of 32 blocks is one contiguous run of
+// every store instruction, whatever the row size), and what is staged is 48 bytes per block instead of 64-128.
+template <int F, int LAYOUT, bool STAGE, int PC, int PAD = 32, bool TMA = false, bool SPLIT = false>
 __global__ void __launch_bounds__(sort_threads<F>(), 1024 / sort_threads<F>())
 decode_sorted_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, uint32_t n_blocks, int width,
 int height, int wib, uint32_t mode_mask, uint32_t flags, uint32_t post_op, uint32_t *invalid_flag, uint32_t *invalid_map,
 ToneArgs tone_args, uint32_t stagger_ns, const __grid_constant__ CUtensorMap tmap) {
 	using T = FormatTraits<F>;
 	using S = SortTraits<F>;
-	using SM = SortedSmem<F, PC, STAGE, LAYOUT>;
+	using SM = SortedSmem<F, PC, STAGE, LAYOUT, SPLIT>;
 	const EmitCtx<PC> ctx(tone_args);
 	constexpr int SORT_THREADS = sort_threads<F>(), SORT_WARPS = SORT_THREADS / 32;
 	constexpr int OW = T::OUT_WORDS, NB = S::NUM_BINS, TB = SM::TB, PER = TB / SORT_THREADS, CHUNKS = SM::CHUNKS;
+	static_assert(!SPLIT || (!STAGE && !TMA && (F == F_BPTC_FLOAT || F == F_BPTC_SIGNED_FLOAT)), "SPLIT: BC6H, direct stores");
 	constexpr int CPR = CHUNKS / 4;			// 16-byte chunks per pixel row of one block
 	static_assert(T::BLOCK_WORDS == 4, "sorted kernel handles 16-byte blocks");
 	static_assert(TB % SORT_THREADS == 0 && NB <= 16, "tile / bin limits");
@@ -966,7 +990,7 @@ ToneArgs tone_args, uint32_t stagger_ns, const __grid_constant__ CUtensorMap tma
 	auto tma_store_tile = [&](uint32_t t0, uint32_t n_in_tile) {
 		uint32_t by = t0 / (uint32_t)wib, bx = t0 - by * (uint32_t)wib;
 		for (uint32_t b = 0; 64u * b < n_in_tile; b++) {
-			tma_store_3d(&tmap, &sm.out[256u * b], 0, (int)(bx >> 3), (int)(4u * by));
+			tma_store_3d(&tmap, &sm.out[64u * CHUNKS * b], 0, (int)(bx >> 3), (int)(4u * by));	// a box = 64 blocks x CHUNKS x 16 bytes
 			bx += 64u;
 			if (bx >= (uint32_t)wib) {
 				bx = 0u;
@@ -1044,6 +1068,29 @@ ToneArgs tone_args, uint32_t stagger_ns, const __grid_constant__ CUtensorMap tma
 	uint32_t tile = blockIdx.x;
 	if (tile >= n_tiles)
 		return;			// (uniform over the CTA; the launcher never starts more CTAs than tiles)
+	// the words of one finished block (block id of the tile that starts at block t0) -> image, from the thread that holds them
+	auto store_direct = [&](uint32_t t0, uint32_t id, auto &w) {
+		constexpr int OWO = post_words<OW, PC>(), CH = OWO / 4;
+		if (LAYOUT == LAYOUT_TILED) {
+			uint8_t *out = dst + (size_t)(t0 + id) * (OWO * 4);
+			if (CH % 2 == 0 && (((uintptr_t)dst) & 31u) == 0) {
+#pragma unroll
+				for (int c = 0; c + 1 < CH; c += 2)
+					st_stream_v8(out + 16 * c, w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3],
+						w[4 * c + 4], w[4 * c + 5], w[4 * c + 6], w[4 * c + 7]);
+			}
+			else {
+#pragma unroll
+				for (int c = 0; c < CH; c++)
+					st_stream_v4(out + 16 * c, w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
+			}
+		}
+		else {
+			const uint32_t i = t0 + id;
+			const uint32_t by = i / (uint32_t)wib, bx = i - by * (uint32_t)wib;
+			store_linear_rows(dst, (size_t)width * (OWO / 4), (int)bx, (int)by, height, w);
+		}
+	};
 	// Start-up stagger.  All CTAs start together and every tile costs about the same, so without it the whole chip
 	// alternates between a phase in which every CTA decodes (the memory system idles) and a phase in which every CTA
 	// drains its tile (the SMs idle at the barrier behind the drain): ncu showed 35 % of all warp samples at that one
@@ -1089,16 +1136,31 @@ ToneArgs tone_args, uint32_t stagger_ns, const __grid_constant__ CUtensorMap tma
 			const bool live = id != SLOT_EMPTY;
 			if (live) {
 				const uint4 w = sm.raw[cur][raw_slot(id)];
-				uint32_t px[OW];
-				const bool ok = decode_px<F, PC>(w, mode_mask, flags, &sm.tables, ctx, px);
+				uint32_t px[SPLIT ? 1 : OW];
+				bool ok;
+				if constexpr (SPLIT) {
+					// the mode-dependent half; the record waits in shared memory for the image-order half below
+					Bc6hPrepared p;
+					ok = bc6h_prepare<F == F_BPTC_SIGNED_FLOAT>(w, mode_mask, sm.tables, p);
+					const uint32_t slot = raw_slot(id);
+					sm.out[slot] = p.q0;
+					sm.out[TB + slot] = p.q1;
+					sm.out[2 * TB + slot] = p.q2;
+				}
+				else
+					ok = decode_px<F, PC>(w, mode_mask, flags, &sm.tables, ctx, px);
 				if (!ok) {
 					bad = true;
 					mark_invalid(invalid_map, tile0 + id);
+					if constexpr (!SPLIT) {
 #pragma unroll
-					for (int k = 0; k < OW; k++)
-						px[k] = invalid_fill(post_op);
+						for (int k = 0; k < OW; k++)
+							px[k] = invalid_fill(post_op);
+					}
 				}
-				if constexpr (STAGE && is_tone_class(PC)) {
+				if constexpr (SPLIT) {
+				}
+				else if constexpr (STAGE && is_tone_class(PC)) {
 					// the toned 8-bit pixels are what is staged; dropping X is left to the copy-out
 					uint32_t t[16];
 					tone_tile<PC>(px, t, post_op, ctx, ok);
@@ -1110,9 +1172,20 @@ ToneArgs tone_args, uint32_t stagger_ns, const __grid_constant__ CUtensorMap tma
 					apply_post_op<OW>(px, post_op);
 					uint32_t q[24];
 					repack<PC_PACK3, 32>(px, q);
+					if constexpr (TMA) {
+						// box of 64 blocks = 4 pixel rows x 8 lines of 192 bytes (eight blocks x 24 bytes), unswizzled
+						uint2 *line = reinterpret_cast<uint2 *>(sm.out) + (id >> 6) * 768u + ((id >> 3) & 7u) * 24u + (id & 7u) * 3u;
 #pragma unroll
-					for (int c = 0; c < 6; c++)
-						sm.out[stage_slot<TB, 6>(id, c)] = make_uint4(q[4 * c], q[4 * c + 1], q[4 * c + 2], q[4 * c + 3]);
+						for (int r = 0; r < 4; r++)
+#pragma unroll
+							for (int j = 0; j < 3; j++)
+								line[r * 192 + j] = make_uint2(q[6 * r + 2 * j], q[6 * r + 2 * j + 1]);
+					}
+					else {
+#pragma unroll
+						for (int c = 0; c < 6; c++)
+							sm.out[stage_slot<TB, 6>(id, c)] = make_uint4(q[4 * c], q[4 * c + 1], q[4 * c + 2], q[4 * c + 3]);
+					}
 				}
 				else if constexpr (STAGE) {
 					// staged in the native layout; a post class is applied by the copy-out below
@@ -1122,28 +1195,7 @@ ToneArgs tone_args, uint32_t stagger_ns, const __grid_constant__ CUtensorMap tma
 						sm.out[stage_slot<TB, CHUNKS, TMA>(id, c)] = make_uint4(px[4 * c], px[4 * c + 1], px[4 * c + 2], px[4 * c + 3]);
 				}
 				else {
-					emit<PC>(px, post_op, ctx, ok, [&](auto &w) {
-						constexpr int OWO = post_words<OW, PC>(), CH = OWO / 4;
-						if (LAYOUT == LAYOUT_TILED) {
-							uint8_t *out = dst + (size_t)(tile0 + id) * (OWO * 4);
-							if (CH % 2 == 0 && (((uintptr_t)dst) & 31u) == 0) {
-#pragma unroll
-								for (int c = 0; c + 1 < CH; c += 2)
-									st_stream_v8(out + 16 * c, w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3],
-										w[4 * c + 4], w[4 * c + 5], w[4 * c + 6], w[4 * c + 7]);
-							}
-							else {
-#pragma unroll
-								for (int c = 0; c < CH; c++)
-									st_stream_v4(out + 16 * c, w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
-							}
-						}
-						else {
-							const uint32_t i = tile0 + id;
-							const uint32_t by = i / (uint32_t)wib, bx = i - by * (uint32_t)wib;
-							store_linear_rows(dst, (size_t)width * (OWO / 4), (int)bx, (int)by, height, w);
-						}
-					});
+					emit<PC>(px, post_op, ctx, ok, [&](auto &w) { store_direct(tile0, id, w); });
 				}
 			}
 		}
@@ -1262,6 +1314,29 @@ ToneArgs tone_args, uint32_t stagger_ns, const __grid_constant__ CUtensorMap tma
 							out += pitch;
 						}
 					}
+				}
+			}
+		}
+		if constexpr (SPLIT) {
+			// ---- the mode-independent half, in image order: lane <-> consecutive blocks
+#pragma unroll 1
+			for (int k = 0; k < PER; k++) {
+				const uint32_t id = k * SORT_THREADS + tid;
+				if (id < n_here) {
+					const uint32_t slot = raw_slot(id);
+					Bc6hPrepared p;
+					p.q0 = sm.out[slot];
+					p.q1 = sm.out[TB + slot];
+					p.q2 = sm.out[2 * TB + slot];
+					const bool ok = bc6h_prepared_valid(p);
+					uint32_t px[OW];
+					pixels_px<F, PC>(p, ctx, px);
+					if (!ok) {
+#pragma unroll
+						for (int j = 0; j < OW; j++)
+							px[j] = invalid_fill(post_op);
+					}
+					emit<PC>(px, post_op, ctx, ok, [&](auto &w) { store_direct(tile0, id, w); });
 				}
 			}
 		}
@@ -1994,16 +2069,20 @@ static bool tma_store_enabled() {
 	static const bool v = [] { const char *e = getenv("DETEXB200_TMA_STORE"); return !(e && e[0] == '0'); }();
 	return v;
 }
-static bool make_linear_tensor_map(CUtensorMap *map, void *dst, size_t pitch, int height) {
+// row_bytes = bytes of one pixel row of one block: 16 (line of eight blocks = 128 bytes, SWIZZLE_128B) or 24 (192-byte lines,
+// no swizzle: the swizzle modes need an inner extent of at most 128 bytes)
+static bool make_linear_tensor_map(CUtensorMap *map, void *dst, size_t pitch, int height, int row_bytes) {
 	const EncodeTiledFn encode = encode_tiled_fn();
-	if (encode == nullptr || pitch % 1024 != 0 || height < 1 || (((uintptr_t)dst) & 15u) != 0)
+	const size_t line = 8 * (size_t)row_bytes;
+	if (encode == nullptr || pitch % (8 * line) != 0 || height < 1 || (((uintptr_t)dst) & 15u) != 0)
 		return false;
-	const cuuint64_t dims[3] = { 128, (cuuint64_t)(pitch / 128), (cuuint64_t)height };
-	const cuuint64_t strides[2] = { 128, (cuuint64_t)pitch };		// bytes, dimensions 1 and 2
-	const cuuint32_t box[3] = { 128, 8, 4 };			// 64 blocks x 4 pixel rows
+	const cuuint64_t dims[3] = { (cuuint64_t)line, (cuuint64_t)(pitch / line), (cuuint64_t)height };
+	const cuuint64_t strides[2] = { (cuuint64_t)line, (cuuint64_t)pitch };		// bytes, dimensions 1 and 2
+	const cuuint32_t box[3] = { (cuuint32_t)line, 8, 4 };			// 64 blocks x 4 pixel rows
 	const cuuint32_t elem[3] = { 1, 1, 1 };
 	return encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, dst, dims, strides, box, elem, CU_TENSOR_MAP_INTERLEAVE_NONE,
-		CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+		row_bytes == 16 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+		CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 // Start-up stagger of the persistent sorted kernels (see the kernel): about one tile period.  DETEXB200_STAGGER_NS
@@ -2013,10 +2092,10 @@ static uint32_t stagger_ns() {
 	return v;
 }
 
-template <int F, int LAYOUT, bool STAGE, int PC, int PAD, bool TMA>
+template <int F, int LAYOUT, bool STAGE, int PC, int PAD, bool TMA, bool SPLIT = false>
 static void launch_sorted_variant(const uint8_t *src, uint8_t *dst, uint32_t n_blocks, const DecodeArgs &a, cudaStream_t stream,
 const CUtensorMap &tmap) {
-	using SM = SortedSmem<F, PC, STAGE, LAYOUT>;
+	using SM = SortedSmem<F, PC, STAGE, LAYOUT, SPLIT>;
 	const size_t smem = sizeof(SM) + (TMA ? 1024 : 0);		// + alignment slack for the swizzled stage
 	const uint64_t tiles = ((uint64_t)n_blocks + SM::TB - 1) / SM::TB;
 	constexpr int SORT_THREADS = sort_threads<F>();
@@ -2026,10 +2105,10 @@ const CUtensorMap &tmap) {
 	int dev = 0;
 	cudaGetDevice(&dev);
 	if (!configured[dev & 63].load()) {
-		cudaFuncSetAttribute(decode_sorted_kernel<F, LAYOUT, STAGE, PC, PAD, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		cudaFuncSetAttribute(decode_sorted_kernel<F, LAYOUT, STAGE, PC, PAD, TMA, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 		configured[dev & 63].store(true);
 	}
-	decode_sorted_kernel<F, LAYOUT, STAGE, PC, PAD, TMA><<<grid, SORT_THREADS, smem, stream>>>(src, dst, n_blocks,
+	decode_sorted_kernel<F, LAYOUT, STAGE, PC, PAD, TMA, SPLIT><<<grid, SORT_THREADS, smem, stream>>>(src, dst, n_blocks,
 		a.width, a.height, a.wib, a.mode_mask, a.flags, a.post_op, a.invalid, a.invalid_map, tone_args_of(a),
 		tiles > 2 * resident ? stagger_ns() : 0u, tmap);
 }
@@ -2065,6 +2144,23 @@ const CUtensorMap &tmap) {
 
 #endif  // DETEXB200_EXPERIMENTS
 
+// Which BC6H launches take the SPLIT structure of decode_sorted_kernel: the LINEAR ones whose rows are narrower than a
+// sector pair -- the 8-bit tone classes (16- and 12-byte rows) and FLOAT_RGB16 (24-byte rows) -- which otherwise stage
+// their pixels.  Measured on B200, 4.19 M blocks, G blocks/s, staged (TMA store where it applies) -> SPLIT:
+//   -> FLOAT_RGB16 17.8 -> 20.5, -> RGBX8 20.1 -> 22.7, -> BGRA8 19.9 -> 22.4, -> RGB8 20.2 -> 22.4, hdr -> RGBX8 18.4 -> 21.3.
+// Everything else loses with it: native LINEAR 26.0 -> 22.4 (7 % more instructions, and with every warp of a CTA in the
+// arithmetic half at the same time the integer pipe throttles more: issue slots 65 % -> 59 % busy), RGBX16 LINEAR
+// 23.2 -> 20.6, TILED 26.1 -> 18.9 (32 sectors in 32 lines per store instruction, issued in bursts: mio_throttle +
+// short_scoreboard 1.2 -> 5.3 warps per issue), signed native 22.3 -> 18.2.  DETEXB200_BC6H_SPLIT=1 / 0 in the
+// environment forces it on / off for every BC6H launch (A/B runs, and the parity tests run under both).
+template <int F, int PC>
+static bool bc6h_split_selected(int layout) {
+	static const int forced = [] { const char *e = getenv("DETEXB200_BC6H_SPLIT"); return e ? (e[0] == '1' ? 1 : 0) : -1; }();
+	if (forced >= 0)
+		return forced == 1;
+	return layout == LAYOUT_LINEAR && F == F_BPTC_FLOAT && (is_tone_class(PC) || stages_packed_half3<F, PC>());
+}
+
 // One instantiation of the sorted kernel: opt in to > 48 KiB of dynamic shared memory once per device, then launch.
 // Staged LINEAR tiles of 16-byte rows leave through the TMA unit when the image allows it (whole boxes of 64 blocks per
 // block row, 16-byte aligned base); otherwise, and for the tiles that are repacked on the way out, the CTA copies them out.
@@ -2081,10 +2177,10 @@ static void launch_sorted(const uint8_t *src, uint8_t *dst, uint32_t n_blocks, c
 	}
 #endif
 	if constexpr (tma_capable<F, PC, STAGE, LAYOUT>()) {
-		constexpr int ROW_BYTES = 16;
+		constexpr int ROW_BYTES = tma_row_bytes<F, PC>();
 		// whole boxes of 64 blocks per block row (pixel rows beyond the image height are clipped by the hardware)
 		if (tma_store_enabled() && a.wib % 64 == 0 && a.height > 4 * (a.hib - 1) &&
-		    make_linear_tensor_map(&tmap, dst, (size_t)a.wib * ROW_BYTES, a.height)) {
+		    make_linear_tensor_map(&tmap, dst, (size_t)a.wib * ROW_BYTES, a.height, ROW_BYTES)) {
 #ifdef DETEXB200_EXPERIMENTS
 			if (stream_kernel_enabled()) {
 				launch_stream<F, LAYOUT, true, PC>(src, dst, n_blocks, a, stream, tmap);
@@ -2155,6 +2251,18 @@ static cudaError_t launch_format(const DecodeArgs &a, cudaStream_t stream) {
 				}
 			}
 #endif
+			if constexpr (F == F_BPTC_FLOAT || F == F_BPTC_SIGNED_FLOAT) {
+				if (bc6h_split_selected<F, PC>(a.layout) && (a.layout == LAYOUT_LINEAR || PC != PC_NATIVE || (tiled_direct() && aligned32))) {
+					CUtensorMap none;
+					memset(&none, 0, sizeof(none));
+					if (a.layout == LAYOUT_TILED)
+						launch_sorted_variant<F, LAYOUT_TILED, false, PC, 1, false, true>(src, dst, (uint32_t)n_blocks, a, stream, none);
+					else
+						launch_sorted_variant<F, LAYOUT_LINEAR, false, PC, 1, false, true>(src, dst, (uint32_t)n_blocks, a, stream, none);
+					count_launch();
+					return cudaGetLastError();
+				}
+			}
 			// LINEAR rows of 16 bytes or less per block are half sectors when written by lanes in sorted
 			// order: those tiles (BC7, the toned BC6H classes) are staged and copied out in image order
 			// (measured for the toned classes: staged 20.2 G blocks/s, direct 15.3)

@@ -25,6 +25,22 @@ static void tables_init() {
 	g_tab_ready = true;
 }
 
+template <bool SIGNED>
+static bool bc6h_split(const uint4 &w, uint32_t (&px)[32]) {
+	Bc6hPrepared p;
+	const bool ok = bc6h_prepare<SIGNED>(w, 0xFFFFFFFFu, g_tab.packed, p);
+	if (ok != bc6h_prepared_valid(p))
+		abort();
+	/* the record travels through memory between the halves */
+	uint8_t bytes[48];
+	memcpy(bytes, &p, 48);
+	Bc6hPrepared r;
+	memcpy(&r, bytes, 48);
+	if (ok)
+		bc6h_pixels<SIGNED>(r, Bc6hHalfSink<SIGNED>{ px });
+	return ok;
+}
+
 extern "C" {
 
 /* the variant the host picks (api.cu): plain, or HDR range when the range is not [0, 1] */
@@ -125,15 +141,20 @@ uint8_t *valid) {
 }
 
 /* BC6H: n blocks -> n tiles of 16 (SIGNED_)FLOAT_RGBX16 pixels (128 bytes, TILED); valid[i] = 0 and a
-   zero tile for an invalid block */
-int emu_bc6h_decode(const uint8_t *blocks, int n, int is_signed, uint8_t *pixels, uint8_t *valid) {
+   zero tile for an invalid block.  split != 0: through the two halves the SPLIT kernels run (bc6h_prepare ->
+   48-byte record -> bc6h_pixels) instead of the one-piece decoder */
+int emu_bc6h_decode(const uint8_t *blocks, int n, int is_signed, int split, uint8_t *pixels, uint8_t *valid) {
 	tables_init();
 	for (int i = 0; i < n; i++) {
 		uint4 w;
 		memcpy(&w, blocks + 16 * (size_t)i, 16);
 		uint32_t px[32];
-		const bool ok = is_signed ? decode_bptc_float<true>(w, 0xFFFFFFFFu, 0u, g_tab.packed, px)
-					  : decode_bptc_float<false>(w, 0xFFFFFFFFu, 0u, g_tab.packed, px);
+		bool ok;
+		if (split)
+			ok = is_signed ? bc6h_split<true>(w, px) : bc6h_split<false>(w, px);
+		else
+			ok = is_signed ? decode_bptc_float<true>(w, 0xFFFFFFFFu, 0u, g_tab.packed, px)
+				       : decode_bptc_float<false>(w, 0xFFFFFFFFu, 0u, g_tab.packed, px);
 		if (!ok)
 			memset(px, 0, sizeof px);
 		memcpy(pixels + 128 * (size_t)i, px, 128);

@@ -24,7 +24,7 @@ def emu(tmp_path_factory):
     lib = C.CDLL(so)
     lib.emu_bc7_decode.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.emu_bc7_decode.restype = C.c_int
-    lib.emu_bc6h_decode.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    lib.emu_bc6h_decode.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     lib.emu_bc6h_decode.restype = C.c_int
     return lib
 
@@ -102,16 +102,18 @@ def test_bc7_emulated_extreme_endpoints(emu, cpu):
     assert np.array_equal(got, want)
 
 
+@pytest.mark.parametrize("split", [0, 1])
 @pytest.mark.parametrize("fmt", ["BPTC_FLOAT", "BPTC_SIGNED_FLOAT"])
-def test_bc6h_emulated_decoder_matches_oracle(emu, cpu, fmt):
+def test_bc6h_emulated_decoder_matches_oracle(emu, cpu, fmt, split):
     """BC6H (decode_bptc_float.cuh) on the CPU: uniform blocks (12.5 % invalid), every forced mode,
-    every partition set, extreme payloads"""
+    every partition set, extreme payloads.  split = 1: the decoder in the two halves the SPLIT kernels run
+    (mode-dependent half -> 48-byte record -> mode-independent half)"""
     def check(b):
         n = b.size // 16
         got = np.empty(n * 128, dtype=np.uint8)
         valid = np.empty(n, dtype=np.uint8)
         b = np.ascontiguousarray(b)
-        assert emu.emu_bc6h_decode(b.ctypes.data, n, int(fmt == "BPTC_SIGNED_FLOAT"), got.ctypes.data, valid.ctypes.data) == 0
+        assert emu.emu_bc6h_decode(b.ctypes.data, n, int(fmt == "BPTC_SIGNED_FLOAT"), split, got.ctypes.data, valid.ctypes.data) == 0
         want, ok, _ = H.cpu_decode(cpu, fmt, b, 4 * n, 4, linear=False)
         assert np.array_equal(got, want)
         assert bool(valid.all()) == ok

@@ -361,6 +361,18 @@ def test_bc7_flow_kernel():
     assert r.returncode == 0 and r.stdout.strip().startswith("OK"), r.stdout[-2000:] + r.stderr[-4000:]
 
 
+@pytest.mark.parametrize("split", ["0", "1"])
+def test_bc6h_kernel_structures(split):
+    """BC6H runs one of two structures of the mode-sorted kernel depending on the target format (kernels.cu,
+    bc6h_split_selected); DETEXB200_BC6H_SPLIT forces one for every BC6H launch of a process.  Both are checked
+    against the CPU checker in a child process (tests/bc6h_structure_check.py)."""
+    here = os.path.dirname(os.path.abspath(__file__))
+    env = dict(os.environ, DETEXB200_BC6H_SPLIT=split)
+    r = subprocess.run([sys.executable, os.path.join(here, "bc6h_structure_check.py")], env=env, capture_output=True,
+                       text=True, timeout=900)
+    assert r.returncode == 0 and r.stdout.strip().startswith("OK"), r.stdout[-2000:] + r.stderr[-4000:]
+
+
 # ---- round 2: narrow images, pageable / pinned callers, threads, device sets, configs[4] at full size ----------
 def test_linear_image_narrower_than_its_block_grid(cpu):
     """width may be anything in ((wib - 1) * 4, wib * 4] for the reference (texture.c:133-136 clips the last
