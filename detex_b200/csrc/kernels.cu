@@ -757,6 +757,24 @@ ToneArgs tone_args) {
 // inside decode_block<F> becomes warp-uniform.  Results are stored straight to each block's own
 // place (16-byte row segments; L2 merges the half sectors of horizontally adjacent blocks).
 template <int F> struct SortTraits { static constexpr bool ENABLED = false; static constexpr int NUM_BINS = 1; };
+// Bin of BC7 mode m = nibble m.  The sorted groups of a tile are dealt round-robin to the warps of the CTA, so with
+// equally frequent modes (distribution M: block i has mode i % 8) the bin ORDER decides which modes meet in one warp:
+// eight warps and a 512-block tile give warp w one group of bin w / 2 and one of bin w / 2 + 4, a 1024-block tile the
+// even or the odd bins.  The modes cost between 121 and 173 us per 8.4 M blocks (profiles/r02_sweep_bc7_single_modes.log);
+// in mode order the heaviest warp carries modes 0 + 4 = 308 against a mean of 278, in the order m0 m1 m3 m2 | m5 m6 m4 m7
+// (the best of the 8! orders for both tile sizes) 294.  -DDETEXB200_BC7_BIN_NIBBLES=0x76543210u builds the mode order.
+#ifndef DETEXB200_BC7_BIN_NIBBLES
+#define DETEXB200_BC7_BIN_NIBBLES 0x75462310u
+#endif
+// the inverse: mode of a BC7 bin (bin 8 = invalid stays 8)
+__host__ __device__ constexpr int bc7_mode_of_bin(int bin) {
+	for (int m = 0; m < 8; m++)
+		if ((int)((DETEXB200_BC7_BIN_NIBBLES >> (4 * m)) & 7u) == bin)
+			return m;
+	return 8;
+}
+static_assert(bc7_mode_of_bin(0) + bc7_mode_of_bin(1) + bc7_mode_of_bin(2) + bc7_mode_of_bin(3) + bc7_mode_of_bin(4) +
+	bc7_mode_of_bin(5) + bc7_mode_of_bin(6) + bc7_mode_of_bin(7) == 28, "DETEXB200_BC7_BIN_NIBBLES must be a permutation of 0-7");
 template <> struct SortTraits<F_BPTC> {
 	static constexpr bool ENABLED = true;
 	static constexpr int NUM_BINS = 9;		// modes 0-7 + invalid
@@ -769,7 +787,7 @@ template <> struct SortTraits<F_BPTC> {
 		const int m = __ffs((int)(b.x & 0xFFu)) - 1;
 		const bool ok = m >= 0 && ((mode_mask >> m) & 1u) && !(m >= 4 && (flags & FLAG_OPAQUE_ONLY)) &&
 			!(m < 4 && (flags & FLAG_NON_OPAQUE_ONLY));
-		return ok ? m : 8;
+		return ok ? (int)((DETEXB200_BC7_BIN_NIBBLES >> (4 * m)) & 7u) : 8;
 	}
 };
 struct SortTraitsBc6h {
@@ -885,6 +903,18 @@ __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk
 // the shared-memory source of every committed store has been read (the buffer may be overwritten)
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 
+// mbarrier with one expected arrival per phase, in the CTA's shared memory
+__device__ __forceinline__ void mbar_init1(void *bar) {
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(void *bar) {
+	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(void *bar, uint32_t parity) {
+	asm volatile("{\n\t.reg .pred p;\n\tMBAR_WAIT:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra MBAR_DONE;\n\t"
+		"bra MBAR_WAIT;\n\tMBAR_DONE:\n\t}" :: "r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+}
+
 // whether a staged LINEAR kernel can hand its tile to the TMA unit: 16-byte rows staged as they are stored
 template <int F, int PC, bool STAGE, int LAYOUT> constexpr bool tma_capable() {
 	if (STAGE && LAYOUT == LAYOUT_LINEAR && stages_packed_half3<F, PC>())
@@ -903,6 +933,7 @@ struct SortedSmem {
 	uint4 raw[2][TB];		// double-buffered compressed tile, filled by cp.async
 	uint16_t id[2][CAP];		// tile-local block index in each sorted slot, double-buffered across tiles
 	int count[2][16];		// per-mode histogram, double-buffered across tiles
+	unsigned long long stage_bar;	// mbarrier: the TMA unit has read the staged tile (TMA variants)
 	uint8_t bin_lut[256];		// byte 0 of a block -> bin under this launch's mode_mask / flags
 	BptcTables tables;
 };
@@ -962,6 +993,8 @@ ToneArgs tone_args, uint32_t stagger_ns, const __grid_constant__ CUtensorMap tma
 	const uint32_t n_tiles = (n_blocks + TB - 1) / TB;
 	if (tid < 32)
 		(&sm.count[0][0])[tid] = 0;
+	if (TMA && tid == 0)
+		mbar_init1(&sm.stage_bar);
 	bptc_tables_load(sm.tables);
 	// the bin of a block depends on its first byte only (BC7: lowest set bit; BC6H: 2 / 5 mode bits)
 	for (int v = tid; v < 256; v += SORT_THREADS) {
@@ -1114,6 +1147,26 @@ ToneArgs tone_args, uint32_t stagger_ns, const __grid_constant__ CUtensorMap tma
 	asm volatile("cp.async.commit_group;" ::: "memory");
 	__syncthreads();		// histogram of the first tile complete
 	int total = scatter(0);
+	// TMA variants: the store of tile t is issued after B2 and the TMA unit needs about a microsecond to read the stage.
+	// Nobody waits for that at a CTA barrier (ncu, round 2, BC7 M LINEAR, with thread 0 waiting before B1: 23 % of all
+	// warp samples sat at B1): every warp first decodes a group of tile t + 1 into registers; thread 0 then collects the
+	// bulk group -- normally complete by then -- and arrives on an mbarrier, which the others pass before their first
+	// write to the stage.
+	bool drain_pending = false;
+	uint32_t drain_parity = 0u;
+	auto await_drain = [&]() {
+#ifdef DETEXB200_TMA_EARLY_WAIT
+		(void)drain_parity;
+#else
+		if (tid == 0) {
+			tma_store_wait_read();
+			mbar_arrive(&sm.stage_bar);
+		}
+		mbar_wait(&sm.stage_bar, drain_parity);
+		drain_parity ^= 1u;
+#endif
+		drain_pending = false;
+	};
 	for (int cur = 0;; cur ^= 1) {
 		const uint32_t tile0 = tile * TB, n_here = min((uint32_t)TB, n_blocks - tile0);
 		const uint32_t next = tile + gridDim.x;
@@ -1134,10 +1187,10 @@ ToneArgs tone_args, uint32_t stagger_ns, const __grid_constant__ CUtensorMap tma
 			g_next += SORT_WARPS * 32;
 			id_next = g_next + (PAD < 32 ? lane : 0) < total ? sm.id[cur][g_next + lane] : SLOT_EMPTY;
 			const bool live = id != SLOT_EMPTY;
+			uint32_t px[SPLIT ? 1 : OW];
+			bool ok = true;
 			if (live) {
 				const uint4 w = sm.raw[cur][raw_slot(id)];
-				uint32_t px[SPLIT ? 1 : OW];
-				bool ok;
 				if constexpr (SPLIT) {
 					// the mode-dependent half; the record waits in shared memory for the image-order half below
 					Bc6hPrepared p;
@@ -1158,6 +1211,12 @@ ToneArgs tone_args, uint32_t stagger_ns, const __grid_constant__ CUtensorMap tma
 							px[k] = invalid_fill(post_op);
 					}
 				}
+			}
+			if constexpr (TMA) {
+				if (drain_pending)
+					await_drain();		// (warp-uniform) the pixels are in registers; the stage is written next
+			}
+			if (live) {
 				if constexpr (SPLIT) {
 				}
 				else if constexpr (STAGE && is_tone_class(PC)) {
@@ -1198,6 +1257,10 @@ ToneArgs tone_args, uint32_t stagger_ns, const __grid_constant__ CUtensorMap tma
 					emit<PC>(px, post_op, ctx, ok, [&](auto &w) { store_direct(tile0, id, w); });
 				}
 			}
+		}
+		if constexpr (TMA) {
+			if (drain_pending)
+				await_drain();		// (a warp without a group in this tile)
 		}
 		if (has_next) {
 			asm volatile("cp.async.wait_group 0;" ::: "memory");	// my copies of the next tile have landed
@@ -1343,8 +1406,17 @@ ToneArgs tone_args, uint32_t stagger_ns, const __grid_constant__ CUtensorMap tma
 		if (has_next)
 			total = scatter(cur ^ 1);
 		if constexpr (TMA) {
-			if (tid == 0)
-				tma_store_wait_read();	// the stage may be overwritten; shared memory outlives the reads
+#ifdef DETEXB200_TMA_EARLY_WAIT
+			const bool wait_now = true;		// A/B: thread 0 waits for the TMA unit before B1
+#else
+			const bool wait_now = !has_next;	// (shared memory must outlive the reads of the last tile)
+#endif
+			if (wait_now) {
+				if (tid == 0)
+					tma_store_wait_read();	// the stage may be overwritten
+			}
+			else
+				drain_pending = true;
 		}
 		if (!has_next)
 			break;
@@ -1880,7 +1952,12 @@ int height, int wib, uint32_t mode_mask, uint32_t flags, uint32_t post_op, uint3
 					flow_wait(&sm.out_cnt[(j - 2) & 3], FLOW_OUT * ((j - 2) / 4 + 1), &sm.error);
 				const uint32_t id = sm.id[j & 1][g + lane];
 				// the group's bin from its position: number of bins that start at or before g (uniform)
-				const int mode = __popc(__ballot_sync(0xFFFFFFFFu, lane < NB && start_cur <= g)) - 1;
+				const int bin_g = __popc(__ballot_sync(0xFFFFFFFFu, lane < NB && start_cur <= g)) - 1;
+				int mode = 8;
+#pragma unroll
+				for (int b = 0; b < 8; b++)
+					if (bin_g == b)
+						mode = bc7_mode_of_bin(b);
 				if (id != SLOT_EMPTY) {
 					uint4 *raw_dec = sm.raw[j & 3];
 					const uint32_t rs = raw_slot(id);
