@@ -214,70 +214,92 @@ __device__ __forceinline__ int stored_components(uint32_t pf) {
 	return (1 + (int)((pf & 0xF00u) >> 8)) >> (pf & 0x3u);
 }
 
-// One step of the chain on the component registers.  sf / tf: formats before and after.
-__device__ __forceinline__ void apply_step(uint32_t op, uint32_t sf, uint32_t tf, uint32_t (&c)[4], const ConvertProgram &p) {
+// One step of the chain on the component registers of K pixels.  sf / tf: formats before and after.  The operation is
+// the same for every pixel of a launch: the switch is taken once per K pixels, the bodies are unrolled over them.
+template <int K>
+__device__ __forceinline__ void apply_step_k(uint32_t op, uint32_t sf, uint32_t tf, uint32_t (&px)[K][4], const ConvertProgram &p) {
 	const int n_in = stored_components(sf), n_out = stored_components(tf);
 	const uint32_t cs_out = 1u << (tf & 3u);
 	const uint32_t one = cs_out == 1u ? 0xFFu : (cs_out == 2u ? ((tf & 0x2000u) ? 0x3C00u : 0xFFFFu) : 0x3F800000u);
+#define DETEX_EACH_PIXEL _Pragma("unroll") for (int k_ = 0; k_ < K; k_++)
 	switch (op) {
 	case ST_KEEP:
 		break;
-	case ST_SWAP_RB: {
-		const uint32_t t = c[0];
-		c[0] = c[2];
-		c[2] = t;
+	case ST_SWAP_RB:
+		DETEX_EACH_PIXEL {
+			uint32_t (&c)[4] = px[k_];
+			const uint32_t t = c[0];
+			c[0] = c[2];
+			c[2] = t;
+		}
 		break;
-	}
-	case ST_RGB_TO_BGRX: {					// convert.c:73-86
-		const uint32_t t = c[0];
-		c[0] = c[2];
-		c[2] = t;
-		c[3] = 0xFFu;
+	case ST_RGB_TO_BGRX:					// convert.c:73-86
+		DETEX_EACH_PIXEL {
+			uint32_t (&c)[4] = px[k_];
+			const uint32_t t = c[0];
+			c[0] = c[2];
+			c[2] = t;
+			c[3] = 0xFFu;
+		}
 		break;
-	}
 	case ST_FLIP_SIGN: {					// convert.c:89-186: -128 / +128, -32768 / +32768
 		const uint32_t top = (sf & 1u) ? 0x8000u : 0x80u;
+		DETEX_EACH_PIXEL {
 #pragma unroll
-		for (int j = 0; j < 4; j++)
-			c[j] ^= top;
+			for (int j = 0; j < 4; j++)
+				px[k_][j] ^= top;
+		}
 		break;
 	}
 	case ST_PAD:						// convert.c:237-260, :660-669, :692-698, :719-735
+		DETEX_EACH_PIXEL {
 #pragma unroll
-		for (int j = 0; j < 4; j++)
-			if (j >= n_in)
-				c[j] = j == 3 ? one : 0u;
+			for (int j = 0; j < 4; j++)
+				if (j >= n_in)
+					px[k_][j] = j == 3 ? one : 0u;
+		}
 		break;
 	case ST_NARROW:						// convert.c:263-331
+		DETEX_EACH_PIXEL {
+			uint32_t (&c)[4] = px[k_];
 #pragma unroll
-		for (int j = 0; j < 4; j++)
-			c[j] = ((c[j] + 127u) * 255u) / 65535u;		// 16-bit inputs only; kernels.cu has the cheap form
-		if (n_out == 4 && !(tf & 0x4u))
-			c[3] = 0xFFu;				// RGBX16 -> RGBX8 writes alpha 0xFF (:312-316)
+			for (int j = 0; j < 4; j++)
+				c[j] = ((c[j] + 127u) * 255u) / 65535u;		// 16-bit inputs only; kernels.cu has the cheap form
+			if (n_out == 4 && !(tf & 0x4u))
+				c[3] = 0xFFu;				// RGBX16 -> RGBX8 writes alpha 0xFF (:312-316)
+		}
 		break;
 	case ST_WIDEN:						// convert.c:333-404
+		DETEX_EACH_PIXEL {
+			uint32_t (&c)[4] = px[k_];
 #pragma unroll
-		for (int j = 0; j < 4; j++)
-			c[j] = c[j] * 257u;			// v * 65535 / 255
-		if (n_out == 4 && !(tf & 0x4u))
-			c[3] = 0xFFFFu;				// RGBX8 -> RGBX16 writes 0xFFFF (:384)
+			for (int j = 0; j < 4; j++)
+				c[j] = c[j] * 257u;			// v * 65535 / 255
+			if (n_out == 4 && !(tf & 0x4u))
+				c[3] = 0xFFFFu;				// RGBX8 -> RGBX16 writes 0xFFFF (:384)
+		}
 		break;
 	case ST_INT_TO_HALF: {					// convert.c:473-586
 		// RGBX16 reads its components through int16_t (:565-567) and writes 1.0 into X (:574)
 		const bool quirk_signed = n_in == 4;
+		DETEX_EACH_PIXEL {
+			uint32_t (&c)[4] = px[k_];
 #pragma unroll
-		for (int j = 0; j < 4; j++) {
-			const float v = quirk_signed ? (float)(int)(short)(unsigned short)c[j] : (float)c[j];
-			c[j] = float_bits_to_half(__float_as_uint(__fmul_rn(v, 1.0f / 65535.0f)));
+			for (int j = 0; j < 4; j++) {
+				const float v = quirk_signed ? (float)(int)(short)(unsigned short)c[j] : (float)c[j];
+				c[j] = float_bits_to_half(__float_as_uint(__fmul_rn(v, 1.0f / 65535.0f)));
+			}
+			if (quirk_signed)
+				c[3] = 0x3C00u;
 		}
-		if (quirk_signed)
-			c[3] = 0x3C00u;
 		break;
 	}
 	case ST_HALF_TO_INT:					// convert.c:589-608 -> half-float.c:304-312
+		DETEX_EACH_PIXEL {
 #pragma unroll
-		for (int j = 0; j < 4; j++)
-			c[j] = normalized_float_to_u16(__uint_as_float(half_to_float_bits(c[j])));
+			for (int j = 0; j < 4; j++)
+				px[k_][j] = normalized_float_to_u16(__uint_as_float(half_to_float_bits(px[k_][j])));
+		}
 		break;
 	case ST_HALF_HDR_TO_INT: case ST_FLOAT_HDR: {		// hdr.c:119-214
 		const bool half_in = op == ST_HALF_HDR_TO_INT;
@@ -292,39 +314,58 @@ __device__ __forceinline__ void apply_step(uint32_t op, uint32_t sf, uint32_t tf
 			hi = signed_pow(hi, e);
 			factor = 1.0f / (hi - lo);
 		}
+		DETEX_EACH_PIXEL {
+			uint32_t (&c)[4] = px[k_];
 #pragma unroll
-		for (int j = 0; j < 4; j++) {
-			float f = half_in ? __uint_as_float(half_to_float_bits(c[j])) : __uint_as_float(c[j]);
-			if (p.gamma == 1.0f) {
-				if (!identity)
-					f = __fmul_rd(__fsub_rd(f, lo), factor);
+			for (int j = 0; j < 4; j++) {
+				float f = half_in ? __uint_as_float(half_to_float_bits(c[j])) : __uint_as_float(c[j]);
+				if (p.gamma == 1.0f) {
+					if (!identity)
+						f = __fmul_rd(__fsub_rd(f, lo), factor);
+				}
+				else {
+					// the half path corrects every value (table, hdr.c:40-50); the float path only rescales
+					if (half_in)
+						f = signed_pow(f, e);
+					f = (f - lo) * factor;
+				}
+				c[j] = half_in ? normalized_float_to_u16(f) : __float_as_uint(clamp01(f));
 			}
-			else {
-				// the half path corrects every value (table, hdr.c:40-50); the float path only rescales
-				if (half_in)
-					f = signed_pow(f, e);
-				f = (f - lo) * factor;
-			}
-			c[j] = half_in ? normalized_float_to_u16(f) : __float_as_uint(clamp01(f));
 		}
 		break;
 	}
 	case ST_FLOAT_TO_HALF:					// convert.c:407-425
+		DETEX_EACH_PIXEL {
 #pragma unroll
-		for (int j = 0; j < 4; j++)
-			c[j] = float_bits_to_half(c[j]);
+			for (int j = 0; j < 4; j++)
+				px[k_][j] = float_bits_to_half(px[k_][j]);
+		}
 		break;
 	case ST_FLOAT_TO_INT:					// convert.c:428-446 -> half-float.c:315-322
+		DETEX_EACH_PIXEL {
 #pragma unroll
-		for (int j = 0; j < 4; j++)
-			c[j] = normalized_float_to_u16(__uint_as_float(c[j]));
+			for (int j = 0; j < 4; j++)
+				px[k_][j] = normalized_float_to_u16(__uint_as_float(px[k_][j]));
+		}
 		break;
 	case ST_HALF_TO_FLOAT:					// convert.c:449-467
+		DETEX_EACH_PIXEL {
 #pragma unroll
-		for (int j = 0; j < 4; j++)
-			c[j] = half_to_float_bits(c[j]);
+			for (int j = 0; j < 4; j++)
+				px[k_][j] = half_to_float_bits(px[k_][j]);
+		}
 		break;
 	}
+#undef DETEX_EACH_PIXEL
+}
+
+// one pixel
+__device__ __forceinline__ void apply_step(uint32_t op, uint32_t sf, uint32_t tf, uint32_t (&c)[4], const ConvertProgram &p) {
+	uint32_t px[1][4] = { { c[0], c[1], c[2], c[3] } };
+	apply_step_k<1>(op, sf, tf, px, p);
+#pragma unroll
+	for (int j = 0; j < 4; j++)
+		c[j] = px[0][j];
 }
 
 

@@ -2087,7 +2087,7 @@ uint64_t launch_count() { return g_launches.load(); }
 void count_launch() { g_launches.fetch_add(1); }
 
 static std::atomic<int> g_sm_count{0};
-static int sm_count() {
+int sm_count() {
 	int n = g_sm_count.load();
 	if (n == 0) {
 		int dev = 0;

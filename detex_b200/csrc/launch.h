@@ -60,5 +60,6 @@ void set_error_text(const char *text);
 
 uint64_t launch_count();
 void count_launch();
+int sm_count();		// multiprocessors of the current device (148 on B200)
 
 }  // namespace detexb200
