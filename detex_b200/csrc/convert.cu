@@ -8,8 +8,10 @@
 //     operation code per entry instead of a function pointer;
 //   * the search is restated on the host (plan());
 //   * ONE kernel executes the whole chain: a CTA stages a tile of source pixels in shared memory
-//     with coalesced loads, each thread takes pixels apart into up to four component registers,
-//     applies the steps in order, and the converted tile leaves through shared memory again.
+//     (cp.async, double-buffered), each thread takes pixels apart into up to four component registers,
+//     applies the steps in order, and the converted tile leaves through shared memory again;
+//   * chains that only shuffle 8-bit components are folded into one byte permutation on the host and
+//     run register to register (byte_map_kernel).
 // No intermediate buffer ever reaches HBM.  All integer steps are bit-exact; the float <-> half
 // steps follow the reference's integer bit manipulation (half-float.c:93-275) and its
 // round-down float -> uint16 (half-float.c:304-322) with explicit rounding-mode intrinsics.
